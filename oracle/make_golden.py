@@ -1,0 +1,70 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+Weights and inputs are regenerated from seeds on the consumer side (oracle/weights.py), so
+the fixtures hold outputs only: x_hat, likelihoods, the rANS-bound symbol / index lists
+captured from the reference's compress(), net_decoder_forward's output, and a few
+intermediate tensors (y, z) that localise a mismatch.
+"""
+import os
+
+import numpy as np
+import torch
+
+from oracle import ref_loader, weights
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name, B, H, W, seed, y_gain, sigma_spread, vbr levels for compress, vbr level for forward
+CASES = [
+    ("MLICPP_S", 2, 64, 128, 1234, 16.0, 6.0, None, None),
+    ("MLICPP_L", 1, 64, 128, 1234, 16.0, 6.0, None, None),
+    ("MLICPP_M_SMALL_DEC", 1, 64, 128, 1234, 16.0, 6.0, None, None),
+    ("MLICPP_S_VBR", 1, 64, 128, 1234, 16.0, 6.0, range(6), 2),
+    ("MLICPP_L_VBR", 1, 64, 64, 1234, 16.0, 6.0, range(6), 1),
+]
+
+
+def case_file(name, B, H, W):
+    return os.path.join(OUT, f"{name}_b{B}_{H}x{W}.npz")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for name, B, H, W, seed, yg, ss, levels, fwd_level in CASES:
+        net = ref_loader.get_reference_model(name)
+        sd = weights.seeded_state_dict(net.state_dict(), seed, y_gain=yg, sigma_spread=ss)
+        net.load_state_dict(sd)
+        net.update(force=True)
+        x = weights.synthetic_image(B, H, W, seed=2024)
+        rec = {"meta": np.array([B, H, W, seed], dtype=np.int64), "y_gain": np.float32(yg),
+               "sigma_spread": np.float32(ss)}
+        with torch.no_grad():
+            out = net(x) if levels is None else net(x, stage=2, s=fwd_level)
+            rec["x_hat"] = out["x_hat"].numpy()
+            rec["y_likelihoods"] = out["likelihoods"]["y_likelihoods"].numpy()
+            rec["z_likelihoods"] = out["likelihoods"]["z_likelihoods"].numpy()
+            rec["y"] = net.g_a(x).numpy()
+            rec["z"] = net.h_a(net.g_a(x)).numpy()
+            if levels is None:
+                net.compress(x)
+                s_, i_ = ref_loader.recorded_symbols()
+                rec["symbols"] = np.asarray(s_, dtype=np.int32)
+                rec["indexes"] = np.asarray(i_, dtype=np.int32)
+            else:
+                rec["fwd_level"] = np.int64(fwd_level)
+                for lv in levels:
+                    net.compress(x, stage=2, s=lv)
+                    s_, i_ = ref_loader.recorded_symbols()
+                    rec[f"symbols_s{lv}"] = np.asarray(s_, dtype=np.int32)
+                    rec[f"indexes_s{lv}"] = np.asarray(i_, dtype=np.int32)
+            rec["decoder_x_hat"] = net.net_decoder_forward(x).numpy()
+        path = case_file(name, B, H, W)
+        np.savez_compressed(path, **rec)
+        print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB",
+              {k: (v.shape if hasattr(v, 'shape') else v) for k, v in rec.items() if k.startswith(('sym', 'ind'))})
+
+
+if __name__ == "__main__":
+    main()
