@@ -1,0 +1,92 @@
+/* mlic_b200 -- C ABI of the B200-native MLIC++ network-forward engine.
+ *
+ * The reference (LuZWCHA/MLIC) has no FFI: its seam is the Python model object returned by
+ * models.get_model(name) (MLIC++/models/model_loader.py:4-18).  This header is what a binding for
+ * that seam calls; mlic_b200/models.py is the ctypes binding and mirrors the reference classes.
+ * Each entry point cites the reference method it replaces (paths relative to /root/reference/MLIC++).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * status otherwise, with a human-readable message available from mlic_last_error().  All image /
+ * likelihood tensors are fp32 NCHW, exactly the reference's layout.  "dev" pointers are CUDA device
+ * pointers on the engine's device; the caller owns every buffer.  No entry point synchronises the
+ * stream unless it says so.  An engine is not re-entrant: use one engine per host thread / stream.
+ */
+#ifndef MLIC_B200_H_
+#define MLIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlic_engine mlic_engine;
+
+enum { MLIC_KIND_BASE = 0, MLIC_KIND_SD = 1, MLIC_KIND_VBR = 2 };   /* MLICPlusPlus / ...SD / ...Vbr */
+enum { MLIC_PREC_FP32 = 0, MLIC_PREC_BF16 = 1 };                    /* validation mode / fast mode   */
+enum { MLIC_MODE_FORWARD = 0, MLIC_MODE_COMPRESS = 1, MLIC_MODE_DECODER = 2 };
+
+/* Buffers of one call.  Unused outputs may be NULL.  B images of H x W (multiples of 64). */
+typedef struct {
+    const float* x;          /* in : [B,3,H,W]                      (forward, compress)                          */
+    float* x_hat;            /* out: [B,3,H,W]                                                                    */
+    float* y_likelihoods;    /* out: [B,M,H/16,W/16]                (forward)                                     */
+    float* z_likelihoods;    /* out: [B,N,H/64,W/64]                (forward)                                     */
+    int32_t* symbols;        /* out: [2*slices][B,C,H/16,W/32] flat, order A0,N0,A1,N1,...   (compress)           */
+    int32_t* indexes;        /* out: same shape: CDF indexes into the 64-entry scale table   (compress)           */
+    int32_t* z_symbols;      /* out: [B,N,H/64,W/64] round(z - median)                       (compress)           */
+    float* y;                /* out (optional tap): g_a output [B,M,H/16,W/16]                                    */
+    float* y_hat;            /* out (optional tap): quantised latent after LRP [B,M,H/16,W/16]                    */
+    double* rd_sums;         /* out (optional, forward): [2] = { sum log2(likelihoods), sum (x - x_hat)^2 }       */
+} mlic_buffers;
+
+/* Engine for one model configuration (config/config.py:19-62): N, M, slice_num and the class kind. */
+int mlic_engine_create(int N, int M, int slice_num, int kind, mlic_engine** out);
+void mlic_engine_destroy(mlic_engine* e);
+
+/* One state_dict entry, reference name and shape (host fp32, copied).  Replaces load_state_dict
+ * (models/mlicpp.py:461-468). */
+int mlic_engine_set_param(mlic_engine* e, const char* name, const float* host_data, const int64_t* shape, int ndim);
+
+/* Packs the weights onto the current CUDA device (NCHW fp32 -> GEMM layouts, bf16 copies, folded GDN /
+ * EntropyBottleneck re-parametrisations, scale table of utils/func.py:16-19).  Call after the last
+ * set_param and again after any parameter change; replaces update() (models/mlicpp.py:470-475). */
+int mlic_engine_finalize(mlic_engine* e);
+
+/* Knobs: name = "tensor_cores" (1 = tcgen05 implicit-GEMM in bf16 mode [default], 0 = CUDA-core GEMM only). */
+int mlic_engine_set_option(mlic_engine* e, const char* name, int value);
+
+/* Device workspace needed by one call of the given mode / precision / shape. */
+int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes);
+
+/* forward(x) -> {x_hat, likelihoods}  (models/mlicpp.py:79-185; VBR: models/mlicpp_vbr.py:137-336 with
+ * stage 2; `gain` is the level's Gain value or `inputscale`, ignored for non-VBR kinds).
+ * mode = MLIC_MODE_COMPRESS: the network walk of compress() up to the rANS coder
+ *   (models/mlicpp.py:199-277, utils/ckbd.py:123-144; VBR utils/ckbd.py:76-90,146-158) -> symbols / indexes.
+ * mode = MLIC_MODE_DECODER: net_decoder_forward (models/mlicpp.py:380-459); `x` is not read. */
+int mlic_run(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* dev,
+             void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Same call on HOST buffers: copies x in, runs, copies the requested outputs back and synchronises.
+ * Workspace and device staging are owned and cached by the engine.  `pinned` != 0 promises that the host
+ * pointers are page-locked (async copies). */
+int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* host,
+                  int pinned);
+
+/* Number of kernels the engine launched in the last mlic_run / mlic_run_host call. */
+int64_t mlic_last_launch_count(const mlic_engine* e);
+
+/* Stand-alone fused quantise / likelihood / CDF-index kernel on NCHW fp32 device tensors of one slice
+ * (CompressAI GaussianConditional.forward / quantize / build_indexes; call sites models/mlicpp.py:132-134,
+ * utils/ckbd.py:128-129).  y, scales, means, y_hat, lik: [n]; sym, idx: [n] (any may be NULL among outputs). */
+int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, float* y_hat,
+                              float* lik, int32_t* sym, int32_t* idx, void* cuda_stream);
+
+const char* mlic_last_error(void);
+const char* mlic_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLIC_B200_H_ */

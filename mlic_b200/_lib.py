@@ -1,0 +1,66 @@
+"""ctypes binding of include/mlic_b200.h.  There is no fallback: if the shared library is missing
+or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmlic_b200.so")
+
+KIND_BASE, KIND_SD, KIND_VBR = 0, 1, 2
+PREC_FP32, PREC_BF16 = 0, 1
+MODE_FORWARD, MODE_COMPRESS, MODE_DECODER = 0, 1, 2
+
+# every symbol include/mlic_b200.h declares (tests check the library exports exactly these)
+EXPORTS = (
+    "mlic_engine_create", "mlic_engine_destroy", "mlic_engine_set_param", "mlic_engine_finalize",
+    "mlic_engine_set_option", "mlic_workspace_bytes", "mlic_run", "mlic_run_host", "mlic_last_launch_count",
+    "mlic_gaussian_conditional", "mlic_last_error", "mlic_version",
+)
+
+
+class Buffers(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_hat", C.c_void_p), ("y_likelihoods", C.c_void_p), ("z_likelihoods", C.c_void_p),
+        ("symbols", C.c_void_p), ("indexes", C.c_void_p), ("z_symbols", C.c_void_p),
+        ("y", C.c_void_p), ("y_hat", C.c_void_p), ("rd_sums", C.c_void_p),
+    ]
+
+
+class MlicError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libmlic_b200.so (built by `python -m mlic_b200.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MlicError(f"{LIB_PATH} not found: build the CUDA extension first (python -m mlic_b200.build); "
+                        "mlic_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+    L.mlic_engine_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
+    L.mlic_engine_destroy.argtypes = [vp]
+    L.mlic_engine_destroy.restype = None
+    L.mlic_engine_set_param.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
+    L.mlic_engine_finalize.argtypes = [vp]
+    L.mlic_engine_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.mlic_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(sz)]
+    L.mlic_run.argtypes = [vp, i32, i32, i32, i32, i32, f32, C.POINTER(Buffers), vp, sz, vp]
+    L.mlic_run_host.argtypes = [vp, i32, i32, i32, i32, i32, f32, C.POINTER(Buffers), i32]
+    L.mlic_last_launch_count.argtypes = [vp]
+    L.mlic_last_launch_count.restype = i64
+    L.mlic_gaussian_conditional.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp]
+    L.mlic_last_error.restype = C.c_char_p
+    L.mlic_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != 0:
+        raise MlicError(lib().mlic_last_error().decode("utf-8", "replace"))

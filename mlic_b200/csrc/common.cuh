@@ -1,0 +1,160 @@
+// Shared device-side vocabulary of the MLIC++ engine: NHWC activation views, the GEMM
+// epilogue description, exact-erf GELU, checkerboard parity, typed vector load/store.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace mlic {
+
+typedef __nv_bfloat16 bf16;
+
+// NHWC view: p points at channel 0 of the view, ld = elements between consecutive pixels.
+struct Act {
+    void* p;
+    int B, H, W, C, ld;
+};
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_HALF_TANH = 2 };
+enum { PAR_NONE = 0, PAR_ANCHOR = 1, PAR_NONANCHOR = 2 };
+enum { GDN_NONE = 0, GDN_FWD = 1, GDN_INV = 2 };
+
+// anchor = (row + col) odd  (reference: MLIC++/utils/ckbd.py:35-45)
+__device__ __forceinline__ bool parity_keep(int par, int h, int w) {
+    return par == PAR_NONE || (((h + w) & 1) == (par == PAR_ANCHOR ? 1 : 0));
+}
+
+// What happens to one accumulator row segment on its way to memory.  Order:
+//   v = premask ? (keep ? acc : 0) : acc;  v += bias;  gdn: v = x * (r)sqrt(v);  act;  postmask;  v += res;
+//   store out (optionally pixel-shuffled r=2);  out2 = v*v (optional, same addressing as out).
+struct Epi {
+    const float* bias;      // [N] in GEMM column order, may be null
+    int act, premask, postmask;
+    const void* res; int res_ld;       // residual, addressed like the OUTPUT
+    int gdn; const void* gdn_x; int gdn_ld;   // x operand of (I)GDN, addressed like the GEMM-space pixel
+    int shuffle;            // 0 | 1: PixelShuffle(2); GEMM column n' = (2r+s)*Cq + c  (weights permuted at pack time)
+    void* out; int out_ld;
+    int out_f32;            // 1: `out` is float* even when activations are bf16 (y, entropy parameters)
+    void* out2; int out2_ld;
+    int Hout, Wout, N;      // GEMM-space output grid and column count
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU(approximate='none')
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4-element vector access (16 B for float, 8 B for bf16); pointers must be so aligned.
+__device__ __forceinline__ void load4(const float* p, float v[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float v[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float v[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+
+// Apply the epilogue to 4 consecutive GEMM columns n..n+3 of GEMM-space pixel (b,h,w) and store.
+// `vec` = host-verified that every pointer/ld involved allows 4-wide vector access.
+template <typename T>
+__device__ __forceinline__ void epi_store4(const Epi& e, int b, int h, int w, int n, float v[4], bool vec) {
+    if (n >= e.N) return;
+    const bool keep_pre = parity_keep(e.premask, h, w);
+    const bool keep_post = parity_keep(e.postmask, h, w);
+    int oh = h, ow = w, oc = n, OH = e.Hout, OW = e.Wout;
+    bool straddle = false;
+    if (e.shuffle) {
+        const int Cq = e.N >> 2;
+        const int g = n / Cq;
+        oc = n - g * Cq;
+        oh = 2 * h + (g >> 1);
+        ow = 2 * w + (g & 1);
+        OH *= 2; OW *= 2;
+        straddle = (Cq & 3) != 0;       // the 4 columns may cross a shuffle group (final 3-channel conv)
+    }
+    const size_t gpix = ((size_t)b * e.Hout + h) * e.Wout + w;
+    float x4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e.gdn) {
+        const T* xp = reinterpret_cast<const T*>(e.gdn_x) + gpix * e.gdn_ld + n;
+        if (vec && n + 3 < e.N) load4(xp, x4);
+        else for (int j = 0; j < 4; ++j) if (n + j < e.N) x4[j] = to_f<T>(xp[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = keep_pre ? v[j] : 0.0f;
+        if (e.bias && n + j < e.N) a += e.bias[n + j];
+        if (e.gdn == GDN_FWD) a = x4[j] * rsqrtf(a);
+        else if (e.gdn == GDN_INV) a = x4[j] * sqrtf(a);
+        if (e.act == ACT_GELU) a = gelu_erf(a);
+        else if (e.act == ACT_HALF_TANH) a = 0.5f * tanhf(a);
+        if (!keep_post) a = 0.0f;
+        v[j] = a;
+    }
+    if (!straddle && n + 3 < e.N) {
+        const size_t opix = ((size_t)b * OH + oh) * OW + ow;
+        if (e.res) {
+            const T* rp = reinterpret_cast<const T*>(e.res) + opix * e.res_ld + oc;
+            float r4[4];
+            if (vec) load4(rp, r4);
+            else for (int j = 0; j < 4; ++j) r4[j] = to_f<T>(rp[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += r4[j];
+        }
+        if (e.out_f32) {
+            float* op = reinterpret_cast<float*>(e.out) + opix * e.out_ld + oc;
+            if (vec) store4(op, v);
+            else for (int j = 0; j < 4; ++j) op[j] = v[j];
+        } else {
+            T* op = reinterpret_cast<T*>(e.out) + opix * e.out_ld + oc;
+            if (vec) store4(op, v);
+            else for (int j = 0; j < 4; ++j) op[j] = from_f<T>(v[j]);
+        }
+        if (e.out2) {
+            float s4[4] = {v[0] * v[0], v[1] * v[1], v[2] * v[2], v[3] * v[3]};
+            T* qp = reinterpret_cast<T*>(e.out2) + opix * e.out2_ld + oc;
+            if (vec) store4(qp, s4);
+            else for (int j = 0; j < 4; ++j) qp[j] = from_f<T>(s4[j]);
+        }
+    } else {
+        // scalar tail: columns may cross a shuffle group or the end of N
+        for (int j = 0; j < 4; ++j) {
+            const int nj = n + j;
+            if (nj >= e.N) break;
+            int ohj = h, owj = w, ocj = nj;
+            if (e.shuffle) {
+                const int Cq = e.N >> 2;
+                const int g = nj / Cq;
+                ocj = nj - g * Cq;
+                ohj = 2 * h + (g >> 1);
+                owj = 2 * w + (g & 1);
+            }
+            const size_t opix = ((size_t)b * OH + ohj) * OW + owj;
+            float a = v[j];
+            if (e.res) a += to_f<T>(reinterpret_cast<const T*>(e.res)[opix * e.res_ld + ocj]);
+            if (e.out_f32) reinterpret_cast<float*>(e.out)[opix * e.out_ld + ocj] = a;
+            else reinterpret_cast<T*>(e.out)[opix * e.out_ld + ocj] = from_f<T>(a);
+            if (e.out2) reinterpret_cast<T*>(e.out2)[opix * e.out2_ld + ocj] = from_f<T>(a * a);
+        }
+    }
+}
+
+}  // namespace mlic

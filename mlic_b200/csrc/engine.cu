@@ -1,0 +1,950 @@
+// The MLIC++ network walk (g_a, h_a, EntropyBottleneck, h_s, the 10-slice x (anchor, non-anchor)
+// multi-reference entropy model, g_s) over the kernels of kernels.cu / gemm_tc.cu, and the C ABI of
+// include/mlic_b200.h.
+//
+// Layout in HBM (one call, B images, latent grid h x w = H/16 x W/16, all activations NHWC):
+//   LRPW  [B,h,w, Me + M]   : hyper_means | y_hat slice 0 | ... | slice S-1   -> every LRP / context input is a
+//                             channel-prefix view, no torch.cat               (models/mlicpp.py:119,143-144)
+//   EPW   [B,h,w, 10C + 2Me]: local 2C | intra 2C | inter 2C | channel 4C | hyper_params 2Me
+//                             -> both EntropyParameters inputs are channel-suffix views (mlicpp.py:146,160)
+//   y32   [B,h,w, M] fp32, lik [B,h,w, M] fp32, pa / pn [B,h,w, 2C] fp32 (entropy parameters never leave fp32)
+// Activations are fp32 (validation mode) or bf16 (fast mode); accumulation is fp32 in both.
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mlic_b200.h"
+#include "kernels.h"
+
+using namespace mlic;
+
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CUDA_OK(x)                                                                             \
+    do {                                                                                       \
+        cudaError_t _e = (x);                                                                  \
+        if (_e != cudaSuccess) return fail("%s: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+struct HostT {
+    std::vector<float> v;
+    std::vector<int64_t> shape;
+    int64_t dim(int i) const { return shape[i]; }
+};
+
+struct ConvW {          // GEMM-packed convolution / linear weights
+    float* w32 = nullptr;       // [N][ks*ks*Cin], k = tap*Cin + c
+    bf16* wbf = nullptr;        // [N][ks*ks*Cpad], zero padded per tap
+    float* bias = nullptr;      // [N] (GEMM column order)
+    int Cin = 0, N = 0, ks = 1, Cpad = 0, shuffle = 0;
+};
+struct DwW {
+    float* w9 = nullptr;        // [9][C]
+    float* bias = nullptr;      // [C]
+    int C = 0;
+};
+struct LnW { float* g = nullptr; float* b = nullptr; int C = 0; };
+
+struct EpiOpt {
+    int act = ACT_NONE, premask = PAR_NONE, postmask = PAR_NONE;
+    const Act* res = nullptr;
+    int gdn = GDN_NONE;
+    const Act* gdn_x = nullptr;
+    const Act* out2 = nullptr;
+    float* out_f32 = nullptr;   // fp32 destination [pix][out_f32_ld] instead of `out`
+    int out_f32_ld = 0;
+};
+
+}  // namespace
+
+struct mlic_engine {
+    int N, M, S, C, kind;
+    bool sd, vbr;
+    int Me;                  // channels of hyper_means as the entropy model sees them (M, or M/4 for SD)
+    std::map<std::string, HostT> params;
+    bool finalized = false;
+    int use_tc = 1;
+
+    std::vector<void*> dev_allocs;
+    std::unordered_map<std::string, ConvW> convs;
+    std::unordered_map<std::string, DwW> dws;
+    std::unordered_map<std::string, LnW> lns;
+    std::unordered_map<std::string, float*> misc;
+    float* eb_packed = nullptr;
+    float* eb_medians = nullptr;
+    float* scale_table = nullptr;
+
+    // per-call state
+    int bf = 0;
+    bool dry = false;
+    cudaStream_t st = nullptr;
+    uint8_t* ws_base = nullptr;
+    size_t ws_size = 0, ws_off = 0, ws_peak = 0;
+    int64_t launches = 0;
+    int rc = 0;              // sticky error of the current walk
+
+    // host-call staging (mlic_run_host)
+    void* h_ws = nullptr; size_t h_ws_bytes = 0;
+    void* h_io = nullptr; size_t h_io_bytes = 0;
+    cudaStream_t h_stream = nullptr;
+
+    ~mlic_engine() {
+        for (void* p : dev_allocs) cudaFree(p);
+        if (h_ws) cudaFree(h_ws);
+        if (h_io) cudaFree(h_io);
+        if (h_stream) cudaStreamDestroy(h_stream);
+    }
+
+    // ------------------------------------------------------------------ parameter access / packing
+    const HostT* get(const std::string& name) {
+        auto it = params.find(name);
+        if (it == params.end()) { rc = fail("missing parameter '%s'", name.c_str()); return nullptr; }
+        return &it->second;
+    }
+    template <typename T> T* upload(const std::vector<T>& h) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(h.size() * sizeof(T), 16)) != cudaSuccess) { rc = fail("cudaMalloc failed"); return nullptr; }
+        dev_allocs.push_back(d);
+        if (!h.empty()) cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        return (T*)d;
+    }
+    static uint16_t f2bf(float f) {            // round-to-nearest-even, as __float2bfloat16_rn
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+        u += 0x7fffu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    }
+    // w: [N][Cin][ks][ks] (+ bias [N]); shuffle: PixelShuffle(2) column permutation n' = (2r+s)*Cq + c <- o = 4c + 2r + s
+    void pack_conv_raw(const std::string& key, const float* w, const float* b, int N_, int Cin, int ks, int shuffle) {
+        ConvW cw;
+        cw.Cin = Cin; cw.N = N_; cw.ks = ks; cw.shuffle = shuffle;
+        cw.Cpad = (Cin + 63) / 64 * 64;
+        const int taps = ks * ks;
+        std::vector<float> w32((size_t)N_ * taps * Cin), bias(N_, 0.f);
+        std::vector<uint16_t> wbf((size_t)N_ * taps * cw.Cpad, 0);
+        for (int o = 0; o < N_; ++o) {
+            int n = o;
+            if (shuffle) { int Cq = N_ / 4; n = (o & 3) * Cq + (o >> 2); }
+            for (int c = 0; c < Cin; ++c)
+                for (int t = 0; t < taps; ++t) {
+                    float v = w[((size_t)o * Cin + c) * taps + t];
+                    w32[((size_t)n * taps + t) * Cin + c] = v;
+                    wbf[((size_t)n * taps + t) * cw.Cpad + c] = f2bf(v);
+                }
+            if (b) bias[n] = b[o];
+        }
+        cw.w32 = upload(w32);
+        cw.wbf = (bf16*)upload(wbf);
+        cw.bias = upload(bias);
+        convs[key] = cw;
+    }
+    void pack_conv(const std::string& p, int shuffle = 0) {
+        const HostT* w = get(p + ".weight");
+        const HostT* b = get(p + ".bias");
+        if (!w || !b) return;
+        int ks = w->shape.size() == 4 ? (int)w->dim(2) : 1;
+        pack_conv_raw(p, w->v.data(), b->v.data(), (int)w->dim(0), (int)w->dim(1), ks, shuffle);
+    }
+    void pack_dw_list(const std::string& key, const std::vector<std::string>& ps) {     // concatenated depthwise convs
+        int Ct = 0;
+        for (auto& p : ps) { const HostT* w = get(p + ".weight"); if (!w) return; Ct += (int)w->dim(0); }
+        std::vector<float> w9((size_t)9 * Ct), bias(Ct);
+        int c0 = 0;
+        for (auto& p : ps) {
+            const HostT* w = get(p + ".weight");
+            const HostT* b = get(p + ".bias");
+            if (!w || !b) return;
+            int Cc = (int)w->dim(0);
+            for (int c = 0; c < Cc; ++c) {
+                for (int t = 0; t < 9; ++t) w9[(size_t)t * Ct + c0 + c] = w->v[(size_t)c * 9 + t];
+                bias[c0 + c] = b->v[c];
+            }
+            c0 += Cc;
+        }
+        DwW d; d.C = Ct; d.w9 = upload(w9); d.bias = upload(bias);
+        dws[key] = d;
+    }
+    void pack_ds(const std::string& p) { pack_dw_list(p + ".depth_conv", {p + ".depth_conv"}); pack_conv(p + ".point_conv"); }
+    void pack_c3(const std::string& p, bool dense) { if (dense) pack_conv(p); else pack_ds(p); }
+    void pack_gdn(const std::string& p) {
+        const HostT* beta = get(p + ".beta");
+        const HostT* gamma = get(p + ".gamma");
+        if (!beta || !gamma) return;
+        const int Cc = (int)beta->dim(0);
+        // NonNegativeParametrizer (CompressAI): eff = max(p, bound)^2 - pedestal, all in fp32 as torch computes it
+        const float ped = (float)ldexp(1.0, -36);
+        const float bound_b = sqrtf(1e-6f + ped), bound_g = sqrtf(0.0f + ped);
+        std::vector<float> g((size_t)Cc * Cc), b(Cc);
+        for (int i = 0; i < Cc; ++i) { float t = fmaxf(beta->v[i], bound_b); b[i] = t * t - ped; }
+        for (size_t i = 0; i < g.size(); ++i) { float t = fmaxf(gamma->v[i], bound_g); g[i] = t * t - ped; }
+        pack_conv_raw(p, g.data(), b.data(), Cc, Cc, 1, 0);
+    }
+    void pack_ln(const std::string& p) {
+        const HostT* g = get(p + ".weight");
+        const HostT* b = get(p + ".bias");
+        if (!g || !b) return;
+        LnW l; l.C = (int)g->dim(0); l.g = upload(g->v); l.b = upload(b->v);
+        lns[p] = l;
+    }
+    void pack_rb(const std::string& p, bool dense) {
+        pack_c3(p + ".conv1", dense); pack_c3(p + ".conv2", dense);
+        if (params.count(p + ".skip.weight")) pack_conv(p + ".skip");
+    }
+    void pack_qkv(const std::string& p, bool fuse_pw) {
+        if (fuse_pw) {      // one GEMM producing [Q | K | V]
+            const HostT *wq = get(p + ".queries.0.weight"), *wk = get(p + ".keys.0.weight"), *wv = get(p + ".values.0.weight");
+            const HostT *bq = get(p + ".queries.0.bias"), *bk = get(p + ".keys.0.bias"), *bv = get(p + ".values.0.bias");
+            if (!wq || !wk || !wv || !bq || !bk || !bv) return;
+            std::vector<float> w(wq->v), b(bq->v);
+            w.insert(w.end(), wk->v.begin(), wk->v.end()); w.insert(w.end(), wv->v.begin(), wv->v.end());
+            b.insert(b.end(), bk->v.begin(), bk->v.end()); b.insert(b.end(), bv->v.begin(), bv->v.end());
+            int D = (int)wq->dim(0);
+            pack_conv_raw(p + ".qkv_pw", w.data(), b.data(), 3 * D, D, 1, 0);
+        } else {
+            pack_conv(p + ".queries.0"); pack_conv(p + ".keys.0"); pack_conv(p + ".values.0");
+        }
+        pack_dw_list(p + ".qkv_dw", {p + ".queries.1", p + ".keys.1", p + ".values.1"});
+    }
+    void pack_dw_mlp(const std::string& p) {
+        pack_conv(p + ".0"); pack_dw_list(p + ".2", {p + ".2"}); pack_conv(p + ".4");
+    }
+
+    int finalize() {
+        for (void* p : dev_allocs) cudaFree(p);
+        dev_allocs.clear(); convs.clear(); dws.clear(); lns.clear(); misc.clear();
+        rc = 0;
+        // g_a / h_a
+        std::string p = "g_a.analysis_transform.";
+        for (int i : {0, 2, 4}) {
+            std::string q = p + std::to_string(i);
+            pack_c3(q + ".conv1", sd); pack_c3(q + ".conv2", sd); pack_gdn(q + ".gdn"); pack_conv(q + ".skip");
+            pack_rb(p + std::to_string(i + 1), sd);
+        }
+        pack_c3(p + "6", sd);
+        for (int i : {0, 2, 4, 6, 8}) pack_c3("h_a.reduction." + std::to_string(i), sd);
+        // g_s / h_s
+        p = "g_s.synthesis_transform.";
+        pack_rb(p + "0", false);
+        for (int i : {1, 3, 5}) {
+            std::string q = p + std::to_string(i);
+            pack_conv(q + ".subpel_conv.0", 1); pack_ds(q + ".conv"); pack_gdn(q + ".igdn"); pack_conv(q + ".upsample.0", 1);
+            pack_rb(p + std::to_string(i + 1), false);
+        }
+        pack_conv(p + "7.0", 1);
+        p = "h_s.increase.";
+        pack_ds(p + "0"); pack_conv(p + "2.0", 1); pack_ds(p + "4"); pack_conv(p + "6.0", 1); pack_ds(p + "8");
+        // entropy model
+        for (int i = 0; i < S; ++i) {
+            std::string is = std::to_string(i);
+            std::string lc = "local_context." + is;
+            pack_ln(lc + ".norm1"); pack_ln(lc + ".norm2");
+            pack_conv(lc + ".qkv_proj"); pack_conv(lc + ".proj"); pack_conv(lc + ".mlp.fc1"); pack_conv(lc + ".mlp.fc2");
+            {   // fusion Conv2d(C,2C,k=5) applied to [C,5,5] windows == linear over K = tap*C + c
+                const HostT* w = get(lc + ".fusion.weight");
+                const HostT* b = get(lc + ".fusion.bias");
+                if (w && b) {
+                    int No = (int)w->dim(0), Ci = (int)w->dim(1);
+                    std::vector<float> wl((size_t)No * 25 * Ci);
+                    for (int o = 0; o < No; ++o)
+                        for (int c = 0; c < Ci; ++c)
+                            for (int t = 0; t < 25; ++t) wl[((size_t)o * 25 + t) * Ci + c] = w->v[((size_t)o * Ci + c) * 25 + t];
+                    pack_conv_raw(lc + ".fusion", wl.data(), b->v.data(), No, 25 * Ci, 1, 0);
+                }
+                // relative position bias [2][25][25] = table[index[a][b]][head]   (context.py:95-100)
+                const HostT* tab = get(lc + ".relative_position_table");
+                const HostT* idx = get(lc + ".relative_position_index");
+                if (tab && idx) {
+                    std::vector<float> rb(2 * 625);
+                    for (int hh = 0; hh < 2; ++hh)
+                        for (int ab = 0; ab < 625; ++ab) rb[hh * 625 + ab] = tab->v[(size_t)((int)idx->v[ab]) * 2 + hh];
+                    misc[lc + ".rel_bias"] = upload(rb);
+                }
+            }
+            for (const char* tag : {"anchor", "nonanchor"}) {
+                std::string ep = std::string("entropy_parameters_") + tag + "." + is + ".fusion.";
+                for (int j : {0, 2, 4, 6}) pack_conv(ep + std::to_string(j));
+                std::string lr = std::string("lrp_") + tag + "." + is + ".lrp_transform.";
+                for (int j = 0; j < (sd ? 4 : 3); ++j) pack_ds(lr + std::to_string(2 * j));
+            }
+            if (i > 0) {
+                std::string cc = "channel_context." + is + ".fushion.";
+                for (int j : {0, 2, 4}) pack_c3(cc + std::to_string(j), sd);
+                std::string gi = "global_inter_context." + is;
+                pack_qkv(gi, true); pack_conv(gi + ".reprojection"); pack_dw_mlp(gi + ".mlp"); pack_conv(gi + ".skip");
+                std::string ga = "global_intra_context." + is;
+                pack_qkv(ga, false); pack_conv(ga + ".reprojection"); pack_dw_mlp(ga + ".mlp");
+            }
+        }
+        // EntropyBottleneck: softplus(matrices), tanh(factors) folded
+        {
+            std::vector<float> packed((size_t)N * 58), med(N);
+            const int moff[5] = {0, 3, 12, 21, 30}, msz[5] = {3, 9, 9, 9, 3};
+            const int boff[5] = {33, 36, 39, 42, 45}, bsz[5] = {3, 3, 3, 3, 1};
+            const int foff[4] = {46, 49, 52, 55};
+            for (int i = 0; i < 5; ++i) {
+                const HostT* m = get("entropy_bottleneck.matrices." + std::to_string(i));
+                const HostT* b = get("entropy_bottleneck.biases." + std::to_string(i));
+                if (!m || !b) break;
+                for (int c = 0; c < N; ++c) {
+                    for (int j = 0; j < msz[i]; ++j) {
+                        float x = m->v[(size_t)c * msz[i] + j];
+                        packed[(size_t)c * 58 + moff[i] + j] = x > 20.f ? x : log1pf(expf(x));     // F.softplus
+                    }
+                    for (int j = 0; j < bsz[i]; ++j) packed[(size_t)c * 58 + boff[i] + j] = b->v[(size_t)c * bsz[i] + j];
+                }
+                if (i < 4) {
+                    const HostT* f = get("entropy_bottleneck.factors." + std::to_string(i));
+                    if (!f) break;
+                    for (int c = 0; c < N; ++c)
+                        for (int j = 0; j < 3; ++j) packed[(size_t)c * 58 + foff[i] + j] = tanhf(f->v[(size_t)c * 3 + j]);
+                }
+            }
+            const HostT* q = get("entropy_bottleneck.quantiles");
+            if (q) for (int c = 0; c < N; ++c) med[c] = q->v[(size_t)c * 3 + 1];
+            eb_packed = upload(packed);
+            eb_medians = upload(med);
+        }
+        {   // utils/func.py:16-19 -- exp(linspace(log .11, log 256, 64)) in fp32 (torch.linspace is symmetric around the middle)
+            std::vector<float> tab(64);
+            auto it = params.find("gaussian_conditional.scale_table");
+            if (it != params.end() && it->second.v.size() == 64) tab = it->second.v;
+            else {
+                const float lo = logf(0.11f), hi = logf(256.0f);
+                const float step = (hi - lo) / 63.0f;
+                for (int k = 0; k < 64; ++k) {
+                    float v = k < 32 ? lo + step * (float)k : hi - step * (float)(63 - k);
+                    tab[k] = expf(v);
+                }
+            }
+            scale_table = upload(tab);
+        }
+        if (rc) return rc;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return fail("finalize: %s", cudaGetErrorString(e));
+        finalized = true;
+        return 0;
+    }
+
+    // ------------------------------------------------------------------ workspace arena
+    int esz() const { return bf ? 2 : 4; }
+    void* ws_alloc(size_t bytes) {
+        size_t o = (ws_off + 255) & ~(size_t)255;
+        ws_off = o + bytes;
+        if (ws_off > ws_peak) ws_peak = ws_off;
+        if (!dry && ws_off > ws_size) { if (!rc) rc = fail("workspace too small: need > %zu, have %zu", ws_off, ws_size); return ws_base; }
+        return ws_base + o;
+    }
+    Act act(int B, int H, int W, int Cc) {
+        Act a; a.B = B; a.H = H; a.W = W; a.C = Cc; a.ld = (Cc + 7) / 8 * 8;
+        a.p = ws_alloc((size_t)B * H * W * a.ld * esz());
+        return a;
+    }
+    float* f32(size_t n) { return (float*)ws_alloc(n * 4); }
+    Act view(const Act& a, int c0, int Cc) const {
+        Act v = a; v.p = (uint8_t*)a.p + (size_t)c0 * esz(); v.C = Cc;
+        return v;
+    }
+    bool go() const { return !dry && !rc; }
+    void after_launch(const char* what) {
+        ++launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && !rc) rc = fail("%s launch: %s", what, cudaGetErrorString(e));
+    }
+
+    // ------------------------------------------------------------------ primitive layers
+    const ConvW* cw(const std::string& k) {
+        auto it = convs.find(k);
+        if (it == convs.end()) { if (!rc) rc = fail("conv '%s' not packed", k.c_str()); return nullptr; }
+        return &it->second;
+    }
+    const DwW* dw(const std::string& k) {
+        auto it = dws.find(k);
+        if (it == dws.end()) { if (!rc) rc = fail("dwconv '%s' not packed", k.c_str()); return nullptr; }
+        return &it->second;
+    }
+    bool al4(const void* p) const { return ((uintptr_t)p % (size_t)(4 * esz())) == 0; }
+
+    // out = epilogue(conv(in, W)); `out` is an activation view of w->N (or N/4 when shuffled) channels.
+    void gemm(const Act& in, const std::string& key, int stride, int pad, const Act* out, const EpiOpt& o) {
+        const ConvW* w = cw(key);
+        if (!w) return;
+        if (in.C != w->Cin) { if (!rc) rc = fail("gemm '%s': input has %d channels, weights expect %d", key.c_str(), in.C, w->Cin); return; }
+        Epi e;
+        memset(&e, 0, sizeof e);
+        e.bias = w->bias; e.act = o.act; e.premask = o.premask; e.postmask = o.postmask;
+        e.N = w->N; e.shuffle = w->shuffle;
+        e.Hout = (in.H + 2 * pad - w->ks) / stride + 1;
+        e.Wout = (in.W + 2 * pad - w->ks) / stride + 1;
+        bool vec = (w->N % 4 == 0);
+        if (o.out_f32) { e.out = o.out_f32; e.out_ld = o.out_f32_ld; e.out_f32 = 1; vec = vec && (o.out_f32_ld % 4 == 0) && ((uintptr_t)o.out_f32 % 16 == 0); }
+        else if (out) { e.out = out->p; e.out_ld = out->ld; vec = vec && (out->ld % 4 == 0) && al4(out->p); }
+        else { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return; }
+        if (o.res) { e.res = o.res->p; e.res_ld = o.res->ld; vec = vec && (o.res->ld % 4 == 0) && al4(o.res->p); }
+        if (o.gdn) { e.gdn = o.gdn; e.gdn_x = o.gdn_x->p; e.gdn_ld = o.gdn_x->ld; vec = vec && (o.gdn_x->ld % 4 == 0) && al4(o.gdn_x->p); }
+        if (o.out2) { e.out2 = o.out2->p; e.out2_ld = o.out2->ld; vec = vec && (o.out2->ld % 4 == 0) && al4(o.out2->p); }
+        if (w->shuffle && ((w->N / 4) % 4 != 0)) vec = false;
+        if (!go()) return;
+        if (bf && use_tc && (stride == 1 || w->ks == 1)) {
+            TcConv t;
+            t.in = in.p; t.B = in.B; t.Cin = in.C; t.ld = in.ld; t.ks = w->ks; t.pad = pad; t.w = w->wbf; t.Cpad = w->Cpad;
+            t.H = e.Hout + (w->ks - 1) - 2 * pad;     // == in.H for stride 1
+            t.W = e.Wout + (w->ks - 1) - 2 * pad;
+            if (stride == 1) { t.H = in.H; t.W = in.W; }
+            else { t.H = e.Hout; t.W = e.Wout; }      // 1x1 stride s: sub-sampled grid
+            t.sW = in.ld * stride; t.sH = in.W * in.ld * stride; t.sB = in.H * in.W * in.ld;
+            if (tc_conv_supported(t, e)) {
+                int r = launch_conv_gemm_tc(t, e, vec ? 1 : 0, st);
+                if (r) { if (!rc) rc = fail("tcgen05 conv '%s': %s", key.c_str(), tc_last_error()); return; }
+                ++launches;
+                return;
+            }
+        }
+        ConvGeom g;
+        g.B = in.B; g.H = in.H; g.W = in.W; g.Cin = in.C; g.ld = in.ld; g.Hout = e.Hout; g.Wout = e.Wout;
+        g.ks = w->ks; g.stride = stride; g.pad = pad; g.Ktot = w->ks * w->ks * w->Cin;
+        int avec = vec && (in.ld % 4 == 0) && al4(in.p);
+        // the kernel's `vec` covers both the A loads and the epilogue accesses
+        launch_conv_gemm_simt(bf, in.p, g, w->w32, e, (avec && vec) ? 1 : 0, st);
+        after_launch(key.c_str());
+    }
+    void dwconv(const Act& in, const std::string& key, int stride, int actv, const Act& out) {
+        const DwW* d = dw(key);
+        if (!d) return;
+        if (d->C != in.C) { if (!rc) rc = fail("dwconv '%s': %d channels vs %d", key.c_str(), in.C, d->C); return; }
+        if (!go()) return;
+        launch_dwconv3x3(bf, in, out, d->w9, d->bias, stride, actv, st);
+        after_launch(key.c_str());
+    }
+    // DepthWiseConv (modules/layers/conv.py:46-63): dw3x3(stride) -> pw1x1 with epilogue
+    void dsconv(const Act& in, const std::string& p, int stride, const Act* out, const EpiOpt& o) {
+        size_t mark = ws_off;
+        Act t = act(in.B, (in.H - 1) / stride + 1, (in.W - 1) / stride + 1, in.C);
+        dwconv(in, p + ".depth_conv", stride, ACT_NONE, t);
+        gemm(t, p + ".point_conv", 1, 0, out, o);
+        ws_off = mark;
+    }
+    void c3(const Act& in, const std::string& p, int stride, bool dense, const Act* out, const EpiOpt& o) {
+        if (dense) gemm(in, p, stride, 1, out, o);
+        else dsconv(in, p, stride, out, o);
+    }
+    int out_ch(const std::string& p, bool dense) {
+        const ConvW* w = cw(dense ? p : p + ".point_conv");
+        return w ? w->N : 0;
+    }
+    void layernorm(const Act& x, const std::string& p, const Act& out) {
+        auto it = lns.find(p);
+        if (it == lns.end()) { if (!rc) rc = fail("layernorm '%s' not packed", p.c_str()); return; }
+        if (!go()) return;
+        launch_layernorm(bf, x, it->second.g, it->second.b, out, st);
+        after_launch(p.c_str());
+    }
+
+    // ------------------------------------------------------------------ blocks
+    // ResidualBlock (res_blk.py:142-154): GELU(conv2(GELU(conv1 x))) + skip(x)
+    void rb(const Act& x, const std::string& p, bool dense, const Act& out) {
+        size_t mark = ws_off;
+        EpiOpt g; g.act = ACT_GELU;
+        Act t = act(x.B, x.H, x.W, out.C);
+        c3(x, p + ".conv1", 1, dense, &t, g);
+        EpiOpt g2; g2.act = ACT_GELU;
+        Act idn = x;
+        if (convs.count(p + ".skip")) {
+            idn = act(x.B, x.H, x.W, out.C);
+            gemm(x, p + ".skip", 1, 0, &idn, EpiOpt());
+        }
+        g2.res = &idn;
+        c3(t, p + ".conv2", 1, dense, &out, g2);
+        ws_off = mark;
+    }
+    // ResidualBlockWithStride (res_blk.py:82-93): GDN(conv2(GELU(conv1_s2 x))) + skip_1x1_s2(x)
+    void rbws(const Act& x, const std::string& p, bool dense, const Act& out) {
+        size_t mark = ws_off;
+        EpiOpt g; g.act = ACT_GELU;
+        Act t = act(out.B, out.H, out.W, out.C);
+        c3(x, p + ".conv1", 2, dense, &t, g);
+        Act v = act(out.B, out.H, out.W, out.C), sq = act(out.B, out.H, out.W, out.C);
+        EpiOpt o2; o2.out2 = &sq;
+        c3(t, p + ".conv2", 1, dense, &v, o2);
+        Act sk = act(out.B, out.H, out.W, out.C);
+        gemm(x, p + ".skip", 2, 0, &sk, EpiOpt());
+        EpiOpt og; og.gdn = GDN_FWD; og.gdn_x = &v; og.res = &sk;
+        gemm(sq, p + ".gdn", 1, 0, &out, og);
+        ws_off = mark;
+    }
+    // ResidualBlockUpsample (res_blk.py:113-121): IGDN(conv(GELU(subpel x))) + upsample(x)
+    void rbu(const Act& x, const std::string& p, const Act& out) {
+        size_t mark = ws_off;
+        EpiOpt g; g.act = ACT_GELU;
+        Act t = act(out.B, out.H, out.W, out.C);
+        gemm(x, p + ".subpel_conv.0", 1, 1, &t, g);
+        Act v = act(out.B, out.H, out.W, out.C), sq = act(out.B, out.H, out.W, out.C);
+        EpiOpt o2; o2.out2 = &sq;
+        dsconv(t, p + ".conv", 1, &v, o2);
+        Act up = t;      // t is dead after the dsconv: reuse its storage for the identity branch
+        gemm(x, p + ".upsample.0", 1, 1, &up, EpiOpt());
+        EpiOpt og; og.gdn = GDN_INV; og.gdn_x = &v; og.res = &up;
+        gemm(sq, p + ".igdn", 1, 0, &out, og);
+        ws_off = mark;
+    }
+
+    // g_a (transform/analysis.py:9-17): x [B,H,W,3] -> y fp32 [pix][M]
+    void g_a(const Act& x, float* y32) {
+        size_t mark = ws_off;
+        const std::string p = "g_a.analysis_transform.";
+        Act cur = x;
+        for (int i : {0, 2, 4}) {
+            Act a = act(cur.B, cur.H / 2, cur.W / 2, N);
+            rbws(cur, p + std::to_string(i), sd, a);
+            Act b = act(a.B, a.H, a.W, N);
+            rb(a, p + std::to_string(i + 1), sd, b);
+            cur = b;
+        }
+        EpiOpt o; o.out_f32 = y32; o.out_f32_ld = M;
+        c3(cur, p + "6", 2, sd, nullptr, o);
+        ws_off = mark;
+    }
+    // h_a (transform/analysis.py:33-43)
+    void h_a(const Act& y, const Act& z) {
+        size_t mark = ws_off;
+        const std::string p = "h_a.reduction.";
+        const int strides[5] = {1, 1, 2, 1, 2};
+        Act cur = y;
+        for (int j = 0; j < 5; ++j) {
+            EpiOpt o; o.act = j < 4 ? ACT_GELU : ACT_NONE;
+            int s = strides[j];
+            Act nx = j < 4 ? act(cur.B, (cur.H - 1) / s + 1, (cur.W - 1) / s + 1, N) : z;
+            c3(cur, p + std::to_string(2 * j), s, sd, &nx, o);
+            cur = nx;
+        }
+        ws_off = mark;
+    }
+    // h_s (transform/synthesis.py:18-28): z_hat -> hyper_params (written into `out`, 2*Me channels)
+    void h_s(const Act& zh, const Act& out) {
+        size_t mark = ws_off;
+        const std::string p = "h_s.increase.";
+        EpiOpt g; g.act = ACT_GELU;
+        int c0 = out_ch(p + "0", false);
+        Act a = act(zh.B, zh.H, zh.W, c0);
+        dsconv(zh, p + "0", 1, &a, g);
+        Act b = act(zh.B, zh.H * 2, zh.W * 2, c0);
+        gemm(a, p + "2.0", 1, 1, &b, g);
+        int c4 = out_ch(p + "4", false);
+        Act c = act(b.B, b.H, b.W, c4);
+        dsconv(b, p + "4", 1, &c, g);
+        Act d = act(b.B, b.H * 2, b.W * 2, c4);
+        gemm(c, p + "6.0", 1, 1, &d, g);
+        dsconv(d, p + "8", 1, &out, EpiOpt());
+        ws_off = mark;
+    }
+    // g_s (transform/synthesis.py:59-68): y_hat view [B,h,w,M] -> x_hat fp32 NHWC [B,H,W,3]
+    void g_s(const Act& yh, float* xhat_nhwc) {
+        size_t mark = ws_off;
+        const std::string p = "g_s.synthesis_transform.";
+        Act cur = act(yh.B, yh.H, yh.W, M);
+        rb(yh, p + "0", false, cur);
+        for (int i : {1, 3, 5}) {
+            const ConvW* w = cw(p + std::to_string(i) + ".subpel_conv.0");
+            int co = w ? w->N / 4 : 0;
+            Act a = act(cur.B, cur.H * 2, cur.W * 2, co);
+            rbu(cur, p + std::to_string(i), a);
+            Act b = act(a.B, a.H, a.W, co);
+            rb(a, p + std::to_string(i + 1), false, b);
+            cur = b;
+        }
+        EpiOpt o; o.out_f32 = xhat_nhwc; o.out_f32_ld = 3;
+        gemm(cur, p + "7.0", 1, 1, nullptr, o);
+        ws_off = mark;
+    }
+
+    // EntropyParameters (transform/entropy.py:10-29): 1x1 chain in->320->256->128->2C, GELU between; fp32 out
+    void ep(const Act& in, const std::string& p, float* out32) {
+        size_t mark = ws_off;
+        EpiOpt g; g.act = ACT_GELU;
+        Act cur = in;
+        for (int j : {0, 2, 4}) {
+            const ConvW* w = cw(p + ".fusion." + std::to_string(j));
+            Act nx = act(in.B, in.H, in.W, w ? w->N : 0);
+            gemm(cur, p + ".fusion." + std::to_string(j), 1, 0, &nx, g);
+            cur = nx;
+        }
+        EpiOpt o; o.out_f32 = out32; o.out_f32_ld = 2 * C;
+        gemm(cur, p + ".fusion.6", 1, 0, nullptr, o);
+        ws_off = mark;
+    }
+    // LatentResidualPrediction (transform/quantization.py:30-45; :9-28 for SD): slot += mask * 0.5*tanh(stack(in))
+    void lrp(const Act& in, const std::string& p, const Act& slot, int parity) {
+        size_t mark = ws_off;
+        const int nl = sd ? 4 : 3;
+        EpiOpt g; g.act = ACT_GELU;
+        Act cur = in;
+        for (int j = 0; j < nl - 1; ++j) {
+            std::string q = p + ".lrp_transform." + std::to_string(2 * j);
+            Act nx = act(in.B, in.H, in.W, out_ch(q, false));
+            dsconv(cur, q, 1, &nx, g);
+            cur = nx;
+        }
+        EpiOpt o; o.act = ACT_HALF_TANH; o.postmask = parity; o.res = &slot;
+        dsconv(cur, p + ".lrp_transform." + std::to_string(2 * (nl - 1)), 1, &slot, o);
+        ws_off = mark;
+    }
+    // ChannelContext (transform/context.py:118-138; context_old.py:120-126 dense for SD)
+    void channel_ctx(const Act& in, const std::string& p, const Act& out) {
+        size_t mark = ws_off;
+        EpiOpt g; g.act = ACT_GELU;
+        Act a = act(in.B, in.H, in.W, out_ch(p + ".fushion.0", sd));
+        c3(in, p + ".fushion.0", 1, sd, &a, g);
+        Act b = act(in.B, in.H, in.W, out_ch(p + ".fushion.2", sd));
+        c3(a, p + ".fushion.2", 1, sd, &b, g);
+        c3(b, p + ".fushion.4", 1, sd, &out, EpiOpt());
+        ws_off = mark;
+    }
+    // 1x1 -> GELU -> dw3x3 -> GELU -> 1x1 (+ residual)   (context.py:161-167,217-223)
+    void dw_mlp(const Act& in, const std::string& p, const Act& out, const Act* res) {
+        size_t mark = ws_off;
+        EpiOpt g; g.act = ACT_GELU;
+        const ConvW* w0 = cw(p + ".0");
+        int hid = w0 ? w0->N : 0;
+        Act a = act(in.B, in.H, in.W, hid), b = act(in.B, in.H, in.W, hid);
+        gemm(in, p + ".0", 1, 0, &a, g);
+        dwconv(a, p + ".2", 1, ACT_GELU, b);
+        EpiOpt o; o.res = res;
+        gemm(b, p + ".4", 1, 0, &out, o);
+        ws_off = mark;
+    }
+    void lin_attn(const Act& qkv, int D, int heads, int hd, int par_kv, int par_q, const Act& out) {
+        float* scratch = f32(lin_attn_scratch_floats(qkv.B, heads, hd, qkv.H * qkv.W));
+        if (!go()) return;
+        if (launch_lin_attn(bf, qkv, D, heads, hd, par_kv, par_q, scratch, out, st)) { if (!rc) rc = fail("linear attention: unsupported head dim %d", hd); return; }
+        launches += 3;
+        after_launch("lin_attn");
+    }
+    // LinearGlobalInterContext (transform/context.py:226-245)
+    void inter_ctx(const Act& X, const std::string& p, const Act& out) {
+        size_t mark = ws_off;
+        const int D = X.C;
+        Act pw = act(X.B, X.H, X.W, 3 * D), qkv = act(X.B, X.H, X.W, 3 * D);
+        gemm(X, p + ".qkv_pw", 1, 0, &pw, EpiOpt());
+        dwconv(pw, p + ".qkv_dw", 1, ACT_NONE, qkv);
+        Act O = act(X.B, X.H, X.W, D);
+        lin_attn(qkv, D, D / 32, 32, PAR_NONE, PAR_NONE, O);
+        const ConvW* wr = cw(p + ".reprojection");
+        Act A = act(X.B, X.H, X.W, wr ? wr->N : 0);
+        gemm(O, p + ".reprojection", 1, 2, &A, EpiOpt());
+        gemm(A, p + ".skip", 1, 0, &out, EpiOpt());
+        dw_mlp(A, p + ".mlp", out, &out);
+        ws_off = mark;
+    }
+    // LinearGlobalIntraContext (transform/context.py:169-193)
+    void intra_ctx(const Act& x1, const Act& x2, const std::string& p, const Act& out) {
+        size_t mark = ws_off;
+        const int D = x1.C;
+        Act pw = act(x1.B, x1.H, x1.W, 3 * D), qkv = act(x1.B, x1.H, x1.W, 3 * D);
+        Act vq = view(pw, 0, D), vk = view(pw, D, D), vv = view(pw, 2 * D, D);
+        EpiOpt oq; oq.premask = PAR_NONANCHOR;
+        EpiOpt ok; ok.premask = PAR_ANCHOR;
+        gemm(x1, p + ".queries.0", 1, 0, &vq, oq);
+        gemm(x1, p + ".keys.0", 1, 0, &vk, ok);
+        gemm(x2, p + ".values.0", 1, 0, &vv, EpiOpt());
+        dwconv(pw, p + ".qkv_dw", 1, ACT_NONE, qkv);
+        Act O = act(x1.B, x1.H, x1.W, D);
+        lin_attn(qkv, D, 2, D / 2, PAR_ANCHOR, PAR_NONANCHOR, O);
+        Act A = act(x1.B, x1.H, x1.W, 2 * D);
+        gemm(O, p + ".reprojection", 1, 2, &A, EpiOpt());
+        dw_mlp(A, p + ".mlp", out, &A);
+        ws_off = mark;
+    }
+    // LocalContext (transform/context.py:67-112)
+    void local_ctx(const Act& x, const std::string& p, const Act& out) {
+        size_t mark = ws_off;
+        const int Cc = x.C;
+        const size_t npix = (size_t)x.B * x.H * x.W;
+        Act t = act(x.B, x.H, x.W, Cc);
+        layernorm(x, p + ".norm1", t);
+        float* F = f32(npix * 3 * Cc);
+        EpiOpt of; of.out_f32 = F; of.out_f32_ld = 3 * Cc;
+        gemm(t, p + ".qkv_proj", 1, 0, nullptr, of);
+        Act O = act(x.B, x.H, x.W, 25 * Cc);
+        if (go()) {
+            if (launch_local_attn(bf, F, x.B, x.H, x.W, Cc, misc[p + ".rel_bias"], O.p, st)) { if (!rc) rc = fail("local attention: unsupported slice width %d", Cc); }
+            after_launch("local_attn");
+        }
+        Act fu = act(x.B, x.H, x.W, 2 * Cc), pr = act(x.B, x.H, x.W, 2 * Cc), n2 = act(x.B, x.H, x.W, 2 * Cc);
+        gemm(O, p + ".fusion", 1, 0, &fu, EpiOpt());
+        gemm(fu, p + ".proj", 1, 0, &pr, EpiOpt());
+        layernorm(pr, p + ".norm2", n2);
+        Act h = act(x.B, x.H, x.W, 4 * Cc);
+        EpiOpt g; g.act = ACT_GELU;
+        gemm(n2, p + ".mlp.fc1", 1, 0, &h, g);
+        EpiOpt o; o.res = &pr;
+        gemm(h, p + ".mlp.fc2", 1, 0, &out, o);
+        ws_off = mark;
+    }
+
+    // ------------------------------------------------------------------ the whole call
+    int run(int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* io, void* ws, size_t ws_bytes,
+            cudaStream_t stream, bool dry_run) {
+        if (!finalized) return fail("engine not finalized");
+        if (B <= 0 || H <= 0 || W <= 0 || (H % 64) || (W % 64)) return fail("B=%d H=%d W=%d: H and W must be positive multiples of 64", B, H, W);
+        if (mode < 0 || mode > 2) return fail("bad mode %d", mode);
+        bf = precision == MLIC_PREC_BF16;
+        dry = dry_run; st = stream; rc = 0; launches = 0;
+        ws_base = (uint8_t*)ws; ws_size = ws_bytes; ws_off = 0; ws_peak = 0;
+        if (!dry && ((uintptr_t)ws % 256)) return fail("workspace must be 256-byte aligned");
+        if (!dry && bf && use_tc && tc_init()) return fail("%s", tc_last_error());
+        static const mlic_buffers none = {};
+        if (!io) io = &none;
+        const int h = H / 16, w = W / 16, hz = H / 64, wz = W / 64;
+        const size_t npix = (size_t)B * h * w;
+        const int use_gain = (vbr && gain != 0.0f) ? 1 : 0;
+        const float rgain = use_gain ? 1.0f / gain : 1.0f;
+
+        Act LRPW = act(B, h, w, Me + M);
+        Act EPW = act(B, h, w, 10 * C + 2 * Me);
+        float* y32 = f32(npix * M);
+        float* lik = mode == MLIC_MODE_FORWARD ? f32(npix * M) : nullptr;
+        float* pa = f32(npix * 2 * C);
+        float* pn = f32(npix * 2 * C);
+        Act zh = act(B, hz, wz, N);
+        Act hyper = view(EPW, 10 * C, 2 * Me);
+        Act yhat = view(LRPW, Me, M);
+
+        if (mode != MLIC_MODE_DECODER) {
+            if (!dry && !io->x) return fail("x is NULL");
+            size_t mark = ws_off;
+            Act x = act(B, H, W, 3);
+            if (go()) { launch_nchw_to_nhwc(bf, io->x, x, 3, st); after_launch("nchw_to_nhwc"); }
+            g_a(x, y32);
+            ws_off = mark;
+            Act ya = act(B, h, w, M);
+            if (go()) { launch_copy_f32_to_act(bf, y32, M, ya, st); after_launch("copy_y"); }
+            Act z = act(B, hz, wz, N);
+            h_a(ya, z);
+            if (go()) {
+                launch_entropy_bottleneck(bf, z, zh, eb_packed, eb_medians, mode == MLIC_MODE_FORWARD ? io->z_likelihoods : nullptr,
+                                          mode == MLIC_MODE_COMPRESS ? io->z_symbols : nullptr, st);
+                after_launch("entropy_bottleneck");
+            }
+            ws_off = mark;
+            if (io->y && go()) { launch_nhwc_f32_to_nchw(y32, M, B, h, w, M, io->y, st); after_launch("y_tap"); }
+        } else if (go()) {
+            launch_fill_zero(zh.p, (size_t)B * hz * wz * zh.ld * esz(), st);      // z_hat = 0 (mlicpp.py:390-394)
+        }
+        h_s(zh, hyper);
+        if (go()) { launch_copy_channels(bf, view(EPW, 10 * C + Me, Me), view(LRPW, 0, Me), st); after_launch("copy_hyper_means"); }
+
+        const size_t half = (size_t)B * C * h * (w / 2);
+        for (int i = 0; i < S && !rc; ++i) {
+            const std::string is = std::to_string(i);
+            Act slot = view(LRPW, Me + i * C, C);
+            Act lrp_in = view(LRPW, 0, Me + (i + 1) * C);
+            Act s_inter = view(EPW, 4 * C, 2 * C), s_chan = view(EPW, 6 * C, 4 * C), s_intra = view(EPW, 2 * C, 2 * C);
+            Act s_local = i ? view(EPW, 0, 2 * C) : view(EPW, 8 * C, 2 * C);
+            Act ep_a = i ? view(EPW, 4 * C, 6 * C + 2 * Me) : hyper;
+            Act ep_n = i ? view(EPW, 0, 10 * C + 2 * Me) : view(EPW, 8 * C, 2 * C + 2 * Me);
+            if (i) {
+                Act prev = view(LRPW, Me, i * C);
+                inter_ctx(prev, "global_inter_context." + is, s_inter);
+                channel_ctx(prev, "channel_context." + is, s_chan);
+            }
+            ep(ep_a, "entropy_parameters_anchor." + is, pa);
+            QuantArgs q;
+            memset(&q, 0, sizeof q);
+            q.y = y32 + (size_t)i * C; q.y_ld = M; q.pa = pa; q.pn = pn; q.slot = slot;
+            q.B = B; q.H = h; q.W = w; q.C = C; q.mode = mode; q.vbr = use_gain; q.gain = gain; q.rgain = rgain;
+            q.lik = lik ? lik + (size_t)i * C : nullptr; q.lik_ld = M;
+            q.table = scale_table; q.levels = 64;
+            if (mode == MLIC_MODE_COMPRESS) {
+                if (!dry && (!io->symbols || !io->indexes)) return fail("compress needs symbols and indexes buffers");
+                q.sym = io->symbols ? io->symbols + (size_t)(2 * i) * half : nullptr;
+                q.idx = io->indexes ? io->indexes + (size_t)(2 * i) * half : nullptr;
+            }
+            if (go()) { launch_quant_anchor(bf, q, st); after_launch("quant_anchor"); }
+            lrp(lrp_in, "lrp_anchor." + is, slot, PAR_ANCHOR);
+            if (i) intra_ctx(view(LRPW, Me + (i - 1) * C, C), slot, "global_intra_context." + is, s_intra);
+            local_ctx(slot, "local_context." + is, s_local);
+            ep(ep_n, "entropy_parameters_nonanchor." + is, pn);
+            if (mode == MLIC_MODE_COMPRESS) { q.sym += half; q.idx += half; }
+            if (go()) { launch_quant_nonanchor(bf, q, st); after_launch("quant_nonanchor"); }
+            lrp(lrp_in, "lrp_nonanchor." + is, slot, PAR_NONANCHOR);
+        }
+        if (rc) return rc;
+        if (mode == MLIC_MODE_FORWARD && io->y_likelihoods && go()) {
+            launch_nhwc_f32_to_nchw(lik, M, B, h, w, M, io->y_likelihoods, st);
+            after_launch("lik_nchw");
+        }
+        if (io->y_hat && go()) { launch_nhwc_to_nchw(bf, yhat, io->y_hat, st); after_launch("y_hat_tap"); }
+        if (io->x_hat || dry) {
+            float* xh = f32((size_t)B * H * W * 3);
+            g_s(yhat, xh);
+            if (go()) { launch_nhwc_f32_to_nchw(xh, 3, B, H, W, 3, io->x_hat, st); after_launch("x_hat_nchw"); }
+        }
+        if (mode == MLIC_MODE_FORWARD && (io->rd_sums || dry)) {
+            double* partial = (double*)ws_alloc(RD_BLOCKS * sizeof(double));
+            if (go() && io->rd_sums) {
+                if (!io->x_hat || !io->y_likelihoods || !io->z_likelihoods) return fail("rd_sums needs x_hat and both likelihood buffers");
+                cudaMemsetAsync(io->rd_sums, 0, 2 * sizeof(double), st);
+                launch_reduce(io->y_likelihoods, nullptr, (long long)npix * M, 0, partial, io->rd_sums, st);
+                launch_reduce(io->z_likelihoods, nullptr, (long long)B * hz * wz * N, 0, partial, io->rd_sums, st);
+                launch_reduce(io->x, io->x_hat, (long long)B * 3 * H * W, 1, partial, io->rd_sums + 1, st);
+                launches += 6;
+                after_launch("rd_sums");
+            }
+        }
+        return rc;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* mlic_last_error(void) { return g_err; }
+const char* mlic_version(void) { return "mlic_b200 0.1 (sm_100a)"; }
+
+int mlic_engine_create(int N, int M, int slice_num, int kind, mlic_engine** out) {
+    if (!out) return fail("out is NULL");
+    if (N <= 0 || M <= 0 || slice_num <= 0 || M % slice_num) return fail("M must be divisible by slice_num");     // mlicpp.py:21
+    if (kind < 0 || kind > 2) return fail("bad kind %d", kind);
+    int C = M / slice_num;
+    if (C != 32 && C != 64) return fail("slice width %d unsupported (32 or 64)", C);
+    mlic_engine* e = new mlic_engine();
+    e->N = N; e->M = M; e->S = slice_num; e->C = C; e->kind = kind;
+    e->sd = kind == MLIC_KIND_SD; e->vbr = kind == MLIC_KIND_VBR;
+    e->Me = e->sd ? M / 4 : M;
+    *out = e;
+    return 0;
+}
+void mlic_engine_destroy(mlic_engine* e) { delete e; }
+
+int mlic_engine_set_param(mlic_engine* e, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+    if (!e || !name || ndim < 0 || ndim > 8) return fail("bad arguments");
+    HostT t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+    if (n && !host_data) return fail("NULL data for '%s'", name);
+    t.v.assign(host_data, host_data + n);
+    e->params[name] = std::move(t);
+    e->finalized = false;
+    return 0;
+}
+int mlic_engine_finalize(mlic_engine* e) {
+    if (!e) return fail("engine is NULL");
+    return e->finalize();
+}
+int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
+    if (!e || !name) return fail("bad arguments");
+    if (!strcmp(name, "tensor_cores")) { e->use_tc = value; return 0; }
+    return fail("unknown option '%s'", name);
+}
+int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {
+    if (!e || !bytes) return fail("bad arguments");
+    int r = e->run(mode, precision, B, H, W, 1.0f, nullptr, nullptr, 0, nullptr, true);
+    if (r) return r;
+    *bytes = e->ws_peak + 256;
+    return 0;
+}
+int mlic_run(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* dev,
+             void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!e) return fail("engine is NULL");
+    return e->run(mode, precision, B, H, W, gain, dev, workspace, workspace_bytes, (cudaStream_t)cuda_stream, false);
+}
+int64_t mlic_last_launch_count(const mlic_engine* e) { return e ? e->launches : 0; }
+
+int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* host,
+                  int pinned) {
+    if (!e || !host) return fail("bad arguments");
+    (void)pinned;
+    size_t need = 0;
+    int r = mlic_workspace_bytes(e, mode, precision, B, H, W, &need);
+    if (r) return r;
+    if (!e->h_stream) CUDA_OK(cudaStreamCreateWithFlags(&e->h_stream, cudaStreamNonBlocking));
+    if (need > e->h_ws_bytes) {
+        if (e->h_ws) cudaFree(e->h_ws);
+        e->h_ws = nullptr; e->h_ws_bytes = 0;
+        CUDA_OK(cudaMalloc(&e->h_ws, need));
+        e->h_ws_bytes = need;
+    }
+    const int h = H / 16, w = W / 16, hz = H / 64, wz = W / 64;
+    const size_t n_x = (size_t)B * 3 * H * W, n_y = (size_t)B * e->M * h * w, n_z = (size_t)B * e->N * hz * wz;
+    const size_t n_sym = (size_t)2 * e->S * B * e->C * h * (w / 2);
+    // staging layout (bytes, 256-aligned): x | x_hat | y_lik | z_lik | sym | idx | z_sym | y | y_hat | rd
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    size_t o_x = take(n_x * 4), o_xh = take(n_x * 4), o_yl = take(n_y * 4), o_zl = take(n_z * 4), o_sym = take(n_sym * 4),
+           o_idx = take(n_sym * 4), o_zs = take(n_z * 4), o_y = take(n_y * 4), o_yh = take(n_y * 4), o_rd = take(16);
+    if (off > e->h_io_bytes) {
+        if (e->h_io) cudaFree(e->h_io);
+        e->h_io = nullptr; e->h_io_bytes = 0;
+        CUDA_OK(cudaMalloc(&e->h_io, off));
+        e->h_io_bytes = off;
+    }
+    uint8_t* d = (uint8_t*)e->h_io;
+    cudaStream_t s = e->h_stream;
+    mlic_buffers dev;
+    memset(&dev, 0, sizeof dev);
+    if (mode != MLIC_MODE_DECODER) {
+        if (!host->x) return fail("x is NULL");
+        CUDA_OK(cudaMemcpyAsync(d + o_x, host->x, n_x * 4, cudaMemcpyHostToDevice, s));
+        dev.x = (const float*)(d + o_x);
+    }
+    const bool want_rd = host->rd_sums && mode == MLIC_MODE_FORWARD;
+    if (host->x_hat || want_rd) dev.x_hat = (float*)(d + o_xh);
+    if (mode == MLIC_MODE_FORWARD) {
+        if (host->y_likelihoods || want_rd) dev.y_likelihoods = (float*)(d + o_yl);
+        if (host->z_likelihoods || want_rd) dev.z_likelihoods = (float*)(d + o_zl);
+        if (want_rd) dev.rd_sums = (double*)(d + o_rd);
+    }
+    if (mode == MLIC_MODE_COMPRESS) {
+        dev.symbols = (int32_t*)(d + o_sym); dev.indexes = (int32_t*)(d + o_idx);
+        if (host->z_symbols) dev.z_symbols = (int32_t*)(d + o_zs);
+    }
+    if (host->y) dev.y = (float*)(d + o_y);
+    if (host->y_hat) dev.y_hat = (float*)(d + o_yh);
+    r = e->run(mode, precision, B, H, W, gain, &dev, e->h_ws, e->h_ws_bytes, s, false);
+    if (r) { cudaStreamSynchronize(s); return r; }
+    if (host->x_hat) CUDA_OK(cudaMemcpyAsync(host->x_hat, dev.x_hat, n_x * 4, cudaMemcpyDeviceToHost, s));
+    if (host->y_likelihoods && dev.y_likelihoods) CUDA_OK(cudaMemcpyAsync(host->y_likelihoods, dev.y_likelihoods, n_y * 4, cudaMemcpyDeviceToHost, s));
+    if (host->z_likelihoods && dev.z_likelihoods) CUDA_OK(cudaMemcpyAsync(host->z_likelihoods, dev.z_likelihoods, n_z * 4, cudaMemcpyDeviceToHost, s));
+    if (host->symbols && dev.symbols) CUDA_OK(cudaMemcpyAsync(host->symbols, dev.symbols, n_sym * 4, cudaMemcpyDeviceToHost, s));
+    if (host->indexes && dev.indexes) CUDA_OK(cudaMemcpyAsync(host->indexes, dev.indexes, n_sym * 4, cudaMemcpyDeviceToHost, s));
+    if (host->z_symbols && dev.z_symbols) CUDA_OK(cudaMemcpyAsync(host->z_symbols, dev.z_symbols, n_z * 4, cudaMemcpyDeviceToHost, s));
+    if (host->y && dev.y) CUDA_OK(cudaMemcpyAsync(host->y, dev.y, n_y * 4, cudaMemcpyDeviceToHost, s));
+    if (host->y_hat && dev.y_hat) CUDA_OK(cudaMemcpyAsync(host->y_hat, dev.y_hat, n_y * 4, cudaMemcpyDeviceToHost, s));
+    if (want_rd) CUDA_OK(cudaMemcpyAsync(host->rd_sums, dev.rd_sums, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, float* y_hat,
+                              float* lik, int32_t* sym, int32_t* idx, void* cuda_stream) {
+    static float* table = nullptr;          // utils/func.py:16-19, fp32
+    if (!table) {
+        float tab[64];
+        const float lo = logf(0.11f), hi = logf(256.0f), step = (hi - lo) / 63.0f;
+        for (int k = 0; k < 64; ++k) tab[k] = expf(k < 32 ? lo + step * (float)k : hi - step * (float)(63 - k));
+        CUDA_OK(cudaMalloc((void**)&table, sizeof tab));
+        CUDA_OK(cudaMemcpy(table, tab, sizeof tab, cudaMemcpyHostToDevice));
+    }
+    launch_gc_flat(y, scales, means, n, y_hat, lik, sym, idx, table, 64, (cudaStream_t)cuda_stream);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

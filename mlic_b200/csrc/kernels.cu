@@ -1,0 +1,923 @@
+// CUDA-core kernels of the MLIC++ engine (sm_100a): the generic implicit-GEMM convolution used in
+// fp32 validation mode and for the GEMM shapes the tcgen05 kernel does not take, the depthwise 3x3
+// stencil, layout conversion, EntropyBottleneck, LocalContext windowed attention, the linear global
+// attention and the fused quantise / likelihood / CDF-index kernels.
+//
+// Reference semantics (paths relative to /root/reference/MLIC++): modules/layers/conv.py:46-63,
+// modules/transform/context.py:67-112,169-193,226-245, utils/ckbd.py:35-73,123-144, and the
+// CompressAI 1.2.6 GaussianConditional / EntropyBottleneck behaviour restated in SURVEY.md A.7/A.8.
+#include "kernels.h"
+
+#include <math.h>
+#include <algorithm>
+
+namespace mlic {
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// Generic implicit-GEMM convolution, fp32 accumulate on CUDA cores.
+//   D[m][n] = sum_k A[m][k] * Wt[n][k],  m = (b,oh,ow),  k = tap*Cin + c  (tap = ky*ks + kx)
+// Tile 128 x 64 x 16, 256 threads, 8x4 micro-tile, register-prefetched double buffering.
+// Every output is one sequential fp32 FMA chain over k in increasing order (deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int GM = 128, GN = 64, GK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const T* __restrict__ in, ConvGeom g,
+                                                             const float* __restrict__ Wt, Epi e, int vec) {
+    __shared__ __align__(16) float As[2][GK][GM + 4];
+    __shared__ __align__(16) float Bs[2][GK][GN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long Mtot = (long long)g.B * g.Hout * g.Wout;
+    const long long m0 = (long long)blockIdx.x * GM;
+    const int n0 = blockIdx.y * GN;
+    const int N = e.N;
+
+    // A loader: two rows per thread (lr, lr+64), 4 consecutive k each.
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    int ab[2], aoh[2], aow[2];
+    bool aval[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        long long m = m0 + lr + r * 64;
+        aval[r] = m < Mtot;
+        long long mm = aval[r] ? m : 0;
+        int hw = g.Hout * g.Wout;
+        ab[r] = (int)(mm / hw);
+        int rem = (int)(mm - (long long)ab[r] * hw);
+        aoh[r] = rem / g.Wout;
+        aow[r] = rem - aoh[r] * g.Wout;
+    }
+    // B loader: one row n per thread (n = n0 + lr), 4 consecutive k.  (GN = 64 rows x 16 k = 256 x 4)
+    const int bn = n0 + lr;
+    const bool bval = bn < N;
+    const bool avec = vec && ((g.Cin & 3) == 0);
+    const bool bvec = (g.Ktot & 3) == 0;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float ra[2][4], rb[4];
+    const int nchunk = (g.Ktot + GK - 1) / GK;
+
+    auto gload = [&](int kc) {
+        const int k0 = kc * GK + lk;
+        // A
+        if (avec) {
+            int tap = k0 / g.Cin;
+            int c = k0 - tap * g.Cin;
+            int ky = tap / g.ks, kx = tap - ky * g.ks;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                ra[r][0] = ra[r][1] = ra[r][2] = ra[r][3] = 0.f;
+                if (aval[r] && k0 < g.Ktot) {
+                    int ih = aoh[r] * g.stride - g.pad + ky;
+                    int iw = aow[r] * g.stride - g.pad + kx;
+                    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+                        const T* p = in + (((size_t)ab[r] * g.H + ih) * g.W + iw) * g.ld + c;
+                        load4(p, ra[r]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = 0.f;
+                    int k = k0 + j;
+                    if (aval[r] && k < g.Ktot) {
+                        int tap = k / g.Cin;
+                        int c = k - tap * g.Cin;
+                        int ky = tap / g.ks, kx = tap - ky * g.ks;
+                        int ih = aoh[r] * g.stride - g.pad + ky;
+                        int iw = aow[r] * g.stride - g.pad + kx;
+                        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                            v = to_f<T>(in[(((size_t)ab[r] * g.H + ih) * g.W + iw) * g.ld + c]);
+                    }
+                    ra[r][j] = v;
+                }
+            }
+        }
+        // B
+        rb[0] = rb[1] = rb[2] = rb[3] = 0.f;
+        if (bval) {
+            const float* wp = Wt + (size_t)bn * g.Ktot + k0;
+            if (bvec && k0 + 3 < g.Ktot) {
+                float4 t = *reinterpret_cast<const float4*>(wp);
+                rb[0] = t.x; rb[1] = t.y; rb[2] = t.z; rb[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k0 + j < g.Ktot) rb[j] = wp[j];
+            }
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[buf][lk + j][lr] = ra[0][j];
+            As[buf][lk + j][lr + 64] = ra[1][j];
+            Bs[buf][lk + j][lr] = rb[j];
+        }
+    };
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kc = 0; kc < nchunk; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < nchunk) gload(kc + 1);
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kc + 1 < nchunk) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+    const int n = n0 + tx * 4;
+    if (n >= N) return;
+    const int hw = g.Hout * g.Wout;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= Mtot) continue;
+        int b = (int)(m / hw);
+        int rem = (int)(m - (long long)b * hw);
+        int h = rem / g.Wout;
+        int w = rem - h * g.Wout;
+        epi_store4<T>(e, b, h, w, n, acc[i], vec != 0);
+    }
+}
+
+void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const float* Wt, const Epi& e, int vec,
+                           cudaStream_t s) {
+    long long Mtot = (long long)g.B * g.Hout * g.Wout;
+    if (Mtot == 0 || e.N == 0) return;
+    dim3 grid(cdiv(Mtot, GM), cdiv(e.N, GN));
+    if (bf) conv_gemm_simt_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, g, Wt, e, vec);
+    else conv_gemm_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)in, g, Wt, e, vec);
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise 3x3 (pad 1, stride 1|2) + bias (+ GELU), NHWC.  HBM-bound: 4 channels per thread,
+// channel-fastest thread order so every warp access is one contiguous 128..512 B segment; the
+// 9-tap reuse is served by L1/L2.  (modules/layers/conv.py:49-54)
+// ------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in, int B, int H, int W, int C, int ild,
+                                                        T* __restrict__ out, int Ho, int Wo, int old,
+                                                        const float* __restrict__ w9, const float* __restrict__ bias,
+                                                        int stride, int act) {
+    const int cg = (C + VEC - 1) / VEC;
+    const long long total = (long long)B * Ho * Wo * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cg) * VEC;
+        long long p = i / cg;
+        int ow = (int)(p % Wo);
+        long long q = p / Wo;
+        int oh = (int)(q % Ho);
+        int b = (int)(q / Ho);
+        float a[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a[j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int ih = oh * stride - 1 + ky;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int iw = ow * stride - 1 + kx;
+                if (iw < 0 || iw >= W) continue;
+                const T* ip = in + (((size_t)b * H + ih) * W + iw) * ild + c;
+                const float* wp = w9 + (ky * 3 + kx) * C + c;
+                if (VEC == 4) {
+                    float x[4];
+                    load4(ip, x);
+                    float4 wv = *reinterpret_cast<const float4*>(wp);
+                    a[0] = fmaf(x[0], wv.x, a[0]);
+                    a[1 % VEC] = fmaf(x[1 % VEC], wv.y, a[1 % VEC]);
+                    a[2 % VEC] = fmaf(x[2 % VEC], wv.z, a[2 % VEC]);
+                    a[3 % VEC] = fmaf(x[3 % VEC], wv.w, a[3 % VEC]);
+                } else {
+                    a[0] = fmaf(to_f<T>(ip[0]), wp[0], a[0]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            a[j] += bias[c + j];
+            if (act == ACT_GELU) a[j] = gelu_erf(a[j]);
+        }
+        T* op = out + (((size_t)b * Ho + oh) * Wo + ow) * old + c;
+        if (VEC == 4) store4(op, a);
+        else op[0] = from_f<T>(a[0]);
+    }
+}
+
+void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act,
+                      cudaStream_t s) {
+    const int esz = bf ? 2 : 4;
+    bool vec = (in.C % 4 == 0) && (in.ld % 4 == 0) && (out.ld % 4 == 0) &&
+               (((uintptr_t)in.p) % (4 * esz) == 0) && (((uintptr_t)out.p) % (4 * esz) == 0);
+    long long total = (long long)out.B * out.H * out.W * (vec ? in.C / 4 : in.C);
+    if (total == 0) return;
+    int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 32);
+#define DW_LAUNCH(T, V)                                                                                             \
+    dwconv3x3_kernel<T, V><<<blocks, 256, 0, s>>>((const T*)in.p, in.B, in.H, in.W, in.C, in.ld, (T*)out.p, out.H, \
+                                                  out.W, out.ld, w9, bias, stride, act)
+    if (bf) { if (vec) DW_LAUNCH(bf16, 4); else DW_LAUNCH(bf16, 1); }
+    else { if (vec) DW_LAUNCH(float, 4); else DW_LAUNCH(float, 1); }
+#undef DW_LAUNCH
+}
+
+// ------------------------------------------------------------------------------------------
+// Layout conversion.  NCHW fp32 <-> NHWC activations through a 32x32 shared-memory transpose so
+// both sides are coalesced.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW, T* __restrict__ dst, int ld) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int c = c0 + j, p = p0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < C && p < HW) ? src[((size_t)b * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int p = p0 + j, c = c0 + threadIdx.x;
+        if (p < HW && c < C) dst[((size_t)b * HW + p) * ld + c] = from_f<T>(tile[threadIdx.x][j]);
+    }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int ld, int C, int HW, float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int p = p0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (p < HW && c < C) ? to_f<T>(src[((size_t)b * HW + p) * ld + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int c = c0 + j, p = p0 + threadIdx.x;
+        if (c < C && p < HW) dst[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][j];
+    }
+}
+
+void launch_nchw_to_nhwc(int bf, const float* src, const Act& dst, int Csrc, cudaStream_t s) {
+    int HW = dst.H * dst.W;
+    if (HW == 0 || dst.B == 0) return;
+    dim3 grid(cdiv(HW, 32), cdiv(Csrc, 32), dst.B), blk(32, 8);
+    if (bf) nchw_to_nhwc_kernel<bf16><<<grid, blk, 0, s>>>(src, Csrc, HW, (bf16*)dst.p, dst.ld);
+    else nchw_to_nhwc_kernel<float><<<grid, blk, 0, s>>>(src, Csrc, HW, (float*)dst.p, dst.ld);
+}
+void launch_nhwc_to_nchw(int bf, const Act& src, float* dst, cudaStream_t s) {
+    int HW = src.H * src.W;
+    if (HW == 0 || src.B == 0) return;
+    dim3 grid(cdiv(HW, 32), cdiv(src.C, 32), src.B), blk(32, 8);
+    if (bf) nhwc_to_nchw_kernel<bf16><<<grid, blk, 0, s>>>((const bf16*)src.p, src.ld, src.C, HW, dst);
+    else nhwc_to_nchw_kernel<float><<<grid, blk, 0, s>>>((const float*)src.p, src.ld, src.C, HW, dst);
+}
+void launch_nhwc_f32_to_nchw(const float* src, int ld, int B, int H, int W, int C, float* dst, cudaStream_t s) {
+    int HW = H * W;
+    if (HW == 0 || B == 0) return;
+    dim3 grid(cdiv(HW, 32), cdiv(C, 32), B), blk(32, 8);
+    nhwc_to_nchw_kernel<float><<<grid, blk, 0, s>>>(src, ld, C, HW, dst);
+}
+
+template <typename TS, typename TD>
+__global__ void copy_channels_kernel(const TS* __restrict__ src, int sld, TD* __restrict__ dst, int dld, int C,
+                                     long long npix) {
+    long long total = npix * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / C;
+        int c = (int)(i - p * C);
+        dst[p * dld + c] = from_f<TD>(to_f<TS>(src[p * sld + c]));
+    }
+}
+void launch_copy_channels(int bf, const Act& src, const Act& dst, cudaStream_t s) {
+    long long npix = (long long)src.B * src.H * src.W;
+    if (npix * src.C == 0) return;
+    int blocks = (int)std::min<long long>(cdiv(npix * src.C, 256), 148LL * 16);
+    if (bf) copy_channels_kernel<bf16, bf16><<<blocks, 256, 0, s>>>((const bf16*)src.p, src.ld, (bf16*)dst.p, dst.ld, src.C, npix);
+    else copy_channels_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)src.p, src.ld, (float*)dst.p, dst.ld, src.C, npix);
+}
+void launch_copy_f32_to_act(int bf, const float* src, int ld, const Act& dst, cudaStream_t s) {
+    long long npix = (long long)dst.B * dst.H * dst.W;
+    if (npix * dst.C == 0) return;
+    int blocks = (int)std::min<long long>(cdiv(npix * dst.C, 256), 148LL * 16);
+    if (bf) copy_channels_kernel<float, bf16><<<blocks, 256, 0, s>>>(src, ld, (bf16*)dst.p, dst.ld, dst.C, npix);
+    else copy_channels_kernel<float, float><<<blocks, 256, 0, s>>>(src, ld, (float*)dst.p, dst.ld, dst.C, npix);
+}
+void launch_fill_zero(void* p, size_t bytes, cudaStream_t s) { if (bytes) cudaMemsetAsync(p, 0, bytes, s); }
+
+// ------------------------------------------------------------------------------------------
+// EntropyBottleneck (CompressAI; call site models/mlicpp.py:96-98), eval mode.
+//   z_hat = round(z - med) + med ;  lik = sigmoid(L(z_hat+.5)) - sigmoid(L(z_hat-.5)), floored at 1e-9
+//   L: 1->3->3->3->3->1 chain, softplus(matrix) and tanh(factor) folded at pack time.
+// packed[c] = { M0[3] , M1[9], M2[9], M3[9], M4[3], b0[3], b1[3], b2[3], b3[3], b4[1], f0[3], f1[3], f2[3], f3[3] }
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float eb_logits(const float* P, float x) {
+    float v[3], t[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float l = P[j] * x + P[33 + j];
+        v[j] = l + P[46 + j] * tanhf(l);
+    }
+#pragma unroll
+    for (int layer = 1; layer < 4; ++layer) {
+        const float* Mx = P + 3 + (layer - 1) * 9;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float l = Mx[j * 3 + 0] * v[0];
+            l = fmaf(Mx[j * 3 + 1], v[1], l);
+            l = fmaf(Mx[j * 3 + 2], v[2], l);
+            l += P[33 + layer * 3 + j];
+            t[j] = l + P[46 + layer * 3 + j] * tanhf(l);
+        }
+        v[0] = t[0]; v[1] = t[1]; v[2] = t[2];
+    }
+    float l = P[30] * v[0];
+    l = fmaf(P[31], v[1], l);
+    l = fmaf(P[32], v[2], l);
+    return l + P[45];
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <typename T>
+__global__ void entropy_bottleneck_kernel(const T* __restrict__ z, int zld, T* __restrict__ zh, int zhld, int C,
+                                          int HW, long long total, const float* __restrict__ packed,
+                                          const float* __restrict__ med, float* __restrict__ lik_nchw,
+                                          int32_t* __restrict__ sym_nchw) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / C;
+        int c = (int)(i - p * C);
+        int b = (int)(p / HW);
+        int hw = (int)(p - (long long)b * HW);
+        float m = med[c];
+        float q = rintf(to_f<T>(z[p * zld + c]) - m);
+        float v = q + m;
+        if (zh) zh[p * zhld + c] = from_f<T>(v);
+        size_t o = ((size_t)b * C + c) * HW + hw;
+        if (sym_nchw) sym_nchw[o] = (int32_t)q;
+        if (lik_nchw) {
+            const float* P = packed + (size_t)c * 58;
+            float lo = eb_logits(P, v - 0.5f), up = eb_logits(P, v + 0.5f);
+            float l = sigmoidf_(up) - sigmoidf_(lo);
+            lik_nchw[o] = fmaxf(l, 1e-9f);
+        }
+    }
+}
+void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const float* packed, const float* medians,
+                               float* z_lik_nchw, int32_t* z_sym_nchw, cudaStream_t s) {
+    long long total = (long long)z.B * z.H * z.W * z.C;
+    if (!total) return;
+    int blocks = cdiv(total, 128);
+    if (bf) entropy_bottleneck_kernel<bf16><<<blocks, 128, 0, s>>>((const bf16*)z.p, z.ld, (bf16*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw);
+    else entropy_bottleneck_kernel<float><<<blocks, 128, 0, s>>>((const float*)z.p, z.ld, (float*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim of an NHWC view (eps 1e-5, affine); one warp per pixel.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, int xld, int C, long long npix, const float* __restrict__ g,
+                                 const float* __restrict__ b, T* __restrict__ out, int old) {
+    const int lane = threadIdx.x & 31;
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = wid; p < npix; p += nw) {
+        float v[4];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = lane + j * 32;
+            v[j] = c < C ? to_f<T>(x[p * xld + c]) : 0.f;
+            sum += v[j];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        float mean = sum / C;
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = lane + j * 32;
+            float d = c < C ? v[j] - mean : 0.f;
+            var += d * d;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        float rstd = rsqrtf(var / C + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = lane + j * 32;
+            if (c < C) out[p * old + c] = from_f<T>((v[j] - mean) * rstd * g[c] + b[c]);
+        }
+    }
+}
+void launch_layernorm(int bf, const Act& x, const float* g, const float* b, const Act& out, cudaStream_t s) {
+    long long npix = (long long)x.B * x.H * x.W;
+    if (!npix) return;
+    int blocks = (int)std::min<long long>(cdiv(npix, 8), 148LL * 16);
+    if (bf) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)x.p, x.ld, x.C, npix, g, b, (bf16*)out.p, out.ld);
+    else layernorm_kernel<float><<<blocks, 256, 0, s>>>((const float*)x.p, x.ld, x.C, npix, g, b, (float*)out.p, out.ld);
+}
+
+// ------------------------------------------------------------------------------------------
+// LocalContext windowed attention (modules/transform/context.py:80-107).
+//   F[pix][3C] fp32: q = [0,C), k = [C,2C), v = [2C,3C); head split on the way in: channel c = dd*2 + hh.
+//   For pixel l, head hh, window taps a,b in 5x5 (zero q/k/v outside the image):
+//     A[a][b] = (q_a*scale).k_b + bias[hh][a][b] + mask(a,b);  mask = 0 iff taps a and b are both in-image anchors
+//     else -100;  P = softmax_b(A);  o[a][hh*d + dd] = sum_b P[a][b] v_b[dd*2+hh]
+//   O[pix][a][c] (activation type) feeds the `fusion` GEMM (K = 25*C).
+// One block = 8x8 pixel tile with a 2-pixel halo of F staged in shared memory; one thread per
+// (pixel, head, query tap) row.
+// ------------------------------------------------------------------------------------------
+constexpr int LT = 8;           // tile side
+constexpr int LTH = LT + 4;     // with halo
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(256) local_attn_kernel(const float* __restrict__ F, int H, int W,
+                                                         const float* __restrict__ rel_bias, T* __restrict__ O) {
+    constexpr int C = 2 * HD;
+    extern __shared__ float sm[];
+    float* sF = sm;                          // [LTH*LTH][3C + 1]
+    float* sB = sm + LTH * LTH * (3 * C + 1);   // [2][25][25]
+    const int b = blockIdx.z;
+    const int h0 = blockIdx.y * LT, w0 = blockIdx.x * LT;
+    const int FS = 3 * C + 1;
+    for (int i = threadIdx.x; i < LTH * LTH * 3 * C; i += blockDim.x) {
+        int f = i % (3 * C);
+        int pp = i / (3 * C);
+        int hh = h0 - 2 + pp / LTH, ww = w0 - 2 + pp % LTH;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = F[(((size_t)b * H + hh) * W + ww) * (3 * C) + f];
+        sF[pp * FS + f] = v;
+    }
+    for (int i = threadIdx.x; i < 2 * 625; i += blockDim.x) sB[i] = rel_bias[i];
+    __syncthreads();
+    const float scale = rsqrtf((float)HD);
+    for (int row = threadIdx.x; row < LT * LT * 2 * 25; row += blockDim.x) {
+        int a = row % 25;
+        int t = row / 25;
+        int hh = t & 1;
+        int pl = t >> 1;
+        int ph = pl / LT, pw = pl % LT;
+        int gh = h0 + ph, gw = w0 + pw;
+        if (gh >= H || gw >= W) continue;
+        int ay = a / 5, ax = a % 5;
+        int qh = gh + ay - 2, qw = gw + ax - 2;
+        bool qanch = qh >= 0 && qh < H && qw >= 0 && qw < W && (((qh + qw) & 1) == 1);
+        const float* qp = sF + ((ph + ay) * LTH + (pw + ax)) * FS;
+        float q[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) q[d] = qp[d * 2 + hh] * scale;
+        float sc[25];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int bb = 0; bb < 25; ++bb) {
+            int by = bb / 5, bx = bb % 5;
+            const float* kp = sF + ((ph + by) * LTH + (pw + bx)) * FS + C;
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) s = fmaf(q[d], kp[d * 2 + hh], s);
+            int kh = gh + by - 2, kw = gw + bx - 2;
+            bool kanch = kh >= 0 && kh < H && kw >= 0 && kw < W && (((kh + kw) & 1) == 1);
+            s += sB[(hh * 25 + a) * 25 + bb];
+            s += (qanch && kanch) ? 0.0f : -100.0f;
+            sc[bb] = s;
+            mx = fmaxf(mx, s);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int bb = 0; bb < 25; ++bb) {
+            sc[bb] = expf(sc[bb] - mx);
+            den += sc[bb];
+        }
+        float inv = 1.0f / den;
+        float o[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+        for (int bb = 0; bb < 25; ++bb) {
+            int by = bb / 5, bx = bb % 5;
+            const float* vp = sF + ((ph + by) * LTH + (pw + bx)) * FS + 2 * C;
+            float p = sc[bb] * inv;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) o[d] = fmaf(p, vp[d * 2 + hh], o[d]);
+        }
+        T* op = O + ((((size_t)b * H + gh) * W + gw) * 25 + a) * C + hh * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            float v4[4] = {o[d], o[d + 1], o[d + 2], o[d + 3]};
+            store4(op + d, v4);
+        }
+    }
+}
+int launch_local_attn(int bf, const float* F, int B, int H, int W, int C, const float* rel_bias, void* O,
+                      cudaStream_t s) {
+    if (B * H * W == 0) return 0;
+    dim3 grid(cdiv(W, LT), cdiv(H, LT), B);
+    size_t smem = (size_t)(LTH * LTH * (3 * C + 1) + 2 * 625) * sizeof(float);
+#define LA_LAUNCH(T, HD)                                                                                      \
+    do {                                                                                                      \
+        cudaFuncSetAttribute(local_attn_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        local_attn_kernel<T, HD><<<grid, 256, smem, s>>>(F, H, W, rel_bias, (T*)O);                           \
+    } while (0)
+    if (C == 32) { if (bf) LA_LAUNCH(bf16, 16); else LA_LAUNCH(float, 16); }
+    else if (C == 64) { if (bf) LA_LAUNCH(bf16, 32); else LA_LAUNCH(float, 32); }
+    else return 1;
+#undef LA_LAUNCH
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Linear (kernelised) global attention (context.py:179-188 intra, :234-240 inter).
+//   qkv NHWC view: Q = [0,D), K = [D,2D), V = [2D,3D); head g owns channels g*hd..g*hd+hd-1.
+//   Khat = softmax over positions (only positions of parity par_kv when set), Qhat = softmax over the hd head
+//   channels per position, ctx[g] = Khat V^T (hd x hd), out = ctx^T Qhat (positions of parity par_q, else 0).
+// Three deterministic passes over a fixed chunking of the positions:
+//   1. per-chunk column max of K                      -> pmax[B][nch][D]
+//   2. per-chunk sum exp(K-max), sum exp(K-max) V^T   -> pctx[B][heads][nch][hd*hd + hd]
+//   3. reduce chunks (fixed order), normalise, apply to softmax_c(Q)
+// ------------------------------------------------------------------------------------------
+constexpr int LA_CH = 64;   // max chunks
+static inline int lin_chunks(int HW) { int n = (HW + 255) / 256; return n < 1 ? 1 : (n > LA_CH ? LA_CH : n); }
+
+size_t lin_attn_scratch_floats(int B, int heads, int hd, int HW) {
+    int nch = lin_chunks(HW);
+    size_t D = (size_t)heads * hd;
+    return (size_t)B * nch * D + (size_t)B * heads * nch * (hd * hd + hd) + (size_t)B * heads * (hd * hd);
+}
+
+template <typename T>
+__global__ void lin_colmax_kernel(const T* __restrict__ qkv, int ld, int D, int H, int W, int nch, int par,
+                                  float* __restrict__ pmax) {
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const int HW = H * W;
+    const int per = (HW + nch - 1) / nch;
+    const int p0 = ch * per, p1 = min(HW, p0 + per);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float m = -INFINITY;
+        for (int p = p0; p < p1; ++p) {
+            if (par != PAR_NONE) {
+                int h = p / W, w = p - h * W;
+                if (!parity_keep(par, h, w)) continue;
+            }
+            m = fmaxf(m, to_f<T>(qkv[((size_t)b * HW + p) * ld + D + c]));
+        }
+        pmax[((size_t)b * nch + ch) * D + c] = m;
+    }
+}
+
+// block = (chunk, head, b); 256 threads; thread t owns ctx entries (c1 = t / (hd/ (hd*hd/256)) ...) generic: loops.
+template <typename T, int HD>
+__global__ void __launch_bounds__(256) lin_ctx_kernel(const T* __restrict__ qkv, int ld, int D, int H, int W, int nch,
+                                                      int par, const float* __restrict__ pmax,
+                                                      float* __restrict__ pctx) {
+    constexpr int TP = 32;               // positions staged per step
+    __shared__ float sE[TP][HD + 1];
+    __shared__ float sV[TP][HD + 1];
+    __shared__ float sMax[HD];
+    const int ch = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const int heads = gridDim.y;
+    const int HW = H * W;
+    const int per = (HW + nch - 1) / nch;
+    const int p0 = ch * per, p1 = min(HW, p0 + per);
+    if (threadIdx.x < HD) {
+        float m = -INFINITY;
+        for (int k = 0; k < nch; ++k) m = fmaxf(m, pmax[((size_t)b * nch + k) * D + g * HD + threadIdx.x]);
+        sMax[threadIdx.x] = m;
+    }
+    __syncthreads();
+    constexpr int PER_T = (HD * HD + 255) / 256;
+    float acc[PER_T];
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) acc[j] = 0.f;
+    float ssum = 0.f;      // threads < HD accumulate sum exp for channel threadIdx.x
+    for (int ps = p0; ps < p1; ps += TP) {
+        for (int i = threadIdx.x; i < TP * HD; i += blockDim.x) {
+            int pp = i / HD, c = i - pp * HD;
+            int p = ps + pp;
+            float e = 0.f, v = 0.f;
+            if (p < p1) {
+                bool keep = true;
+                if (par != PAR_NONE) {
+                    int h = p / W, w = p - h * W;
+                    keep = parity_keep(par, h, w);
+                }
+                if (keep) {
+                    const T* base = qkv + ((size_t)b * HW + p) * ld + g * HD + c;
+                    e = expf(to_f<T>(base[D]) - sMax[c]);
+                    v = to_f<T>(base[2 * D]);
+                }
+            }
+            sE[pp][c] = e;
+            sV[pp][c] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER_T; ++j) {
+            int idx = threadIdx.x + j * 256;
+            if (idx < HD * HD) {
+                int c1 = idx / HD, c2 = idx - c1 * HD;
+                float a = acc[j];
+#pragma unroll 8
+                for (int pp = 0; pp < TP; ++pp) a = fmaf(sE[pp][c1], sV[pp][c2], a);
+                acc[j] = a;
+            }
+        }
+        if (threadIdx.x < HD) {
+            for (int pp = 0; pp < TP; ++pp) ssum += sE[pp][threadIdx.x];
+        }
+        __syncthreads();
+    }
+    float* dst = pctx + (((size_t)b * heads + g) * nch + ch) * (HD * HD + HD);
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+        int idx = threadIdx.x + j * 256;
+        if (idx < HD * HD) dst[idx] = acc[j];
+    }
+    if (threadIdx.x < HD) dst[HD * HD + threadIdx.x] = ssum;
+}
+
+template <int HD>
+__global__ void lin_ctx_reduce_kernel(const float* __restrict__ pctx, int nch, float* __restrict__ ctx) {
+    // block = (head, b); ctx[b][g][c1][c2] = sum_ch pctx / sum_ch S[c1]
+    const size_t bg = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const float* src = pctx + bg * nch * (HD * HD + HD);
+    for (int idx = threadIdx.x; idx < HD * HD; idx += blockDim.x) {
+        int c1 = idx / HD;
+        float a = 0.f, sden = 0.f;
+        for (int k = 0; k < nch; ++k) {
+            a += src[(size_t)k * (HD * HD + HD) + idx];
+            sden += src[(size_t)k * (HD * HD + HD) + HD * HD + c1];
+        }
+        ctx[bg * HD * HD + idx] = a / sden;
+    }
+}
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(128) lin_out_kernel(const T* __restrict__ qkv, int ld, int H, int W, int par_q,
+                                                      const float* __restrict__ ctx, T* __restrict__ out, int old) {
+    __shared__ float sC[HD][HD];
+    const int g = blockIdx.y, b = blockIdx.z;
+    const int heads = gridDim.y;
+    const int HW = H * W;
+    const float* cp = ctx + ((size_t)b * heads + g) * HD * HD;
+    for (int i = threadIdx.x; i < HD * HD; i += blockDim.x) sC[i / HD][i % HD] = cp[i];
+    __syncthreads();
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    T* op = out + ((size_t)b * HW + p) * old + g * HD;
+    bool keep = true;
+    if (par_q != PAR_NONE) {
+        int h = p / W, w = p - h * W;
+        keep = parity_keep(par_q, h, w);
+    }
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    if (keep) {
+        const T* qp = qkv + ((size_t)b * HW + p) * ld + g * HD;
+        float q[HD];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            load4(qp + d, q + d);
+            mx = fmaxf(fmaxf(mx, q[d]), fmaxf(q[d + 1], fmaxf(q[d + 2], q[d + 3])));
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            q[d] = expf(q[d] - mx);
+            den += q[d];
+        }
+        float inv = 1.0f / den;
+#pragma unroll
+        for (int c1 = 0; c1 < HD; ++c1) {
+            float qq = q[c1] * inv;
+#pragma unroll
+            for (int c2 = 0; c2 < HD; ++c2) o[c2] = fmaf(sC[c1][c2], qq, o[c2]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) store4(op + d, o + d);
+}
+
+int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv, int par_q, float* scratch,
+                    const Act& out, cudaStream_t s) {
+    const int B = qkv.B, H = qkv.H, W = qkv.W, HW = H * W;
+    if (B * HW == 0) return 0;
+    const int nch = lin_chunks(HW);
+    float* pmax = scratch;
+    float* pctx = pmax + (size_t)B * nch * D;
+    float* ctx = pctx + (size_t)B * heads * nch * (hd * hd + hd);
+#define LIN_LAUNCH(T, HD)                                                                                          \
+    do {                                                                                                           \
+        lin_colmax_kernel<T><<<dim3(nch, B), 128, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax);    \
+        lin_ctx_kernel<T, HD><<<dim3(nch, heads, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv,   \
+                                                                  pmax, pctx);                                     \
+        lin_ctx_reduce_kernel<HD><<<dim3(heads, B), 256, 0, s>>>(pctx, nch, ctx);                                  \
+        lin_out_kernel<T, HD><<<dim3(cdiv(HW, 128), heads, B), 128, 0, s>>>((const T*)qkv.p, qkv.ld, H, W, par_q,  \
+                                                                            ctx, (T*)out.p, out.ld);               \
+    } while (0)
+    if (hd == 32) { if (bf) LIN_LAUNCH(bf16, 32); else LIN_LAUNCH(float, 32); }
+    else if (hd == 16) { if (bf) LIN_LAUNCH(bf16, 16); else LIN_LAUNCH(float, 16); }
+    else return 1;
+#undef LIN_LAUNCH
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused quantise / likelihood / CDF-index (models/mlicpp.py:117,132-135;
+// utils/ckbd.py:82-90,123-158).  One thread per (pixel, channel), channel-fastest.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cdf_index(float sigma, const float* __restrict__ table, int levels) {
+    float s = fmaxf(sigma, 0.11f);
+    int idx = levels - 1;
+    for (int k = 0; k < levels - 1; ++k) idx -= (s <= table[k]) ? 1 : 0;
+    return idx;
+}
+__device__ __forceinline__ float gauss_lik(float yq, float sigma, float mu) {
+    float s = fmaxf(sigma, 0.11f);
+    float v = fabsf(yq - mu);
+    const float c = -0.70710678118654752440f;
+    float up = 0.5f * erfcf(c * ((0.5f - v) / s));
+    float lo = 0.5f * erfcf(c * ((-0.5f - v) / s));
+    return fmaxf(up - lo, 1e-9f);
+}
+
+template <typename T>
+__global__ void quant_anchor_kernel(QuantArgs a) {
+    const int C = a.C;
+    const long long total = (long long)a.B * a.H * a.W * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / C;
+        int c = (int)(i - p * C);
+        int w = (int)(p % a.W);
+        long long q = p / a.W;
+        int h = (int)(q % a.H);
+        int b = (int)(q / a.H);
+        T* slot = reinterpret_cast<T*>(a.slot.p) + p * a.slot.ld + c;
+        if (((h + w) & 1) == 0) { *slot = from_f<T>(0.f); continue; }
+        const float sigma = a.pa[p * 2 * C + c];
+        const float mu = a.pa[p * 2 * C + C + c];
+        float out;
+        if (a.mode == 2) {
+            out = mu;
+        } else {
+            const float y = a.y[p * a.y_ld + c];
+            if (a.mode == 0) {
+                out = a.vbr ? rintf((y - mu) * a.gain) * a.rgain + mu : rintf(y - mu) + mu;
+            } else {
+                float sq = a.vbr ? rintf((y - mu) - mu) : rintf(y - mu);
+                size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
+                a.sym[o] = (int32_t)sq;
+                a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels);
+                out = a.vbr ? sq * a.rgain + mu : sq + mu;
+            }
+        }
+        *slot = from_f<T>(out);
+    }
+}
+
+template <typename T>
+__global__ void quant_nonanchor_kernel(QuantArgs a) {
+    const int C = a.C;
+    const long long total = (long long)a.B * a.H * a.W * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / C;
+        int c = (int)(i - p * C);
+        int w = (int)(p % a.W);
+        long long q = p / a.W;
+        int h = (int)(q % a.H);
+        int b = (int)(q / a.H);
+        const bool anchor = ((h + w) & 1) == 1;
+        T* slot = reinterpret_cast<T*>(a.slot.p) + p * a.slot.ld + c;
+        const float* pp = anchor ? a.pa : a.pn;
+        const float sigma = pp[p * 2 * C + c];
+        const float mu = pp[p * 2 * C + C + c];
+        if (a.mode == 2) {           // decoder walk: both halves take means_anchor (mlicpp.py:405,418)
+            if (anchor) *slot = from_f<T>(to_f<T>(*slot) + mu);
+            continue;
+        }
+        const float y = a.y[p * a.y_ld + c];
+        if (a.mode == 0) {
+            float lik;
+            if (a.vbr) {
+                float yg = y * a.gain, sg = sigma * a.gain, mg = mu * a.gain;
+                lik = gauss_lik(rintf(yg - mg) + mg, sg, mg);
+            } else {
+                lik = gauss_lik(rintf(y - mu) + mu, sigma, mu);
+            }
+            a.lik[p * a.lik_ld + c] = lik;
+            if (!anchor) *slot = from_f<T>(a.vbr ? rintf((y - mu) * a.gain) * a.rgain + mu : rintf(y - mu) + mu);
+        } else if (!anchor) {
+            float sq = rintf(y - mu);
+            size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
+            a.sym[o] = (int32_t)sq;
+            a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels);
+            *slot = from_f<T>(a.vbr ? sq * a.rgain + mu : sq + mu);
+        }
+    }
+}
+
+void launch_quant_anchor(int bf, const QuantArgs& a, cudaStream_t s) {
+    long long total = (long long)a.B * a.H * a.W * a.C;
+    if (!total) return;
+    int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
+    if (bf) quant_anchor_kernel<bf16><<<blocks, 256, 0, s>>>(a);
+    else quant_anchor_kernel<float><<<blocks, 256, 0, s>>>(a);
+}
+void launch_quant_nonanchor(int bf, const QuantArgs& a, cudaStream_t s) {
+    long long total = (long long)a.B * a.H * a.W * a.C;
+    if (!total) return;
+    int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
+    if (bf) quant_nonanchor_kernel<bf16><<<blocks, 256, 0, s>>>(a);
+    else quant_nonanchor_kernel<float><<<blocks, 256, 0, s>>>(a);
+}
+
+// Stand-alone flat version (any layout, elementwise): the GaussianConditional boundary of the C ABI.
+__global__ void gc_flat_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ mu,
+                               size_t n, float* __restrict__ y_hat, float* __restrict__ lik, int32_t* __restrict__ sym,
+                               int32_t* __restrict__ idx, const float* __restrict__ table, int levels) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float m = mu[i], s = sc[i];
+        float q = rintf(y[i] - m);
+        float yh = q + m;
+        if (y_hat) y_hat[i] = yh;
+        if (lik) lik[i] = gauss_lik(yh, s, m);
+        if (sym) sym[i] = (int32_t)q;
+        if (idx) idx[i] = cdf_index(s, table, levels);
+    }
+}
+void launch_gc_flat(const float* y, const float* sc, const float* mu, size_t n, float* y_hat, float* lik, int32_t* sym,
+                    int32_t* idx, const float* table, int levels, cudaStream_t s) {
+    if (!n) return;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    gc_flat_kernel<<<blocks, 256, 0, s>>>(y, sc, mu, n, y_hat, lik, sym, idx, table, levels);
+}
+
+// ------------------------------------------------------------------------------------------
+// Rate / distortion sums (loss/rd_loss.py:37-48): out[0] += sum log2(lik), out[1] += sum (a-b)^2.
+// Deterministic two-level reduction in double: per-block partials then a single-block final pass.
+// ------------------------------------------------------------------------------------------
+__global__ void reduce_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int mode,
+                                      double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (mode == 0) acc += (double)log2f(a[i]);
+        else { double d = (double)a[i] - (double)b[i]; acc += d * d; }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void reduce_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out += sh[0];
+}
+void launch_reduce(const float* a, const float* b, long long n, int mode, double* partial /*[RD_BLOCKS]*/, double* out,
+                   cudaStream_t s) {
+    if (n <= 0) return;
+    int blocks = (int)std::min<long long>(cdiv(n, 256), RD_BLOCKS);
+    reduce_partial_kernel<<<blocks, 256, 0, s>>>(a, b, n, mode, partial);
+    reduce_final_kernel<<<1, 256, 0, s>>>(partial, blocks, out);
+}
+
+}  // namespace mlic

@@ -1,0 +1,82 @@
+// Host-side launch API of the engine's kernels.  `bf` selects the activation element type
+// (0 = fp32 validation mode, 1 = bf16 fast mode); arithmetic is fp32 everywhere.
+#pragma once
+#include "common.cuh"
+
+namespace mlic {
+
+struct ConvGeom {
+    int B, H, W, Cin, ld;       // input view
+    int Hout, Wout;
+    int ks, stride, pad;
+    int Ktot;                   // row length of the fp32 weight matrix [N][Ktot], Ktot = ks*ks*Cin
+};
+
+// ---- CUDA-core kernels (kernels.cu) ----
+void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const float* Wt, const Epi& e, int vec,
+                           cudaStream_t s);
+void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act,
+                      cudaStream_t s);
+void launch_nchw_to_nhwc(int bf, const float* src, const Act& dst, int Csrc, cudaStream_t s);
+void launch_nhwc_to_nchw(int bf, const Act& src, float* dst, cudaStream_t s);
+void launch_nhwc_f32_to_nchw(const float* src, int ld, int B, int H, int W, int C, float* dst, cudaStream_t s);
+void launch_copy_channels(int bf, const Act& src, const Act& dst, cudaStream_t s);
+void launch_copy_f32_to_act(int bf, const float* src, int ld, const Act& dst, cudaStream_t s);
+void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
+
+// EntropyBottleneck: z (NHWC act) -> z_hat (NHWC act), z_lik (fp32 NCHW), z_sym (int32 NCHW, optional)
+void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const float* packed /*[N][58]*/,
+                               const float* medians, float* z_lik_nchw, int32_t* z_sym_nchw, cudaStream_t s);
+
+// LocalContext windowed attention: F[pix][3C] fp32 (q|k|v) -> O[pix][25][C] (activation type); C = 32 or 64.
+// returns non-zero for an unsupported C.
+int launch_local_attn(int bf, const float* F, int B, int H, int W, int C, const float* rel_bias /*[2][25][25]*/,
+                      void* O, cudaStream_t s);
+void launch_layernorm(int bf, const Act& x, const float* g, const float* b, const Act& out, cudaStream_t s);
+
+// Linear (kernelised) global attention: K softmax over positions, Q softmax over head channels.
+//   qkv view: channels [0,D) = Q, [D,2D) = K, [2D,3D) = V.  par_kv / par_q: parity filters (intra context).
+size_t lin_attn_scratch_floats(int B, int heads, int hd, int HW);
+int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv, int par_q, float* scratch,
+                    const Act& out, cudaStream_t s);      // non-zero: unsupported head dim
+
+// Fused quantise / likelihood / CDF-index kernels.
+struct QuantArgs {
+    const float* y; int y_ld;       // latent slice (fp32 NHWC view at channel i*C)
+    const float* pa;                // anchor entropy parameters [pix][2C] (scales | means), fp32
+    const float* pn;                // non-anchor entropy parameters [pix][2C] (may be null in the anchor pass)
+    Act slot;                       // y_hat slice i inside the LRP/concat workspace (activation type)
+    int B, H, W, C;
+    int mode;                       // 0 forward, 1 compress, 2 decoder walk
+    int vbr; float gain, rgain;     // VBR: gain g and 1/g as computed on the host in fp32
+    float* lik; int lik_ld;         // forward: likelihood slice inside the fp32 NHWC [pix][M] buffer
+    int32_t* sym; int32_t* idx;     // compress: base of this half-slice (flattened over [B,C,H,W/2])
+    const float* table; int levels; // scale table (fp32, as stored in gaussian_conditional.scale_table)
+};
+void launch_quant_anchor(int bf, const QuantArgs& a, cudaStream_t s);
+void launch_quant_nonanchor(int bf, const QuantArgs& a, cudaStream_t s);
+
+void launch_gc_flat(const float* y, const float* scales, const float* means, size_t n, float* y_hat, float* lik,
+                    int32_t* sym, int32_t* idx, const float* table, int levels, cudaStream_t s);
+
+// Rate/distortion sums: mode 0: *out += sum log2(a[i]) ; mode 1: *out += sum (a[i]-b[i])^2  (double, deterministic)
+constexpr int RD_BLOCKS = 1024;
+void launch_reduce(const float* a, const float* b, long long n, int mode, double* partial /*[RD_BLOCKS]*/, double* out,
+                   cudaStream_t s);
+
+// ---- tcgen05 / TMA implicit-GEMM convolution (gemm_tc.cu), bf16 activations only ----
+struct TcConv {
+    const void* in;             // bf16 NHWC view base
+    int B, H, W, Cin, ld;       // input view as the conv sees it (for a stride-2 1x1: the sub-sampled grid)
+    int sW, sH, sB;             // element strides of the W / H / B dims of that view
+    int ks, pad;                // stride-1 taps around the output pixel
+    const void* w;              // bf16 [N][ks*ks*Cpad], Cpad = roundup(Cin,64), zero padded per tap
+    int Cpad;
+};
+bool tc_conv_supported(const TcConv& c, const Epi& e);
+// returns cudaError_t-like int (0 ok)
+int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s);
+int tc_init();                   // resolves cuTensorMapEncodeTiled; 0 on success
+const char* tc_last_error();
+
+}  // namespace mlic

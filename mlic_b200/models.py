@@ -1,0 +1,364 @@
+"""Drop-in model API of the reference (MLIC++/models/model_loader.py:4-18): `get_model(name)` returns an
+nn.Module with the reference's state_dict (same dotted names and shapes) whose forward / compress /
+net_decoder_forward run on the B200 engine (libmlic_b200.so, hand-written sm_100a kernels) through the
+C ABI in include/mlic_b200.h.  There is no PyTorch or CPU compute path behind these methods.
+
+Reference methods mirrored (paths relative to /root/reference/MLIC++):
+  forward              models/mlicpp.py:79-185   (VBR: models/mlicpp_vbr.py:137-336)
+  compress             models/mlicpp.py:199-290  (network walk; the rANS coder stays a host component)
+  net_decoder_forward  models/mlicpp.py:380-459
+  update / load_state_dict / update_resolutions   models/mlicpp.py:187-197,461-475
+"""
+import ctypes as C
+import math
+import time
+import types
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .params import KIND_CODE, MODEL_TABLE, VBR_GAINS, VBR_LAMBDAS, build_entries
+
+
+def model_config(name):
+    """config/config.py:19-62 (context_window / act are carried for API parity; the engine fixes them)."""
+    cfg = MODEL_TABLE[name]
+    return types.SimpleNamespace(N=cfg["N"], M=cfg["M"], slice_num=cfg["slice_num"], context_window=5, act=nn.GELU)
+
+
+def get_scale_table(min=0.11, max=256, levels=64):  # noqa: A002  (utils/func.py:16-19)
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+def _relpos_index(ws=5):
+    """modules/layers/attention.py:28-38"""
+    ch, cw = torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")
+    co = torch.stack([ch, cw]).flatten(1)
+    rel = (co[:, :, None] - co[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1)
+
+
+def _init_tensor(entry):
+    kind, arg = entry.init
+    shape = entry.shape
+    dt = {"float32": torch.float32, "int32": torch.int32, "int64": torch.int64}[entry.dtype]
+    if kind == "uniform_fan":
+        b = 1.0 / math.sqrt(arg) if arg else 0.05
+        return (torch.rand(shape) * 2 - 1) * b
+    if kind == "uniform":
+        return (torch.rand(shape) * 2 - 1) * arg
+    if kind == "const":
+        return torch.full(shape, float(arg), dtype=dt)
+    if kind == "gdn_gamma":
+        return torch.sqrt(0.1 * torch.eye(shape[0]) + 2.0 ** -36)
+    if kind == "eb_quantiles":
+        return torch.tensor([-10.0, 0.0, 10.0]).repeat(shape[0], 1, 1)
+    if kind == "eb_target":
+        t = math.log(2 / 1e-9 - 1)
+        return torch.tensor([-t, 0.0, t])
+    if kind == "eb_matrix":
+        scale = 10.0 ** (1.0 / 5.0)
+        return torch.full(shape, math.log(math.expm1(1.0 / scale / arg)))
+    if kind == "trunc_normal":
+        return nn.init.trunc_normal_(torch.zeros(shape), std=arg)
+    if kind == "relpos_index":
+        return _relpos_index(5)
+    if kind == "vbr_gain":
+        return torch.tensor(VBR_GAINS, dtype=torch.float32)
+    if kind == "empty":
+        return torch.zeros(shape, dtype=dt)
+    raise ValueError(kind)
+
+
+class _Tree(nn.Module):
+    """Generic container: gives the parameter tree the reference's attribute / index structure."""
+
+    def __getitem__(self, i):
+        return self._modules[str(i)]
+
+    def __len__(self):
+        return len(self._modules)
+
+
+class MLICPlusPlus(nn.Module):
+    """B200 engine behind the reference's MLICPlusPlus interface (models/mlicpp.py:12-76)."""
+
+    KIND = "base"
+
+    def __init__(self, config, name=None, **kwargs):
+        super().__init__()
+        self.N, self.M = int(config.N), int(config.M)
+        self.slice_num = int(config.slice_num)
+        self.context_window = getattr(config, "context_window", 5)
+        self.slice_ch = self.M // self.slice_num
+        assert self.slice_ch * self.slice_num == self.M          # models/mlicpp.py:21
+        self.model_name = name or self._name_for(config)
+        self.precision = "bf16"          # "bf16" fast mode | "fp32" validation mode
+        self.tensor_cores = True
+        for key, ent in build_entries(self.model_name).items():
+            self._place(key, _init_tensor(ent), ent.is_param)
+        # attributes the reference exposes on sub-modules
+        for i in range(self.slice_num):
+            lc = self.local_context[i]
+            lc.attn_mask, lc.H, lc.W = None, -1, -1
+        self._engine = None
+        self._engine_sig = None
+        self._ws = {}
+        self.last_launch_count = 0
+
+    def _name_for(self, config):
+        for nm, cfg in MODEL_TABLE.items():
+            if (cfg["N"], cfg["M"], cfg["slice_num"], cfg["kind"]) == (self.N, self.M, self.slice_num, self.KIND):
+                return nm
+        raise ValueError("no registered MLIC++ configuration matches this config")
+
+    def _place(self, key, tensor, is_param):
+        parts = key.split(".")
+        mod = self
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, _Tree())
+            mod = mod._modules[p]
+        if is_param:
+            mod.register_parameter(parts[-1], nn.Parameter(tensor))
+        else:
+            mod.register_buffer(parts[-1], tensor)
+
+    # ------------------------------------------------------------------ state handling
+    def load_state_dict(self, state_dict, strict=True):
+        """models/mlicpp.py:461-468: CDF buffers are resized to the checkpoint's before loading."""
+        own = dict(self.named_buffers())
+        for k in ("_quantized_cdf", "_offset", "_cdf_length", "scale_table"):
+            for pre in ("gaussian_conditional.", "entropy_bottleneck."):
+                full = pre + k
+                if full in state_dict and full in own and own[full].shape != state_dict[full].shape:
+                    own[full].resize_(state_dict[full].shape)
+        out = super().load_state_dict(state_dict, strict=strict)
+        self._engine_sig = None
+        return out
+
+    def update(self, scale_table=None, force=False):
+        """models/mlicpp.py:470-475.  Populates gaussian_conditional.scale_table; the quantised CDF tables that
+        only the host rANS coder reads are not rebuilt here (coder is out of this path's scope)."""
+        if scale_table is None:
+            scale_table = get_scale_table()
+        gc = self.gaussian_conditional
+        if not force and gc.scale_table.numel() == len(scale_table):
+            return False
+        gc.scale_table.resize_(len(scale_table))
+        gc.scale_table.copy_(torch.as_tensor(scale_table, dtype=torch.float32))
+        self._engine_sig = None
+        return True
+
+    def update_resolutions(self, H, W, device=None):
+        """models/mlicpp.py:187-197.  The engine evaluates the checkerboard window mask analytically, so there is
+        no [L,25,25] tensor to rebuild; the cached grid size is recorded for API parity."""
+        for i in range(self.slice_num):
+            self.local_context[i].H, self.local_context[i].W = H, W
+
+    def aux_loss(self):
+        """CompressAI CompressionModel.aux_loss: sum |logits_cumulative(quantiles) - target| (training-side helper,
+        plain torch on the parameters; not part of the forward hot path)."""
+        eb = self.entropy_bottleneck
+        logits = eb.quantiles
+        for i in range(5):
+            logits = torch.matmul(nn.functional.softplus(getattr(eb.matrices, str(i))), logits) + getattr(eb.biases, str(i))
+            if i < 4:
+                logits = logits + torch.tanh(getattr(eb.factors, str(i))) * torch.tanh(logits)
+        return torch.abs(logits - eb.target).sum()
+
+    def set_precision(self, precision):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        return self
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _signature(self):
+        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+
+    def _sync_engine(self, device):
+        if not torch.cuda.is_available():
+            raise _lib.MlicError("mlic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        L = _lib.lib()
+        sig = (str(device), self._signature())
+        if self._engine is not None and sig == self._engine_sig:
+            return L
+        if self._engine is None:
+            h = C.c_void_p()
+            _lib.check(L.mlic_engine_create(self.N, self.M, self.slice_num, KIND_CODE[self.KIND], C.byref(h)))
+            self._engine = h
+        with torch.cuda.device(device):
+            for k, v in self.state_dict().items():
+                t = v.detach().to("cpu", torch.float32).contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                _lib.check(L.mlic_engine_set_param(self._engine, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+            _lib.check(L.mlic_engine_finalize(self._engine))
+        self._engine_sig = sig
+        return L
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None) is not None:
+                _lib.lib().mlic_engine_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+    def _gain(self, stage, s, inputscale, absolute=False):
+        return 0.0
+
+    def _run(self, mode, x, B, H, W, gain=0.0, want=()):
+        """One engine call.  x: CUDA tensor (device path) or CPU tensor (host path through mlic_run_host)."""
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (the reference pads, utils/testing.py:130-137)")
+        host = x is not None and not x.is_cuda
+        dev = torch.device("cuda", torch.cuda.current_device()) if (host or x is None) else x.device
+        L = self._sync_engine(dev)
+        _lib.check(L.mlic_engine_set_option(self._engine, b"tensor_cores", 1 if self.tensor_cores else 0))
+        prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        odev = "cpu" if host else dev
+        h, w, hz, wz = H // 16, W // 16, H // 64, W // 64
+        out = {}
+        buf = _lib.Buffers()
+        if x is not None:
+            x = x.detach().to(torch.float32).contiguous()
+            buf.x = x.data_ptr()
+
+        def new(name, shape, dtype=torch.float32):
+            t = torch.empty(shape, dtype=dtype, device=odev, pin_memory=host)
+            out[name] = t
+            setattr(buf, name, t.data_ptr())
+
+        new("x_hat", (B, 3, H, W))
+        if mode == _lib.MODE_FORWARD:
+            new("y_likelihoods", (B, self.M, h, w))
+            new("z_likelihoods", (B, self.N, hz, wz))
+            if "rd_sums" in want:
+                new("rd_sums", (2,), torch.float64)
+        if mode == _lib.MODE_COMPRESS:
+            n = 2 * self.slice_num * B * self.slice_ch * h * (w // 2)
+            new("symbols", (n,), torch.int32)
+            new("indexes", (n,), torch.int32)
+            new("z_symbols", (B, self.N, hz, wz), torch.int32)
+        for tap in ("y", "y_hat"):
+            if tap in want:
+                new(tap, (B, self.M, h, w))
+        with torch.cuda.device(dev):
+            if host:
+                _lib.check(L.mlic_run_host(self._engine, mode, prec, B, H, W, float(gain), C.byref(buf), 1))
+            else:
+                need = C.c_size_t()
+                _lib.check(L.mlic_workspace_bytes(self._engine, mode, prec, B, H, W, C.byref(need)))
+                key = str(dev)
+                ws = self._ws.get(key)
+                if ws is None or ws.numel() < need.value:
+                    self._ws[key] = ws = None
+                    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+                    self._ws[key] = ws
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                _lib.check(L.mlic_run(self._engine, mode, prec, B, H, W, float(gain), C.byref(buf), C.c_void_p(ws.data_ptr()),
+                                      ws.numel(), C.c_void_p(stream)))
+        self.last_launch_count = int(L.mlic_last_launch_count(self._engine))
+        return out
+
+    # ------------------------------------------------------------------ the reference's public methods
+    @torch.no_grad()
+    def forward(self, x, *, taps=()):
+        """models/mlicpp.py:79-185 -> {"x_hat", "likelihoods": {"y_likelihoods", "z_likelihoods"}}"""
+        B, _, H, W = x.shape
+        self.update_resolutions(H // 16, W // 16)
+        o = self._run(_lib.MODE_FORWARD, x, B, H, W, 0.0, taps)
+        res = {"x_hat": o["x_hat"], "likelihoods": {"y_likelihoods": o["y_likelihoods"], "z_likelihoods": o["z_likelihoods"]}}
+        res.update({k: o[k] for k in taps})
+        return res
+
+    @torch.no_grad()
+    def compress(self, x, *, taps=()):
+        """models/mlicpp.py:199-290 up to the entropy coder: returns the coder's inputs (`symbols`, `indexes`: flat
+        int32 in the reference's list order A0,N0,A1,N1,...; `z_symbols`) instead of byte strings, plus `x_hat`."""
+        t0 = time.time()
+        B, _, H, W = x.shape
+        self.update_resolutions(H // 16, W // 16)
+        o = self._run(_lib.MODE_COMPRESS, x, B, H, W, 0.0, taps)
+        if x.is_cuda:
+            torch.cuda.synchronize(x.device)
+        o.update(strings=None, shape=(H // 64, W // 64), cost_time=time.time() - t0)
+        return o
+
+    def decompress(self, strings, shape, **kwargs):
+        """models/mlicpp.py:292-378 needs the host rANS decoder inside the slice loop."""
+        raise NotImplementedError("decompress() needs the CompressAI rANS decoder in the loop; the network walk it "
+                                  "performs is available as net_decoder_forward()")
+
+    @torch.no_grad()
+    def net_decoder_forward(self, x):
+        """models/mlicpp.py:380-459: decoder-side network walk (z_hat = 0); x is used for its shape only."""
+        B, _, H, W = x.shape
+        self.update_resolutions(H // 16, W // 16)
+        if x.is_cuda:
+            with torch.cuda.device(x.device):
+                o = self._run(_lib.MODE_DECODER, None, B, H, W, 0.0)
+            return o["x_hat"]
+        raise _lib.MlicError("net_decoder_forward expects a CUDA tensor (its values are not read)")
+
+
+class MLICPlusPlusSD(MLICPlusPlus):
+    """models/mlicpp_small_decoder.py:16-83 (dense encoder, quarter-width decoder)."""
+    KIND = "sd"
+
+
+class MLICPlusPlusVbr(MLICPlusPlus):
+    """models/mlicpp_vbr.py:14-117: 6 gain levels, stage-2 gain-scaled quantisation (no_quantoffset=True)."""
+    KIND = "vbr"
+
+    def __init__(self, config, name=None, **kwargs):
+        super().__init__(config, name=name, **kwargs)
+        self.lmbda = list(VBR_LAMBDAS)
+        self.levels = len(self.lmbda)
+        self.no_quantoffset = True
+        self.vr_entbttlnck = None
+
+    def _scale(self, s, inputscale, absolute):
+        if inputscale != 0:
+            return float(inputscale)
+        if absolute:                                   # mlicpp_vbr.py:540-543
+            assert s in range(0, self.levels), f"s should in range(0, {self.levels}), but get s:{s}"
+            return abs(float(self.Gain[s]))
+        s = max(0, min(int(s), self.Gain.numel() - 1))  # mlicpp_vbr.py:122-135
+        return float(self.Gain[s])
+
+    @torch.no_grad()
+    def forward(self, x, stage=2, s=1, inputscale=0, *, taps=()):
+        if stage not in (1, 2):
+            raise ValueError(f"Invalid stage (stage={stage}) parameter for this model.")     # mlicpp_vbr.py:119-120
+        B, _, H, W = x.shape
+        gain = self._scale(s, inputscale, False) if stage == 2 else 0.0
+        o = self._run(_lib.MODE_FORWARD, x, B, H, W, gain, taps)
+        res = {"x_hat": o["x_hat"], "likelihoods": {"y_likelihoods": o["y_likelihoods"], "z_likelihoods": o["z_likelihoods"]}}
+        res.update({k: o[k] for k in taps})
+        return res
+
+    @torch.no_grad()
+    def compress(self, x, stage=2, s=1, inputscale=0, *, taps=()):
+        t0 = time.time()
+        B, _, H, W = x.shape
+        o = self._run(_lib.MODE_COMPRESS, x, B, H, W, self._scale(s, inputscale, True), taps)
+        if x.is_cuda:
+            torch.cuda.synchronize(x.device)
+        o.update(strings=None, shape=(H // 64, W // 64), cost_time=time.time() - t0)
+        return o
+
+
+_CLASSES = {"base": MLICPlusPlus, "sd": MLICPlusPlusSD, "vbr": MLICPlusPlusVbr}
+
+
+def get_model(name):
+    """models/model_loader.py:4-18 (+ MLICPP_L_VBR, which BASELINE.json names)."""
+    if name not in MODEL_TABLE:
+        raise KeyError(f"unknown model '{name}'; known: {sorted(MODEL_TABLE)}")
+    return _CLASSES[MODEL_TABLE[name]["kind"]](model_config(name), name=name)

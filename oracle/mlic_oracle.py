@@ -103,7 +103,7 @@ class Oracle:
         self.N, self.M, self.S = cfg["N"], cfg["M"], cfg["slices"]
         self.C = self.M // self.S
         self.dtype = dtype
-        self.w = {k: (v.detach().to(dtype) if torch.is_floating_point(v) else v.detach())
+        self.w = {k: (v.detach().cpu().to(dtype) if torch.is_floating_point(v) else v.detach().cpu())
                   for k, v in state_dict.items()}
         self.table = scale_table()
         self.trace = None
