@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""Headline benchmark: megapixels/s of MLICPP_L forward (g_a + h_a + EB + h_s + 10-slice entropy model + g_s ->
+x_hat, y/z likelihoods) on synthetic 1920x1088 images (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's engine (bf16 fast mode, tcgen05 GEMMs)
+    python bench.py --impl reference ...                     # the reference's CPU forward (oracle port) on host cores
+
+One process per GPU (torchrun for N > 1); images are sharded by batch (weak scaling, no data-path collective; one
+NCCL all-reduce carries the aggregate rate/distortion sums).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 1088, 1920
+MP_PER_IMAGE = 1920 * 1088 / 1e6
+MODEL = "MLICPP_L"
+FLOP_PER_IMAGE = 1.753e12          # 876.4 GMAC per 1920x1088 image
+METRIC = "megapixels/sec MLICPP_L forward @1920x1088"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def seeded_model(name, device=None):
+    import mlic_b200
+    from oracle import weights              # deterministic weights only (bench's checker / baseline leg)
+    net = mlic_b200.get_model(name)
+    sd = weights.seeded_state_dict(net.state_dict(), 1234)
+    net.load_state_dict(sd)
+    net.update(force=True)
+    return net.to(device) if device is not None else net
+
+
+def cpu_forward_mps(sample_hw, runs, threads):
+    """Oracle (CPU restatement of the reference forward) on `threads` host threads -> MP/s on one image of sample_hw."""
+    from oracle import mlic_oracle, weights
+    torch.set_num_threads(threads)
+    net = seeded_model(MODEL)
+    orc = mlic_oracle.Oracle(MODEL, net.state_dict())
+    h, w = sample_hw
+    x = weights.synthetic_image(1, h, w, seed=2024, kind="rand")
+    times = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        orc.forward(x)
+        times.append(time.perf_counter() - t0)
+    return (h * w / 1e6) / min(times), times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    # bounded sample: probe throughput on 256x256, then pick the largest crop that keeps the run within ~150 s
+    probe, _ = cpu_forward_mps((256, 256), 1, threads)
+    budget = 150.0 / max(total, 1)
+    cands = [(1088, 1920), (576, 1920), (576, 960), (512, 512), (256, 256)]
+    hw = cands[-1]
+    for c in cands:
+        if (c[0] * c[1] / 1e6) / probe * 1.3 <= budget:
+            hw = c
+            break
+    from oracle import mlic_oracle, weights
+    net = seeded_model(MODEL)
+    orc = mlic_oracle.Oracle(MODEL, net.state_dict())
+    x = weights.synthetic_image(1, hw[0], hw[1], seed=2024, kind="rand")
+    for _ in range(args.warmup):
+        orc.forward(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.forward(x)
+    dt = time.perf_counter() - t0
+    mps = args.steps * (hw[0] * hw[1] / 1e6) / dt
+    sample = f"1 image {hw[1]}x{hw[0]} per step (crop of the 1920x1088 workload), fp32, torch CPU, {threads} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": mps, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MLICPP_L forward 1920x1088 (configs[1])", "sample": sample},
+            "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="images per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oracle import weights
+    net = seeded_model(MODEL, dev).set_precision(args.precision)
+    B = args.batch
+    # every rank gets its own images (seeded by global image index): weak scaling, batch shard
+    x_host = weights.synthetic_image(B, H, W, seed=2024 + rank * B, kind="rand").pin_memory()
+    x = x_host.to(dev, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = net(x)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    net.set_profile(True)
+    net.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = net(x)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tc_ms, tc_flops, tc_launches = net.profile_read(reset=True)
+    net.set_profile(False)
+    launches = net.last_launch_count * args.steps
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps * MP_PER_IMAGE / (ms / 1e3)
+
+    # aggregate rate / distortion (the only collective on the path: 3 numbers)
+    npx = B * H * W
+    stats = torch.tensor([float(torch.log2(out["likelihoods"]["y_likelihoods"].double()).sum() +
+                                torch.log2(out["likelihoods"]["z_likelihoods"].double()).sum()),
+                          float(((out["x_hat"].double() - x.double()) ** 2).sum()), float(npx)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats)
+    bpp = -float(stats[0]) / float(stats[2])
+    mse = float(stats[1]) / (3 * float(stats[2]))
+
+    # end to end through the public API with HOST buffers: pinned x -> H2D -> forward -> D2H of x_hat and likelihoods
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            net(x_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            o = net(x_host)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        d2h = sum(v.numel() * v.element_size() for v in (o["x_hat"], o["likelihoods"]["y_likelihoods"], o["likelihoods"]["z_likelihoods"]))
+        e2e = {"value": world * B * args.steps * MP_PER_IMAGE / dt, "unit": "MP/s",
+               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": d2h}
+
+    if rank == 0:
+        pk = peaks()
+        tc_tflops = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel (tcgen05 implicit GEMM, all conv / 1x1 / GDN GEMMs of the step)",
+                "achieved": tc_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tc_tflops / pk["tf_sust"],
+                "peak_source": pk["src"] + " bf16_tflops_sustained", "traffic": None,
+                "launches": tc_launches, "kernel_ms_per_step": tc_ms / max(args.steps, 1),
+                "share_of_step": tc_ms / ms if ms > 0 else None,
+                "whole_step_tflops": world * B * args.steps * FLOP_PER_IMAGE / (ms * 1e-3) / 1e12 / world}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            mps, times = cpu_forward_mps((576, 960), 1, threads)
+            cpu = {"value": mps, "unit": "MP/s", "cores": threads, "kind": "port",
+                   "sample": f"1 image 960x576 (crop of the 1920x1088 workload), 1 run of {times[0]:.1f} s, fp32 torch CPU"}
+        line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "MLICPP_L forward 1920x1088 (BASELINE configs[1])", "images_per_gpu_per_step": B,
+                           "global_batch": B * world, "parallelism": f"batch-shard x{world}", "weights": "random-init seed 1234",
+                           "l2": "per-step inputs + activations (>1 GB/image) exceed the 126 MB L2; no explicit flush"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "quality": {"bpp": bpp, "mse": mse}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,7 +54,8 @@ int mlic_engine_set_param(mlic_engine* e, const char* name, const float* host_da
  * set_param and again after any parameter change; replaces update() (models/mlicpp.py:470-475). */
 int mlic_engine_finalize(mlic_engine* e);
 
-/* Knobs: name = "tensor_cores" (1 = tcgen05 implicit-GEMM in bf16 mode [default], 0 = CUDA-core GEMM only). */
+/* Knobs: "tensor_cores" (1 = tcgen05 implicit-GEMM in bf16 mode [default], 0 = CUDA-core GEMM only);
+ *        "profile" (1 = bracket every tcgen05 GEMM launch with a CUDA-event pair on the launch stream). */
 int mlic_engine_set_option(mlic_engine* e, const char* name, int value);
 
 /* Device workspace needed by one call of the given mode / precision / shape. */
@@ -76,6 +77,20 @@ int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, 
 
 /* Number of kernels the engine launched in the last mlic_run / mlic_run_host call. */
 int64_t mlic_last_launch_count(const mlic_engine* e);
+
+/* Live profile of the dominant kernel (the tcgen05 implicit GEMM) since the last reset:
+ * out3 = { summed launch duration in ms, summed algorithmic FLOPs (2*M*N*K), launches }.  Synchronises. */
+int mlic_profile_read(mlic_engine* e, double* out3, int reset);
+
+/* Stand-alone convolution on an NHWC activation tensor (fp32 or bf16 per `precision`; weights / bias are HOST
+ * fp32 in the reference's nn.Conv2d layout [N][Cin][ks][ks]): out = act(conv(in) + bias) (+ residual), optionally
+ * pixel-shuffled by 2 (CompressAI subpel_conv3x3).  tensor_cores = 1 selects the tcgen05 implicit-GEMM kernel where
+ * it applies, 0 the CUDA-core kernel.  Runs `iters` launches and reports the average duration of launches 2..iters
+ * (CUDA events); synchronises.  Kernel-level test / micro-benchmark hook for nn.Conv2d call sites such as
+ * modules/layers/conv.py:55-60 and res_blk.py:107-111. */
+int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int H, int W, int Cin, const float* weight,
+                     const float* bias, int N, int ks, int stride, int pad, int act, int shuffle, const void* residual,
+                     void* out, int iters, float* avg_ms, void* cuda_stream);
 
 /* Stand-alone fused quantise / likelihood / CDF-index kernel on NCHW fp32 device tensors of one slice
  * (CompressAI GaussianConditional.forward / quantize / build_indexes; call sites models/mlicpp.py:132-134,

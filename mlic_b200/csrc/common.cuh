@@ -35,6 +35,7 @@ struct Epi {
     int shuffle;            // 0 | 1: PixelShuffle(2); GEMM column n' = (2r+s)*Cq + c  (weights permuted at pack time)
     void* out; int out_ld;
     int out_f32;            // 1: `out` is float* even when activations are bf16 (y, entropy parameters)
+    int nchw;               // 1 (with out_f32): `out` is a dense fp32 NCHW tensor [B][C][OH][OW] (x_hat); scalar stores
     void* out2; int out2_ld;
     int Hout, Wout, N;      // GEMM-space output grid and column count
 };
@@ -109,7 +110,7 @@ __device__ __forceinline__ void epi_store4(const Epi& e, int b, int h, int w, in
         if (!keep_post) a = 0.0f;
         v[j] = a;
     }
-    if (!straddle && n + 3 < e.N) {
+    if (!straddle && n + 3 < e.N && !e.nchw) {
         const size_t opix = ((size_t)b * OH + oh) * OW + ow;
         if (e.res) {
             const T* rp = reinterpret_cast<const T*>(e.res) + opix * e.res_ld + oc;
@@ -150,7 +151,10 @@ __device__ __forceinline__ void epi_store4(const Epi& e, int b, int h, int w, in
             const size_t opix = ((size_t)b * OH + ohj) * OW + owj;
             float a = v[j];
             if (e.res) a += to_f<T>(reinterpret_cast<const T*>(e.res)[opix * e.res_ld + ocj]);
-            if (e.out_f32) reinterpret_cast<float*>(e.out)[opix * e.out_ld + ocj] = a;
+            if (e.nchw) {
+                const int Cc = e.shuffle ? (e.N >> 2) : e.N;
+                reinterpret_cast<float*>(e.out)[(((size_t)b * Cc + ocj) * OH + ohj) * OW + owj] = a;
+            } else if (e.out_f32) reinterpret_cast<float*>(e.out)[opix * e.out_ld + ocj] = a;
             else reinterpret_cast<T*>(e.out)[opix * e.out_ld + ocj] = from_f<T>(a);
             if (e.out2) reinterpret_cast<T*>(e.out2)[opix * e.out2_ld + ocj] = from_f<T>(a * a);
         }

@@ -70,6 +70,7 @@ struct EpiOpt {
     const Act* out2 = nullptr;
     float* out_f32 = nullptr;   // fp32 destination [pix][out_f32_ld] instead of `out`
     int out_f32_ld = 0;
+    int nchw = 0;               // out_f32 is a dense NCHW tensor (x_hat)
 };
 
 }  // namespace
@@ -100,6 +101,28 @@ struct mlic_engine {
     int64_t launches = 0;
     int rc = 0;              // sticky error of the current walk
 
+    // live profiling of the dominant kernel (tcgen05 implicit GEMM): CUDA-event pairs on the launch stream
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<double> ev_flops;
+    double prof_ms = 0, prof_flops = 0, prof_launches = 0;
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        return ev_pool[ev_used++];
+    }
+    int profile_collect() {          // synchronises the events recorded so far and folds them into the sums
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+            float ms = 0;
+            cudaError_t e = cudaEventSynchronize(ev_pool[i + 1]);
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]);
+            if (e != cudaSuccess) return fail("profile: %s", cudaGetErrorString(e));
+            prof_ms += ms; prof_flops += ev_flops[i / 2]; prof_launches += 1;
+        }
+        ev_used = 0; ev_flops.clear();
+        return 0;
+    }
+
     // host-call staging (mlic_run_host)
     void* h_ws = nullptr; size_t h_ws_bytes = 0;
     void* h_io = nullptr; size_t h_io_bytes = 0;
@@ -107,6 +130,7 @@ struct mlic_engine {
 
     ~mlic_engine() {
         for (void* p : dev_allocs) cudaFree(p);
+        for (cudaEvent_t ev : ev_pool) cudaEventDestroy(ev);
         if (h_ws) cudaFree(h_ws);
         if (h_io) cudaFree(h_io);
         if (h_stream) cudaStreamDestroy(h_stream);
@@ -394,7 +418,11 @@ struct mlic_engine {
         e.Hout = (in.H + 2 * pad - w->ks) / stride + 1;
         e.Wout = (in.W + 2 * pad - w->ks) / stride + 1;
         bool vec = (w->N % 4 == 0);
-        if (o.out_f32) { e.out = o.out_f32; e.out_ld = o.out_f32_ld; e.out_f32 = 1; vec = vec && (o.out_f32_ld % 4 == 0) && ((uintptr_t)o.out_f32 % 16 == 0); }
+        if (o.nchw) {
+            if (!dry && !o.out_f32) { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return; }
+            e.out = o.out_f32; e.out_ld = 0; e.out_f32 = 1; e.nchw = 1; vec = false;
+        }
+        else if (o.out_f32) { e.out = o.out_f32; e.out_ld = o.out_f32_ld; e.out_f32 = 1; vec = vec && (o.out_f32_ld % 4 == 0) && ((uintptr_t)o.out_f32 % 16 == 0); }
         else if (out) { e.out = out->p; e.out_ld = out->ld; vec = vec && (out->ld % 4 == 0) && al4(out->p); }
         else { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return; }
         if (o.res) { e.res = o.res->p; e.res_ld = o.res->ld; vec = vec && (o.res->ld % 4 == 0) && al4(o.res->p); }
@@ -411,7 +439,14 @@ struct mlic_engine {
             else { t.H = e.Hout; t.W = e.Wout; }      // 1x1 stride s: sub-sampled grid
             t.sW = in.ld * stride; t.sH = in.W * in.ld * stride; t.sB = in.H * in.W * in.ld;
             if (tc_conv_supported(t, e)) {
+                cudaEvent_t ev1 = nullptr;
+                if (profile) {
+                    cudaEventRecord(next_event(), st);
+                    ev1 = next_event();
+                    ev_flops.push_back(2.0 * (double)in.B * e.Hout * e.Wout * (double)w->N * (double)(w->ks * w->ks * w->Cin));
+                }
                 int r = launch_conv_gemm_tc(t, e, vec ? 1 : 0, st);
+                if (ev1) cudaEventRecord(ev1, st);
                 if (r) { if (!rc) rc = fail("tcgen05 conv '%s': %s", key.c_str(), tc_last_error()); return; }
                 ++launches;
                 return;
@@ -555,7 +590,7 @@ struct mlic_engine {
         ws_off = mark;
     }
     // g_s (transform/synthesis.py:59-68): y_hat view [B,h,w,M] -> x_hat fp32 NHWC [B,H,W,3]
-    void g_s(const Act& yh, float* xhat_nhwc) {
+    void g_s(const Act& yh, float* xhat_nchw) {
         size_t mark = ws_off;
         const std::string p = "g_s.synthesis_transform.";
         Act cur = act(yh.B, yh.H, yh.W, M);
@@ -569,7 +604,7 @@ struct mlic_engine {
             rb(a, p + std::to_string(i + 1), false, b);
             cur = b;
         }
-        EpiOpt o; o.out_f32 = xhat_nhwc; o.out_f32_ld = 3;
+        EpiOpt o; o.out_f32 = xhat_nchw; o.nchw = 1;
         gemm(cur, p + "7.0", 1, 1, nullptr, o);
         ws_off = mark;
     }
@@ -706,6 +741,7 @@ struct mlic_engine {
         if (mode < 0 || mode > 2) return fail("bad mode %d", mode);
         bf = precision == MLIC_PREC_BF16;
         dry = dry_run; st = stream; rc = 0; launches = 0;
+        if (!dry && profile && ev_used > 200000) { if (profile_collect()) return 1; }
         ws_base = (uint8_t*)ws; ws_size = ws_bytes; ws_off = 0; ws_peak = 0;
         if (!dry && ((uintptr_t)ws % 256)) return fail("workspace must be 256-byte aligned");
         if (!dry && bf && use_tc && tc_init()) return fail("%s", tc_last_error());
@@ -791,11 +827,7 @@ struct mlic_engine {
             after_launch("lik_nchw");
         }
         if (io->y_hat && go()) { launch_nhwc_to_nchw(bf, yhat, io->y_hat, st); after_launch("y_hat_tap"); }
-        if (io->x_hat || dry) {
-            float* xh = f32((size_t)B * H * W * 3);
-            g_s(yhat, xh);
-            if (go()) { launch_nhwc_f32_to_nchw(xh, 3, B, H, W, 3, io->x_hat, st); after_launch("x_hat_nchw"); }
-        }
+        if (io->x_hat || dry) g_s(yhat, io->x_hat);
         if (mode == MLIC_MODE_FORWARD && (io->rd_sums || dry)) {
             double* partial = (double*)ws_alloc(RD_BLOCKS * sizeof(double));
             if (go() && io->rd_sums) {
@@ -851,6 +883,7 @@ int mlic_engine_finalize(mlic_engine* e) {
 int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
     if (!e || !name) return fail("bad arguments");
     if (!strcmp(name, "tensor_cores")) { e->use_tc = value; return 0; }
+    if (!strcmp(name, "profile")) { e->profile = value; return 0; }
     return fail("unknown option '%s'", name);
 }
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {
@@ -866,6 +899,15 @@ int mlic_run(mlic_engine* e, int mode, int precision, int B, int H, int W, float
     return e->run(mode, precision, B, H, W, gain, dev, workspace, workspace_bytes, (cudaStream_t)cuda_stream, false);
 }
 int64_t mlic_last_launch_count(const mlic_engine* e) { return e ? e->launches : 0; }
+
+int mlic_profile_read(mlic_engine* e, double* out3, int reset) {
+    if (!e || !out3) return fail("bad arguments");
+    int r = e->profile_collect();
+    if (r) return r;
+    out3[0] = e->prof_ms; out3[1] = e->prof_flops; out3[2] = e->prof_launches;
+    if (reset) { e->prof_ms = e->prof_flops = e->prof_launches = 0; }
+    return 0;
+}
 
 int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* host,
                   int pinned) {
@@ -929,6 +971,40 @@ int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, 
     if (host->y_hat && dev.y_hat) CUDA_OK(cudaMemcpyAsync(host->y_hat, dev.y_hat, n_y * 4, cudaMemcpyDeviceToHost, s));
     if (want_rd) CUDA_OK(cudaMemcpyAsync(host->rd_sums, dev.rd_sums, 16, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int H, int W, int Cin, const float* weight,
+                     const float* bias, int N, int ks, int stride, int pad, int act, int shuffle, const void* residual,
+                     void* out, int iters, float* avg_ms, void* cuda_stream) {
+    if (!in || !weight || !out || iters < 1) return fail("bad arguments");
+    mlic_engine e;
+    e.N = e.M = e.S = e.C = 0; e.kind = 0; e.sd = e.vbr = false; e.Me = 0;
+    e.rc = 0;
+    e.pack_conv_raw("w", weight, bias, N, Cin, ks, shuffle);
+    if (e.rc) return e.rc;
+    e.bf = precision == MLIC_PREC_BF16; e.use_tc = tensor_cores; e.dry = false; e.st = (cudaStream_t)cuda_stream;
+    if (e.bf && e.use_tc && tc_init()) return fail("%s", tc_last_error());
+    Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin;
+    const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+    Act o; o.p = out; o.B = B;
+    if (shuffle) { o.H = 2 * Ho; o.W = 2 * Wo; o.C = N / 4; } else { o.H = Ho; o.W = Wo; o.C = N; }
+    o.ld = o.C;
+    Act r = o; r.p = const_cast<void*>(residual);
+    EpiOpt eo; eo.act = act; if (residual) eo.res = &r;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    e.gemm(a, "w", stride, pad, &o, eo);          // warm-up / correctness launch
+    CUDA_OK(cudaEventRecord(e0, e.st));
+    for (int i = 1; i < iters; ++i) e.gemm(a, "w", stride, pad, &o, eo);
+    CUDA_OK(cudaEventRecord(e1, e.st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e.rc) return e.rc;
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

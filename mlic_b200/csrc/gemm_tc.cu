@@ -2,23 +2,25 @@
 //
 //   D[m][n] = sum_{tap, c} X[b, oh + ky - pad, ow + kx - pad, c] * Wt[n][tap * Cpad + c]
 //
-// One CTA computes a 128-pixel x BN-column output tile.  The 128 pixels are a TH x TW patch of the
-// output grid (TH * TW = 128) so that the A operand of every (tap, 64-channel chunk) K step is ONE 4-D
-// TMA box {64 ch, TW, TH, 1} of the NHWC activation: the conv halo / zero padding is the TMA's
-// out-of-bounds zero fill, and there is no im2col buffer.  The box lands in shared memory as 128 rows of
-// 128 B with the 128-byte swizzle, which is exactly the canonical K-major SWIZZLE_128B UMMA layout.
-// B (weights, [N][taps * Cpad] bf16, K-major) is a 2-D TMA box {64, BN}.
+// A tile is 128 output pixels x BN columns.  The 128 pixels are a TH x TW patch of the output grid
+// (TH * TW = 128) so that the A operand of every (tap, 64-channel chunk) K step is ONE 4-D TMA box
+// {64 ch, TW, TH, 1} of the NHWC activation: the conv halo / zero padding is the TMA's out-of-bounds zero
+// fill, and there is no im2col buffer.  The box lands in shared memory as 128 rows of 128 B with the
+// 128-byte swizzle, which is exactly the canonical K-major SWIZZLE_128B UMMA layout.  B (weights,
+// [N][taps * Cpad] bf16, K-major) is a 2-D TMA box {64, BN}.
 //
-// Warp roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected
-// lane, tcgen05.mma cta_group::1 kind::f16, M = 128, N = BN, K = 16), warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (tcgen05.ld 32x32b, one output pixel per thread, the shared `Epi` epilogue:
-// bias / (I)GDN / GELU / tanh / parity mask / residual / pixel-shuffle store).
-// Two CTAs are resident per SM (shared-memory budget below), so one CTA's epilogue overlaps the other's
-// main loop.  Every mbarrier wait is bounded and traps instead of hanging.
+// Persistent kernel, one CTA per SM, 384 threads: warp 0 = TMA producer (one elected lane), warp 1 = MMA
+// issuer (one elected lane: tcgen05.mma cta_group::1 kind::f16, M = 128, N = BN, K = 16), warp 2 = TMEM
+// allocator, warps 4..11 = epilogue (tcgen05.ld 32x32b; warp w reads TMEM lanes 32*(w%4).., the two warps of
+// a lane quarter alternate 32-column chunks; one output pixel per thread; bias / (I)GDN / GELU / tanh / parity
+// mask / residual / pixel-shuffle / x^2 side output with 16-byte accesses).  Shared memory holds a 4..8 stage
+// TMA ring (up to 196 KB); TMEM holds two accumulator stages so the epilogue of tile i overlaps the main loop
+// of tile i+1.  Every mbarrier wait is bounded and traps instead of hanging.
 #include "kernels.h"
 
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mlic {
@@ -111,17 +113,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-    uint32_t r[16];
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+enum { STORE_DIRECT = 0, STORE_TMA = 1, STORE_NCHW3 = 2 };
 
 struct TcParams {
     int tilesH, tilesW;     // output patches per image
@@ -129,48 +138,187 @@ struct TcParams {
     int ks, pad;
     int kchunks;            // Cpad / 64
     int Cpad;
-    int BN;                 // columns per CTA (multiple of 16, <= 256)
+    int BN;                 // columns per tile (multiple of 16; of 64 in STORE_TMA mode; <= 256)
+    int tilesN;
+    int ntiles;             // B * tilesH * tilesW * tilesN
     int stages;
-    int tmem_cols;          // power of two >= max(32, BN)
+    int acc_stride;         // TMEM columns between the two accumulator stages (power of two >= BN)
+    int epi_vec;            // STORE_DIRECT: 16-byte epilogue accesses are legal for every pointer involved
+    int ld_vec;             // 16-byte loads of the residual / GDN operand are legal
+    int store_mode;
+    int nstg;               // STORE_TMA: staging buffers (1 or 2) of 16 KB behind the stage ring
+    int debug;              // development only: bit0 skip epilogue stores, bit1 skip TMEM loads
+};
+
+struct TcMaps {
+    CUtensorMap a, b;       // operands
+    CUtensorMap o[4];       // output (one per pixel-shuffle group; o[0] when not shuffled)
+    CUtensorMap o2;         // x^2 side output
 };
 
 constexpr int TC_A_BYTES = 128 * 128;       // 128 rows x 64 bf16
+constexpr int TC_STG_BYTES = 128 * 128;     // one staged 128-pixel x 64-column bf16 block
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 128 + TC_EPI_WARPS * 32;
+constexpr int TC_MAX_N = 2048;
+constexpr int TC_MAX_BIAS = TC_MAX_N + 256;
 
-__global__ void __launch_bounds__(256) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, TcParams p,
-                                                           Epi e, int vec) {
+// 8 consecutive bf16 <-> fp32 through one 16-byte access
+__device__ __forceinline__ void load8_bf16(const bf16* p, float v[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float v[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Epilogue arithmetic for 8 consecutive GEMM columns n..n+7 of one output pixel, in the order of epi_store4
+// (common.cuh): premask, + bias, (I)GDN, activation, postmask, + residual.  bf16 activations.  The mode tests are
+// hoisted out of the element loops and the caller does not unroll across 8-column groups: the epilogue must stay a
+// few hundred instructions, or the eight epilogue warps stall on instruction fetch.
+struct EpiRow {
+    const bf16* xp;      // GDN operand row (at column 0) or null
+    const bf16* rp;      // residual row (at output channel 0 of this pixel) or null
+    bool keep_pre, keep_post;
+};
+__device__ __forceinline__ void epi_math8(const Epi& e, const float* __restrict__ sBias, const EpiRow& row, int n, int oc,
+                                          float* a, bool ldvec) {
+    const bool full = ldvec && n + 8 <= e.N;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (row.keep_pre ? a[j] : 0.0f) + sBias[n + j];
+    if (row.xp) {
+        float x[8];
+        if (full) load8_bf16(row.xp + n, x);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (n + j < e.N) ? __bfloat162float(row.xp[n + j]) : 0.f;
+        }
+        if (e.gdn == GDN_FWD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = x[j] * rsqrtf(a[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = x[j] * sqrtf(a[j]);
+        }
+    }
+    if (e.act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = gelu_erf(a[j]);
+    } else if (e.act == ACT_HALF_TANH) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.5f * tanhf(a[j]);
+    }
+    if (!row.keep_post) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.0f;
+    }
+    if (row.rp) {
+        float r[8];
+        if (full) load8_bf16(row.rp + oc, r);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = (n + j < e.N) ? __bfloat162float(row.rp[oc + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += r[j];
+    }
+}
+
+// pixel-shuffle bookkeeping of one GEMM column: group g = n / Cq -> output pixel (2h + (g >> 1), 2w + (g & 1)), channel n % Cq
+__device__ __forceinline__ void out_coord(const Epi& e, int h, int w, int n, int& oh, int& ow, int& oc, int& OH, int& OW) {
+    oh = h; ow = w; oc = n; OH = e.Hout; OW = e.Wout;
+    if (e.shuffle) {
+        const int Cq = e.N >> 2;
+        const int g = n / Cq;
+        oc = n - g * Cq; oh = 2 * h + (g >> 1); ow = 2 * w + (g & 1); OH *= 2; OW *= 2;
+    }
+}
+
+// STORE_DIRECT: the thread writes its own 8 columns (bias / activation / residual already applied).
+__device__ __forceinline__ void direct_store8(const Epi& e, int b, int h, int w, int n, const float* v, bool vec) {
+    if (vec && n + 8 <= e.N) {
+        int oh, ow, oc, OH, OW;
+        out_coord(e, h, w, n, oh, ow, oc, OH, OW);
+        const size_t opix = ((size_t)b * OH + oh) * OW + ow;
+        if (e.out_f32) {
+            float* op = reinterpret_cast<float*>(e.out) + opix * e.out_ld + oc;
+            *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out) + opix * e.out_ld + oc) = pack8_bf16(v);
+        }
+        if (e.out2) {
+            float s8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s8[k] = v[k] * v[k];
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out2) + opix * e.out2_ld + oc) = pack8_bf16(s8);
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {        // ragged N, odd shuffle groups, unaligned views
+        const int nj = n + j;
+        if (nj >= e.N) break;
+        int oh, ow, oc, OH, OW;
+        out_coord(e, h, w, nj, oh, ow, oc, OH, OW);
+        const size_t opix = ((size_t)b * OH + oh) * OW + ow;
+        if (e.out_f32) reinterpret_cast<float*>(e.out)[opix * e.out_ld + oc] = v[j];
+        else reinterpret_cast<bf16*>(e.out)[opix * e.out_ld + oc] = __float2bfloat16_rn(v[j]);
+        if (e.out2) reinterpret_cast<bf16*>(e.out2)[opix * e.out2_ld + oc] = __float2bfloat16_rn(v[j] * v[j]);
+    }
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory"); }
+
+// Persistent kernel: grid = min(#tiles, #SMs); every role walks the same static tile sequence
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...  (N-tile fastest, so co-running CTAs share the A patch in L2).
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e) {
     extern __shared__ uint8_t smem_raw[];
-    // carve: [barriers | pad to 1024] [stage0 A | stage0 B] ...
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * 128;
-    const int stage_bytes = TC_A_BYTES + b_bytes;      // multiple of 1024 (BN multiple of 16 -> 2048 B steps)
-    __shared__ uint64_t full_bar[8], empty_bar[8], accum_bar;
+    const int stage_bytes = TC_A_BYTES + b_bytes;      // multiple of 1024
+    __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float sBias[TC_MAX_BIAS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tilesH * p.tilesW;
-    const int img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
-    const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
-    const int h0 = th * p.TH, w0 = tw * p.TW;
-    const int n0 = blockIdx.y * p.BN;
     const int ksteps = p.ks * p.ks * p.kchunks;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                     "r"((uint32_t)p.tmem_cols)
+                     "r"((uint32_t)(2 * p.acc_stride))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < TC_MAX_BIAS; i += TC_THREADS) sBias[i] = (e.bias && i < e.N) ? e.bias[i] : 0.0f;
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -180,16 +328,22 @@ __global__ void __launch_bounds__(256) conv_gemm_tc_kernel(const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int k = 0; k < ksteps; ++k) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                const int tap = k / p.kchunks, cc = k - tap * p.kchunks;
-                const int ky = tap / p.ks, kx = tap - ky * p.ks;
-                uint8_t* sa = base + (size_t)stage * stage_bytes;
-                uint8_t* sb = sa + TC_A_BYTES;
-                mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                tma_load_4d(sa, &tmA, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
-                tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                const int nt = t % p.tilesN, mt = t / p.tilesN;
+                const int img = mt / tiles_per_img;
+                const int trem = mt - img * tiles_per_img;
+                const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
+                const int h0 = th * p.TH, w0 = tw * p.TW, n0 = nt * p.BN;
+                for (int k = 0; k < ksteps; ++k) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const int tap = k / p.kchunks, cc = k - tap * p.kchunks;
+                    const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                    uint8_t* sa = base + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                    tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                    tma_load_2d(sa + TC_A_BYTES, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -198,52 +352,171 @@ __global__ void __launch_bounds__(256) conv_gemm_tc_kernel(const __grid_constant
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            for (int k = 0; k < ksteps; ++k) {
-                mbar_wait(&full_bar[stage], phase);
+            int it = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(&acc_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
-                const uint64_t adesc = umma_desc_sw128(sa);
-                const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+                const uint32_t dcol = tmem_base + (uint32_t)(as * p.acc_stride);
+                for (int k = 0; k < ksteps; ++k) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)      // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
-                    umma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                              (k | kk) ? 1u : 0u);
-                tcgen05_commit(&empty_bar[stage]);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    for (int kk = 0; kk < 4; ++kk)      // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
+                        umma_bf16(dcol, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                    tcgen05_commit(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&acc_full[as]);
             }
-            tcgen05_commit(&accum_bar);
         }
     } else if (warp >= 4) {
-        mbar_wait(&accum_bar, 0);
-        tcgen05_fence_after();
-        const int q = warp & 3;
+        // 8 epilogue warps: TMEM lane quarter q = warp % 4 (hardware restriction), column half = (warp - 4) / 4
+        const int q = warp & 3, half = (warp - 4) >> 2;
         const int r = q * 32 + lane;
-        const int h = h0 + r / p.TW, w = w0 + r % p.TW;
-        const bool valid = h < e.Hout && w < e.Wout;
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c = 0; c < p.BN; c += 16) {
-            float v[16];
-            tmem_ld16(trow + (uint32_t)c, v);
-            if (valid) {
+        const bool issuer = (warp == 4 && lane == 0);
+        uint8_t* stg = base + (size_t)p.stages * stage_bytes;
+        const int per = e.out2 ? 2 : 1;             // staging buffers per 64-column block (out [+ out2])
+        const uint32_t nring = (uint32_t)(p.nstg / per);
+        uint32_t blk = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+            const int nt = t % p.tilesN, mt = t / p.tilesN;
+            const int img = mt / tiles_per_img;
+            const int trem = mt - img * tiles_per_img;
+            const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
+            const int h0 = th * p.TH, w0 = tw * p.TW;
+            const int h = h0 + r / p.TW, w = w0 + r % p.TW;
+            const int n0 = nt * p.BN;
+            const bool valid = h < e.Hout && w < e.Wout;
+            const int as = it & 1;
+            EpiRow row;
+            row.keep_pre = parity_keep(e.premask, h, w);
+            row.keep_post = parity_keep(e.postmask, h, w);
+            row.xp = (e.gdn && valid) ? reinterpret_cast<const bf16*>(e.gdn_x) + (((size_t)img * e.Hout + h) * e.Wout + w) * e.gdn_ld : nullptr;
+            mbar_wait(&acc_full[as], (uint32_t)(it >> 1) & 1u);
+            tcgen05_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride);
+            if (p.store_mode == STORE_TMA) {
+                // 64-column blocks: the two halves fill one swizzled 16 KB staging block (two with the x^2 side output),
+                // then one TMA store per block writes it out with full 128-byte lines.
+                for (int kb = 0; kb < p.BN; kb += 64) {
+                    int g = 0, ocb = n0 + kb;                       // the whole block lies in one pixel-shuffle group
+                    if (e.shuffle) { const int Cq = e.N >> 2; g = ocb / Cq; ocb -= g * Cq; }
+                    row.rp = nullptr;
+                    if (e.res && valid) {
+                        int oh, ow, oc, OH, OW;
+                        out_coord(e, h, w, n0 + kb, oh, ow, oc, OH, OW);
+                        row.rp = reinterpret_cast<const bf16*>(e.res) + (((size_t)img * OH + oh) * OW + ow) * e.res_ld;
+                    }
+                    uint8_t* sb = stg + (size_t)((blk % nring) * per) * TC_STG_BYTES;
+                    if (nring == 1) {               // single ring slot: the previous block's stores must have drained it
+                        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        epi_barrier();
+                    }
+#pragma unroll 1
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const int c = kb + half * 32 + sub * 8;
+                        uint32_t raw[8];
+                        tmem_ld8(trow + (uint32_t)c, raw);
+                        tmem_ld_wait();
+                        float v[8];
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) epi_store4<bf16>(e, img, h, w, n0 + c + j, v + j, vec != 0);
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j]);
+                        epi_math8(e, sBias, row, n0 + c, ocb + half * 32 + sub * 8, v, p.ld_vec != 0);
+                        const int jj = half * 4 + sub;
+                        const uint32_t off = (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4));
+                        *reinterpret_cast<uint4*>(sb + off) = pack8_bf16(v);
+                        if (e.out2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
+                            *reinterpret_cast<uint4*>(sb + TC_STG_BYTES + off) = pack8_bf16(v);
+                        }
+                    }
+                    if (kb + 64 >= p.BN) {          // accumulator fully read: hand the TMEM stage back to the MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[as]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (nring > 1 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    epi_barrier();
+                    if (issuer && !(p.debug & 1)) {
+                        tma_store_4d(&tm.o[g], sb, ocb, w0, h0, img);
+                        if (e.out2) tma_store_4d(&tm.o2, sb + TC_STG_BYTES, ocb, w0, h0, img);
+                    }
+                    ++blk;
+                }
+            } else if (p.store_mode == STORE_NCHW3) {
+                // final subpel conv (N = 12 -> 3 channels): column (2r+s)*3 + ch -> out[b][ch][2h+r][2w+s], fp32 NCHW;
+                // consecutive lanes hold consecutive w, so every float2 store instruction writes whole 128-byte lines.
+                if (half == 0) {
+                    uint32_t raw[16];
+                    tmem_ld16(trow, raw);
+                    tmem_ld_wait();
+                    if (valid && !(p.debug & 1)) {
+                        float* o = reinterpret_cast<float*>(e.out);
+                        const int OH = 2 * e.Hout, OW = 2 * e.Wout;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                            for (int rr = 0; rr < 2; ++rr)
+                                *reinterpret_cast<float2*>(o + (((size_t)img * 3 + ch) * OH + 2 * h + rr) * OW + 2 * w) =
+                                    make_float2(__uint_as_float(raw[(2 * rr) * 3 + ch]) + sBias[(2 * rr) * 3 + ch],
+                                                __uint_as_float(raw[(2 * rr + 1) * 3 + ch]) + sBias[(2 * rr + 1) * 3 + ch]);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+            } else {
+                // STORE_DIRECT: 32-column chunks are dealt to the two halves alternately (BN is a multiple of 16)
+                for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+                    const int nsub = (p.BN - c0) >= 32 ? 4 : (p.BN - c0) / 8;
+#pragma unroll 1
+                    for (int sub = 0; sub < nsub; ++sub) {
+                        const int c = c0 + sub * 8, n = n0 + c;
+                        uint32_t raw[8];
+                        tmem_ld8(trow + (uint32_t)c, raw);
+                        tmem_ld_wait();
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j]);
+                        int oc = n;
+                        row.rp = nullptr;
+                        if (e.res && valid) {
+                            int oh, ow, OH, OW;
+                            out_coord(e, h, w, n, oh, ow, oc, OH, OW);
+                            row.rp = reinterpret_cast<const bf16*>(e.res) + (((size_t)img * OH + oh) * OW + ow) * e.res_ld;
+                        }
+                        epi_math8(e, sBias, row, n, oc, v, p.ld_vec != 0);
+                        if (valid && !(p.debug & 1)) direct_store8(e, img, h, w, n, v, p.epi_vec != 0);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
             }
         }
-        tcgen05_fence_before();
+        if (p.store_mode == STORE_TMA && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.acc_stride))
                      : "memory");
     }
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static int pick_bn(int N) {
+static int pick_bn(int N, int mult) {
     int nt = (N + 255) / 256;
-    int bn = ((N + nt - 1) / nt + 15) / 16 * 16;
-    return bn < 16 ? 16 : bn;
+    int bn = ((N + nt - 1) / nt + mult - 1) / mult * mult;
+    return bn < mult ? mult : bn;
 }
 
 bool tc_conv_supported(const TcConv& c, const Epi& e) {
@@ -251,14 +524,31 @@ bool tc_conv_supported(const TcConv& c, const Epi& e) {
     if (((uintptr_t)c.in) % 16 != 0 || (c.ld % 8) != 0) return false;      // TMA: 16-byte base / strides
     if (c.sW <= 0 || c.sH <= 0 || (c.sW % 8) != 0 || (c.sH % 8) != 0 || (c.sB % 8) != 0) return false;
     if (c.Cin < 8 || c.Cpad % 64 != 0) return false;
-    if (e.N < 8) return false;
+    if (e.N < 8 || e.N > TC_MAX_N) return false;
     if (c.H <= 0 || c.W <= 0 || c.B <= 0) return false;
+    if (e.nchw && !(e.shuffle && e.N == 12 && e.out_f32)) return false;
     return true;
+}
+
+static int encode_out_map(CUtensorMap* m, void* basep, int Cdim, int Wd, int Hd, int Bd, size_t sW, size_t sH, size_t sB,
+                          int TW, int TH) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cdim, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)Bd};
+    cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sB * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, basep, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(out) failed: %d (C=%d W=%d H=%d B=%d)", (int)r, Cdim, Wd, Hd, Bd);
+        return 1;
+    }
+    return 0;
 }
 
 int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) {
     if (tc_init()) return 1;
     TcParams p;
+    memset(&p, 0, sizeof p);
     // output patch shape: minimise the number of tiles
     const int cand[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
     long long best = -1;
@@ -269,23 +559,47 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     p.tilesH = (e.Hout + p.TH - 1) / p.TH;
     p.tilesW = (e.Wout + p.TW - 1) / p.TW;
     p.ks = c.ks; p.pad = c.pad; p.Cpad = c.Cpad; p.kchunks = c.Cpad / 64;
-    p.BN = pick_bn(e.N);
-    const int stage_bytes = TC_A_BYTES + p.BN * 128;
-    p.stages = (100 * 1024) / stage_bytes;
-    if (p.stages < 2) p.stages = 2;
-    if (p.stages > 6) p.stages = 6;
-    const int ksteps = p.ks * p.ks * p.kchunks;
-    if (p.stages > ksteps) p.stages = ksteps < 1 ? 1 : ksteps;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
 
-    CUtensorMap tmA, tmB;
+    auto ok16 = [](const void* q, int ld, int esz) { return q == nullptr || ((((uintptr_t)q) % 16 == 0) && ((ld * esz) % 16 == 0)); };
+    const int Cq = e.shuffle ? e.N / 4 : e.N;
+    // store mode
+    p.store_mode = STORE_DIRECT;
+    if (e.nchw) p.store_mode = STORE_NCHW3;
+    else if (!e.out_f32 && e.out && ok16(e.out, e.out_ld, 2) && ok16(e.out2, e.out2_ld, 2) && (!e.shuffle || (Cq % 64) == 0) && !(e.shuffle && e.out2))
+        p.store_mode = STORE_TMA;
+    { const char* d = getenv("MLIC_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
+    if (p.debug & 4) { if (p.store_mode == STORE_TMA) p.store_mode = STORE_DIRECT; }
+    p.BN = pick_bn(e.N, p.store_mode == STORE_TMA ? 64 : ((e.shuffle || e.N % 32 == 0) && e.N >= 32 ? 32 : 16));
+    const int stage_bytes = TC_A_BYTES + p.BN * 128;
+    const int budget = 212 * 1024;      // dynamic shared memory (static: bias + barriers ~ 9.5 KB)
+    p.nstg = 0;
+    if (p.store_mode == STORE_TMA) {
+        const int per = e.out2 ? 2 : 1;
+        p.nstg = (budget - 1024 - 2 * per * TC_STG_BYTES) / stage_bytes >= (p.BN > 192 ? 4 : 3) ? 2 * per : per;
+    }
+    p.stages = (budget - 1024 - p.nstg * TC_STG_BYTES) / stage_bytes;
+    if (p.stages < 2) p.stages = 2;
+    if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+    p.acc_stride = 32;
+    while (p.acc_stride < p.BN) p.acc_stride <<= 1;
+    p.tilesN = (e.N + p.BN - 1) / p.BN;
+    p.ntiles = c.B * p.tilesH * p.tilesW * p.tilesN;
+    p.ld_vec = (ok16(e.res, e.res_ld, 2) && ok16(e.gdn_x, e.gdn_ld, 2) && (e.N % 8 == 0) && (!e.shuffle || (Cq % 32) == 0)) ? 1 : 0;
+    {
+        bool v = vec != 0 && (e.N % 8 == 0) && p.ld_vec;
+        v = v && ok16(e.out, e.out_ld, e.out_f32 ? 4 : 2) && ok16(e.out2, e.out2_ld, 2);
+        if (e.shuffle) v = v && ((Cq % 32) == 0);
+        p.epi_vec = v ? 1 : 0;
+    }
+
+    TcMaps tm;
+    memset(&tm, 0, sizeof tm);
     {
         cuuint64_t dims[4] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.B};
         cuuint64_t strides[3] = {(cuuint64_t)c.sW * 2, (cuuint64_t)c.sH * 2, (cuuint64_t)c.sB * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.in), dims, strides, box, estr,
+        CUresult r = g_encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.in), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -300,7 +614,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         cuuint64_t strides[1] = {Ktot * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(c.w), dims, strides, box, estr,
+        CUresult r = g_encode(&tm.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(c.w), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -309,21 +623,45 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
             return 3;
         }
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t er = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (p.store_mode == STORE_TMA) {
+        bf16* ob = reinterpret_cast<bf16*>(e.out);
+        const size_t ld = (size_t)e.out_ld;
+        if (!e.shuffle) {
+            if (encode_out_map(&tm.o[0], ob, e.N, e.Wout, e.Hout, c.B, ld, (size_t)e.Wout * ld, (size_t)e.Hout * e.Wout * ld, p.TW, p.TH)) return 7;
+        } else {
+            const size_t OW = 2 * (size_t)e.Wout, OH = 2 * (size_t)e.Hout;
+            for (int g = 0; g < 4; ++g) {       // group g = 2r + s -> output pixel (2h + r, 2w + s)
+                bf16* bp = ob + ((size_t)(g >> 1) * OW + (size_t)(g & 1)) * ld;
+                if (encode_out_map(&tm.o[g], bp, Cq, e.Wout, e.Hout, c.B, 2 * ld, 2 * OW * ld, OH * OW * ld, p.TW, p.TH)) return 7;
+            }
+        }
+        if (e.out2) {
+            const size_t ld2 = (size_t)e.out2_ld;
+            if (encode_out_map(&tm.o2, e.out2, e.N, e.Wout, e.Hout, c.B, ld2, (size_t)e.Wout * ld2, (size_t)e.Hout * e.Wout * ld2, p.TW, p.TH)) return 7;
+        }
+    }
+    const size_t smem = (size_t)p.stages * stage_bytes + (size_t)p.nstg * TC_STG_BYTES + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t er = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, budget + 1024);
         if (er != cudaSuccess) {
             snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(er));
             return 4;
         }
-        smem_set = 200 * 1024;
+        attr_set = true;
     }
-    dim3 grid((unsigned)(c.B * p.tilesH * p.tilesW), (unsigned)((e.N + p.BN - 1) / p.BN));
-    conv_gemm_tc_kernel<<<grid, 256, smem, s>>>(tmA, tmB, p, e, vec);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    dim3 grid((unsigned)(p.ntiles < num_sms ? p.ntiles : num_sms));
+    conv_gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tm, p, e);
     cudaError_t er = cudaGetLastError();
     if (er != cudaSuccess) {
-        snprintf(g_tc_err, sizeof g_tc_err, "conv_gemm_tc launch: %s", cudaGetErrorString(er));
+        snprintf(g_tc_err, sizeof g_tc_err, "conv_gemm_tc launch: %s (smem %zu)", cudaGetErrorString(er), smem);
         return 5;
     }
     return 0;

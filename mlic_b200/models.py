@@ -108,6 +108,7 @@ class MLICPlusPlus(nn.Module):
         self._engine = None
         self._engine_sig = None
         self._ws = {}
+        self._profile = False
         self.last_launch_count = 0
 
     def _name_for(self, config):
@@ -171,6 +172,19 @@ class MLICPlusPlus(nn.Module):
                 logits = logits + torch.tanh(getattr(eb.factors, str(i))) * torch.tanh(logits)
         return torch.abs(logits - eb.target).sum()
 
+    def set_profile(self, on):
+        """Bracket every tcgen05 GEMM launch with CUDA events (bench.py's live roofline measurement)."""
+        self._profile = bool(on)
+        return self
+
+    def profile_read(self, reset=True):
+        """-> (summed ms, summed algorithmic FLOPs, launches) of the tcgen05 GEMM launches since the last reset."""
+        if self._engine is None:
+            return 0.0, 0.0, 0
+        out = (C.c_double * 3)()
+        _lib.check(_lib.lib().mlic_profile_read(self._engine, out, 1 if reset else 0))
+        return float(out[0]), float(out[1]), int(out[2])
+
     def set_precision(self, precision):
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -220,6 +234,7 @@ class MLICPlusPlus(nn.Module):
         dev = torch.device("cuda", torch.cuda.current_device()) if (host or x is None) else x.device
         L = self._sync_engine(dev)
         _lib.check(L.mlic_engine_set_option(self._engine, b"tensor_cores", 1 if self.tensor_cores else 0))
+        _lib.check(L.mlic_engine_set_option(self._engine, b"profile", 1 if self._profile else 0))
         prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
         odev = "cpu" if host else dev
         h, w, hz, wz = H // 16, W // 16, H // 64, W // 64

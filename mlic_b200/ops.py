@@ -1,0 +1,48 @@
+"""Kernel-level entry points (tests and micro-benchmarks): thin wrappers over the C ABI."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "gelu": 1, "half_tanh": 2}
+
+
+def conv2d_nhwc(x, weight, bias=None, stride=1, pad=0, act=None, shuffle=False, residual=None, tensor_cores=True, iters=1):
+    """x: CUDA NHWC tensor [B,H,W,Cin], float32 (validation mode) or bfloat16 (fast mode); weight: [N,Cin,ks,ks] (any
+    device, fp32); returns (out NHWC of x.dtype, avg ms of launches 2..iters)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+    B, H, W, Cin = x.shape
+    N, ks = weight.shape[0], weight.shape[2]
+    w = weight.detach().to("cpu", torch.float32).contiguous()
+    b = None if bias is None else bias.detach().to("cpu", torch.float32).contiguous()
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    oshape = (B, 2 * Ho, 2 * Wo, N // 4) if shuffle else (B, Ho, Wo, N)
+    out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == x.dtype and residual.is_contiguous()
+    ms = C.c_float(0)
+    prec = _lib.PREC_BF16 if x.dtype == torch.bfloat16 else _lib.PREC_FP32
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_conv2d_nhwc(prec, 1 if tensor_cores else 0, C.c_void_p(x.data_ptr()), B, H, W, Cin,
+                                               C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()) if b is not None else None,
+                                               N, ks, stride, pad, ACT[act], 1 if shuffle else 0,
+                                               C.c_void_p(residual.data_ptr()) if residual is not None else None,
+                                               C.c_void_p(out.data_ptr()), iters, C.byref(ms), C.c_void_p(st)))
+    return out, float(ms.value)
+
+
+def gaussian_conditional(y, scales, means):
+    """Fused quantise / likelihood / CDF-index on flat fp32 CUDA tensors -> (y_hat, lik, symbols, indexes)."""
+    n = y.numel()
+    y_hat, lik = torch.empty_like(y), torch.empty_like(y)
+    sym = torch.empty(y.shape, dtype=torch.int32, device=y.device)
+    idx = torch.empty(y.shape, dtype=torch.int32, device=y.device)
+    with torch.cuda.device(y.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_gaussian_conditional(C.c_void_p(y.data_ptr()), C.c_void_p(scales.data_ptr()),
+                                                        C.c_void_p(means.data_ptr()), n, C.c_void_p(y_hat.data_ptr()),
+                                                        C.c_void_p(lik.data_ptr()), C.c_void_p(sym.data_ptr()),
+                                                        C.c_void_p(idx.data_ptr()), C.c_void_p(st)))
+    return y_hat, lik, sym, idx

@@ -1,0 +1,44 @@
+"""Development probe (GPU): micro-benchmark + correctness of the conv kernels on the MLICPP_L GEMM shapes."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+from mlic_b200 import ops
+
+SHAPES = [  # name, B, H, W, Cin, N, ks, shuffle
+    ("pw192 @544x960", 1, 544, 960, 192, 192, 1, False),
+    ("pw192 @272x480", 1, 272, 480, 192, 192, 1, False),
+    ("subpel 192->768 @272x480", 1, 272, 480, 192, 768, 3, True),
+    ("subpel 192->768 @136x240", 1, 136, 240, 192, 768, 3, True),
+    ("subpel 320->768 @68x120", 1, 68, 120, 320, 768, 3, True),
+    ("final 192->12 @544x960", 1, 544, 960, 192, 12, 3, True),
+    ("EP 960->320 @68x120", 1, 68, 120, 960, 320, 1, False),
+    ("EP 128->64 @68x120", 1, 68, 120, 128, 64, 1, False),
+    ("reproj5x5 288->96 @68x120", 1, 68, 120, 288, 96, 5, False),
+    ("fusion 800->64 @68x120", 1, 68, 120, 800, 64, 1, False),
+    ("lrp 352->224 @68x120", 1, 68, 120, 352, 224, 1, False),
+    ("hs subpel 480->1920 @34x60", 1, 34, 60, 480, 1920, 3, True),
+    ("ragged 100->72 @13x21", 2, 13, 21, 104, 72, 3, False),
+    ("pw 320->320 @68x120 b2", 2, 68, 120, 320, 320, 1, False),
+]
+check = "--check" in sys.argv
+only = [a for a in sys.argv[1:] if not a.startswith("--")]
+torch.manual_seed(0)
+for name, B, H, W, Cin, N, ks, sh in SHAPES:
+    if only and not any(o in name for o in only):
+        continue
+    x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16)
+    w = torch.randn(N, Cin, ks, ks) / (Cin * ks * ks) ** 0.5
+    b = torch.randn(N) * 0.1
+    res = None
+    if not sh:
+        res = torch.randn(B, H, W, N, device="cuda").to(torch.bfloat16)
+    out, ms = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, res, True, 20)
+    flops = 2.0 * B * H * W * N * Cin * ks * ks
+    byts = x.numel() * 2 + out.numel() * 2
+    msg = f"{name:32s} {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s  {byts/ms/1e6:8.1f} GB/s(alg)"
+    if check:
+        ref, ms2 = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, res, False, 2)
+        d = (out.float() - ref.float()).abs().max().item()
+        msg += f" | simt {ms2*1e3:9.1f} us maxdiff {d:.3e}"
+    print(msg, flush=True)
