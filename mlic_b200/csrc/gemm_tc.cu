@@ -9,13 +9,14 @@
 // 128-byte swizzle, which is exactly the canonical K-major SWIZZLE_128B UMMA layout.  B (weights,
 // [N][taps * Cpad] bf16, K-major) is a 2-D TMA box {64, BN}.
 //
-// Persistent kernel, one CTA per SM, 384 threads: warp 0 = TMA producer (one elected lane), warp 1 = MMA
+// Persistent kernel, one CTA per SM, 640 threads: warp 0 = TMA producer (one elected lane), warp 1 = MMA
 // issuer (one elected lane: tcgen05.mma cta_group::1 kind::f16, M = 128, N = BN, K = 16), warp 2 = TMEM
-// allocator, warps 4..11 = epilogue (tcgen05.ld 32x32b; warp w reads TMEM lanes 32*(w%4).., the two warps of
-// a lane quarter alternate 32-column chunks; one output pixel per thread; bias / (I)GDN / GELU / tanh / parity
-// mask / residual / pixel-shuffle / x^2 side output with 16-byte accesses).  Shared memory holds a 4..8 stage
-// TMA ring (up to 196 KB); TMEM holds two accumulator stages so the epilogue of tile i overlaps the main loop
-// of tile i+1.  Every mbarrier wait is bounded and traps instead of hanging.
+// allocator, warps 4..19 = epilogue (tcgen05.ld 32x32b; warp w reads TMEM lanes 32*(w%4).., the four warps of a
+// lane quarter split every 64-column block; one output pixel per thread; bias / (I)GDN / GELU / tanh / parity
+// mask / residual / pixel-shuffle / x^2 side output).  bf16 outputs are staged in 128B-swizzled shared memory and
+// written by TMA stores (full 128-byte lines; one tensor map per pixel-shuffle group); fp32 / ragged outputs are
+// written directly.  Shared memory holds a 3..8 stage TMA ring; TMEM holds two accumulator stages so the epilogue
+// of tile i overlaps the main loop of tile i+1.  Every mbarrier wait is bounded and traps instead of hanging.
 #include "kernels.h"
 
 #include <cuda.h>
@@ -159,7 +160,7 @@ struct TcMaps {
 constexpr int TC_A_BYTES = 128 * 128;       // 128 rows x 64 bf16
 constexpr int TC_STG_BYTES = 128 * 128;     // one staged 128-pixel x 64-column bf16 block
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 128 + TC_EPI_WARPS * 32;
 constexpr int TC_MAX_N = 2048;
 constexpr int TC_MAX_BIAS = TC_MAX_N + 256;
@@ -188,6 +189,23 @@ __device__ __forceinline__ uint4 pack8_bf16(const float v[8]) {
 // (common.cuh): premask, + bias, (I)GDN, activation, postmask, + residual.  bf16 activations.  The mode tests are
 // hoisted out of the element loops and the caller does not unroll across 8-column groups: the epilogue must stay a
 // few hundred instructions, or the eight epilogue warps stall on instruction fetch.
+// GELU(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below bf16 resolution):
+// one MUFU.RCP, one MUFU.EX2 and 8 FMA-class instructions instead of erff()'s ~30.  Fast (bf16) mode only; the fp32
+// validation path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t, ex;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * z * z));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float q = p * t * ex;                                     // 1 - erf(|z|)
+    const float hx = 0.5f * x;
+    return fmaf(copysignf(1.0f - q, x), hx, hx);                    // 0.5 x (1 + erf(x / sqrt 2))
+}
+
 struct EpiRow {
     const bf16* xp;      // GDN operand row (at column 0) or null
     const bf16* rp;      // residual row (at output channel 0 of this pixel) or null
@@ -215,7 +233,7 @@ __device__ __forceinline__ void epi_math8(const Epi& e, const float* __restrict_
     }
     if (e.act == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = gelu_erf(a[j]);
+        for (int j = 0; j < 8; ++j) a[j] = gelu_fast(a[j]);
     } else if (e.act == ACT_HALF_TANH) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = 0.5f * tanhf(a[j]);
@@ -374,8 +392,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
             }
         }
     } else if (warp >= 4) {
-        // 8 epilogue warps: TMEM lane quarter q = warp % 4 (hardware restriction), column half = (warp - 4) / 4
-        const int q = warp & 3, half = (warp - 4) >> 2;
+        // 16 epilogue warps: TMEM lane quarter q = warp % 4 (hardware restriction), column quarter cq = (warp - 4) / 4:
+        // four warps per SM sub-partition hide the TMEM-load / shared-memory latencies of the short per-block chain
+        const int q = warp & 3, cq = (warp - 4) >> 2;
         const int r = q * 32 + lane;
         const bool issuer = (warp == 4 && lane == 0);
         uint8_t* stg = base + (size_t)p.stages * stage_bytes;
@@ -418,16 +437,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                         epi_barrier();
                     }
 #pragma unroll 1
-                    for (int sub = 0; sub < 4; ++sub) {
-                        const int c = kb + half * 32 + sub * 8;
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int c = kb + cq * 16 + sub * 8;
                         uint32_t raw[8];
                         tmem_ld8(trow + (uint32_t)c, raw);
                         tmem_ld_wait();
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j]);
-                        epi_math8(e, sBias, row, n0 + c, ocb + half * 32 + sub * 8, v, p.ld_vec != 0);
-                        const int jj = half * 4 + sub;
+                        epi_math8(e, sBias, row, n0 + c, ocb + cq * 16 + sub * 8, v, p.ld_vec != 0);
+                        const int jj = cq * 2 + sub;
                         const uint32_t off = (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4));
                         *reinterpret_cast<uint4*>(sb + off) = pack8_bf16(v);
                         if (e.out2) {
@@ -453,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
             } else if (p.store_mode == STORE_NCHW3) {
                 // final subpel conv (N = 12 -> 3 channels): column (2r+s)*3 + ch -> out[b][ch][2h+r][2w+s], fp32 NCHW;
                 // consecutive lanes hold consecutive w, so every float2 store instruction writes whole 128-byte lines.
-                if (half == 0) {
+                if (cq == 0) {
                     uint32_t raw[16];
                     tmem_ld16(trow, raw);
                     tmem_ld_wait();
@@ -473,11 +492,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
             } else {
-                // STORE_DIRECT: 32-column chunks are dealt to the two halves alternately (BN is a multiple of 16)
-                for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
-                    const int nsub = (p.BN - c0) >= 32 ? 4 : (p.BN - c0) / 8;
+                // STORE_DIRECT: 16-column chunks are dealt to the four column quarters in turn (BN is a multiple of 16)
+                for (int c0 = cq * 16; c0 < p.BN; c0 += 64) {
 #pragma unroll 1
-                    for (int sub = 0; sub < nsub; ++sub) {
+                    for (int sub = 0; sub < 2; ++sub) {
                         const int c = c0 + sub * 8, n = n0 + c;
                         uint32_t raw[8];
                         tmem_ld8(trow + (uint32_t)c, raw);

@@ -164,10 +164,55 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const T* __restrict
     }
 }
 
+// 1x1 convolution with Cin <= 4 (the two 3 -> N layers that read the image): store-bound, so one thread produces 8
+// output columns of one pixel; same k-order fp32 FMA chain as the GEMM kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) pw_small_cin_kernel(const T* __restrict__ in, ConvGeom g, const float* __restrict__ Wt,
+                                                           Epi e, int vec) {
+    // thread = (pixel lane, 8-column group); the group's weights stay in registers across the pixel loop
+    const int ng = (e.N + 7) / 8;
+    const int cgp = threadIdx.x % ng, pl = threadIdx.x / ng, npl = blockDim.x / ng;
+    if (pl >= npl) return;
+    const int n = cgp * 8;
+    float wr[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wr[j][c] = (n + j < e.N && c < g.Cin) ? Wt[(size_t)(n + j) * g.Cin + c] : 0.f;
+    const long long npix = (long long)g.B * g.Hout * g.Wout;
+    for (long long pix = (long long)blockIdx.x * npl + pl; pix < npix; pix += (long long)gridDim.x * npl) {
+        const int w = (int)(pix % g.Wout);
+        long long q = pix / g.Wout;
+        const int h = (int)(q % g.Hout);
+        const int b = (int)(q / g.Hout);
+        const T* ip = in + (((size_t)b * g.H + (size_t)h * g.stride) * g.W + (size_t)w * g.stride) * g.ld;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c < g.Cin) x[c] = to_f<T>(ip[c]);
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c < g.Cin) acc = fmaf(x[c], wr[j][c], acc);
+            a[j] = acc;
+        }
+        epi_store4<T>(e, b, h, w, n, a, vec != 0);
+        epi_store4<T>(e, b, h, w, n + 4, a + 4, vec != 0);
+    }
+}
+
 void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const float* Wt, const Epi& e, int vec,
                            cudaStream_t s) {
     long long Mtot = (long long)g.B * g.Hout * g.Wout;
     if (Mtot == 0 || e.N == 0) return;
+    if (g.ks == 1 && g.pad == 0 && g.Cin <= 4 && e.N <= 2048) {
+        const int npl = 256 / ((e.N + 7) / 8);
+        int blocks = (int)std::min<long long>(cdiv(Mtot, npl), 148LL * 16);
+        if (bf) pw_small_cin_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)in, g, Wt, e, vec);
+        else pw_small_cin_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, g, Wt, e, vec);
+        return;
+    }
     dim3 grid(cdiv(Mtot, GM), cdiv(e.N, GN));
     if (bf) conv_gemm_simt_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, g, Wt, e, vec);
     else conv_gemm_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)in, g, Wt, e, vec);
@@ -230,8 +275,99 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in
     }
 }
 
+// bf16 fast path: one block stages a (TH*S+2) x (TW*S+2) pixel x 64-channel input patch in shared memory with
+// 16-byte loads (8 lanes per pixel = one full 128-byte line), then every thread produces 8 channels of one output
+// pixel per step from shared memory: the 9-tap reuse never goes back to L2, and every global access is a full line.
+template <int S>
+struct DwTile { static constexpr int TH = S == 1 ? 8 : 4, TW = S == 1 ? 32 : 16, IH = TH * S + 2, IW = TW * S + 2; };
+
+template <int S>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_tiled_kernel(const bf16* __restrict__ in, int H, int W, int C, int ild,
+                                                              bf16* __restrict__ out, int Ho, int Wo, int old,
+                                                              const float* __restrict__ w9, const float* __restrict__ bias,
+                                                              int act, int tilesW, int tilesH) {
+    using TT = DwTile<S>;
+    __shared__ __align__(16) bf16 sIn[TT::IH * TT::IW * 64];
+    const int cb = blockIdx.y * 64;                 // channel block
+    const int b = blockIdx.z;
+    const int th = blockIdx.x / tilesW, tw = blockIdx.x - th * tilesW;
+    const int oh0 = th * TT::TH, ow0 = tw * TT::TW;
+    const int ih0 = oh0 * S - 1, iw0 = ow0 * S - 1;
+    const int cg = threadIdx.x & 7;                 // 8-channel group inside the 64-channel block
+    const int c = cb + cg * 8;
+    const bool cok = c < C;                          // C % 8 == 0 (host-checked)
+    // stage the input patch (zero outside the image / channel range)
+    for (int i = threadIdx.x >> 3; i < TT::IH * TT::IW; i += 32) {
+        const int py = i / TT::IW, px = i - py * TT::IW;
+        const int ih = ih0 + py, iw = iw0 + px;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (cok && ih >= 0 && ih < H && iw >= 0 && iw < W)
+            v = *reinterpret_cast<const uint4*>(in + (((size_t)b * H + ih) * W + iw) * ild + c);
+        *reinterpret_cast<uint4*>(sIn + (size_t)i * 64 + cg * 8) = v;
+    }
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+        if (cok) { w0 = *reinterpret_cast<const float4*>(w9 + t * C + c); w1 = *reinterpret_cast<const float4*>(w9 + t * C + c + 4); }
+        wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
+        wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
+    }
+    {
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (cok) { b0 = *reinterpret_cast<const float4*>(bias + c); b1 = *reinterpret_cast<const float4*>(bias + c + 4); }
+        br[0] = b0.x; br[1] = b0.y; br[2] = b0.z; br[3] = b0.w; br[4] = b1.x; br[5] = b1.y; br[6] = b1.z; br[7] = b1.w;
+    }
+    __syncthreads();
+    if (!cok) return;
+    for (int p = threadIdx.x >> 3; p < TT::TH * TT::TW; p += 32) {
+        const int oy = p / TT::TW, ox = p - oy * TT::TW;
+        const int oh = oh0 + oy, ow = ow0 + ox;
+        if (oh >= Ho || ow >= Wo) continue;
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const uint4 t = *reinterpret_cast<const uint4*>(sIn + (size_t)((oy * S + ky) * TT::IW + ox * S + kx) * 64 + cg * 8);
+                const uint32_t wv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a[2 * k] = fmaf(__uint_as_float(wv[k] << 16), wr[ky * 3 + kx][2 * k], a[2 * k]);
+                    a[2 * k + 1] = fmaf(__uint_as_float(wv[k] & 0xffff0000u), wr[ky * 3 + kx][2 * k + 1], a[2 * k + 1]);
+                }
+            }
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v0 = a[2 * k] + br[2 * k], v1 = a[2 * k + 1] + br[2 * k + 1];
+            if (act == ACT_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+            __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+            o[k] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oh) * Wo + ow) * old + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act,
                       cudaStream_t s) {
+    if (bf && (in.C % 8 == 0) && (in.ld % 8 == 0) && (out.ld % 8 == 0) && (((uintptr_t)in.p) % 16 == 0) &&
+        (((uintptr_t)out.p) % 16 == 0) && (stride == 1 || stride == 2) && out.B > 0 && out.H > 0 && out.W > 0) {
+        if (stride == 1) {
+            const int tw = cdiv(out.W, DwTile<1>::TW), th = cdiv(out.H, DwTile<1>::TH);
+            dim3 grid(tw * th, cdiv(in.C, 64), out.B);
+            dwconv3x3_tiled_kernel<1><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+                                                           out.ld, w9, bias, act, tw, th);
+        } else {
+            const int tw = cdiv(out.W, DwTile<2>::TW), th = cdiv(out.H, DwTile<2>::TH);
+            dim3 grid(tw * th, cdiv(in.C, 64), out.B);
+            dwconv3x3_tiled_kernel<2><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+                                                           out.ld, w9, bias, act, tw, th);
+        }
+        return;
+    }
     const int esz = bf ? 2 : 4;
     bool vec = (in.C % 4 == 0) && (in.ld % 4 == 0) && (out.ld % 4 == 0) &&
                (((uintptr_t)in.p) % (4 * esz) == 0) && (((uintptr_t)out.p) % (4 * esz) == 0);
@@ -570,21 +706,31 @@ size_t lin_attn_scratch_floats(int B, int heads, int hd, int HW) {
 }
 
 template <typename T>
-__global__ void lin_colmax_kernel(const T* __restrict__ qkv, int ld, int D, int H, int W, int nch, int par,
-                                  float* __restrict__ pmax) {
-    const int b = blockIdx.y, ch = blockIdx.x;
+__global__ void __launch_bounds__(256) lin_colmax_kernel(const T* __restrict__ qkv, int ld, int D, int H, int W, int nch,
+                                                         int par, float* __restrict__ pmax) {
+    // block = (chunk, 32-channel group, b); thread = (position lane 0..7, channel 0..31)
+    __shared__ float sm[8][33];
+    const int ch = blockIdx.x, b = blockIdx.z;
+    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + cl;
     const int HW = H * W;
     const int per = (HW + nch - 1) / nch;
     const int p0 = ch * per, p1 = min(HW, p0 + per);
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        float m = -INFINITY;
-        for (int p = p0; p < p1; ++p) {
+    float m = -INFINITY;
+    if (c < D) {
+        for (int p = p0 + pl; p < p1; p += 8) {
             if (par != PAR_NONE) {
                 int h = p / W, w = p - h * W;
                 if (!parity_keep(par, h, w)) continue;
             }
             m = fmaxf(m, to_f<T>(qkv[((size_t)b * HW + p) * ld + D + c]));
         }
+    }
+    sm[pl][cl] = m;
+    __syncthreads();
+    if (pl == 0 && c < D) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, sm[k][cl]);
         pmax[((size_t)b * nch + ch) * D + c] = m;
     }
 }
@@ -734,7 +880,7 @@ int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv
     float* ctx = pctx + (size_t)B * heads * nch * (hd * hd + hd);
 #define LIN_LAUNCH(T, HD)                                                                                          \
     do {                                                                                                           \
-        lin_colmax_kernel<T><<<dim3(nch, B), 128, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax);    \
+        lin_colmax_kernel<T><<<dim3(nch, (D + 31) / 32, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax); \
         lin_ctx_kernel<T, HD><<<dim3(nch, heads, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv,   \
                                                                   pmax, pctx);                                     \
         lin_ctx_reduce_kernel<HD><<<dim3(heads, B), 256, 0, s>>>(pctx, nch, ctx);                                  \
