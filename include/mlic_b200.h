@@ -94,9 +94,11 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
 
 /* Stand-alone fused quantise / likelihood / CDF-index kernel on NCHW fp32 device tensors of one slice
  * (CompressAI GaussianConditional.forward / quantize / build_indexes; call sites models/mlicpp.py:132-134,
- * utils/ckbd.py:128-129).  y, scales, means, y_hat, lik: [n]; sym, idx: [n] (any may be NULL among outputs). */
-int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, float* y_hat,
-                              float* lik, int32_t* sym, int32_t* idx, void* cuda_stream);
+ * utils/ckbd.py:128-129).  y, scales, means, y_hat, lik: [n]; sym, idx: [n] (any may be NULL among outputs).
+ * scale_table64: the 64-entry fp32 scale table on the device (gaussian_conditional.scale_table), or NULL for the
+ * engine's own exp(linspace(log .11, log 256, 64)). */
+int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, const float* scale_table64,
+                              float* y_hat, float* lik, int32_t* sym, int32_t* idx, void* cuda_stream);
 
 const char* mlic_last_error(void);
 const char* mlic_version(void);

@@ -57,7 +57,7 @@ def lib():
     L.mlic_profile_read.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.mlic_conv2d_nhwc.argtypes = [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32,
                                    C.POINTER(f32), vp]
-    L.mlic_gaussian_conditional.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp]
+    L.mlic_gaussian_conditional.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
     L.mlic_last_error.restype = C.c_char_p
     L.mlic_version.restype = C.c_char_p
     _lib = L

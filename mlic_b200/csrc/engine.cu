@@ -1008,8 +1008,8 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
     return 0;
 }
 
-int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, float* y_hat,
-                              float* lik, int32_t* sym, int32_t* idx, void* cuda_stream) {
+int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, const float* scale_table64,
+                              float* y_hat, float* lik, int32_t* sym, int32_t* idx, void* cuda_stream) {
     static float* table = nullptr;          // utils/func.py:16-19, fp32
     if (!table) {
         float tab[64];
@@ -1018,7 +1018,7 @@ int mlic_gaussian_conditional(const float* y, const float* scales, const float* 
         CUDA_OK(cudaMalloc((void**)&table, sizeof tab));
         CUDA_OK(cudaMemcpy(table, tab, sizeof tab, cudaMemcpyHostToDevice));
     }
-    launch_gc_flat(y, scales, means, n, y_hat, lik, sym, idx, table, 64, (cudaStream_t)cuda_stream);
+    launch_gc_flat(y, scales, means, n, y_hat, lik, sym, idx, scale_table64 ? scale_table64 : table, 64, (cudaStream_t)cuda_stream);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -230,6 +230,8 @@ class MLICPlusPlus(nn.Module):
         """One engine call.  x: CUDA tensor (device path) or CPU tensor (host path through mlic_run_host)."""
         if H % 64 or W % 64:
             raise ValueError("H and W must be multiples of 64 (the reference pads, utils/testing.py:130-137)")
+        if not torch.cuda.is_available():
+            raise _lib.MlicError("mlic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         host = x is not None and not x.is_cuda
         dev = torch.device("cuda", torch.cuda.current_device()) if (host or x is None) else x.device
         L = self._sync_engine(dev)
@@ -343,9 +345,9 @@ class MLICPlusPlusVbr(MLICPlusPlus):
             return float(inputscale)
         if absolute:                                   # mlicpp_vbr.py:540-543
             assert s in range(0, self.levels), f"s should in range(0, {self.levels}), but get s:{s}"
-            return abs(float(self.Gain[s]))
+            return abs(float(self.Gain[s].detach()))
         s = max(0, min(int(s), self.Gain.numel() - 1))  # mlicpp_vbr.py:122-135
-        return float(self.Gain[s])
+        return float(self.Gain[s].detach())
 
     @torch.no_grad()
     def forward(self, x, stage=2, s=1, inputscale=0, *, taps=()):

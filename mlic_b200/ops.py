@@ -33,16 +33,20 @@ def conv2d_nhwc(x, weight, bias=None, stride=1, pad=0, act=None, shuffle=False, 
     return out, float(ms.value)
 
 
-def gaussian_conditional(y, scales, means):
+def gaussian_conditional(y, scales, means, scale_table=None):
     """Fused quantise / likelihood / CDF-index on flat fp32 CUDA tensors -> (y_hat, lik, symbols, indexes)."""
     n = y.numel()
+    tab = None if scale_table is None else scale_table.detach().to(y.device, torch.float32).contiguous()
+    assert tab is None or tab.numel() == 64
     y_hat, lik = torch.empty_like(y), torch.empty_like(y)
     sym = torch.empty(y.shape, dtype=torch.int32, device=y.device)
     idx = torch.empty(y.shape, dtype=torch.int32, device=y.device)
     with torch.cuda.device(y.device):
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.lib().mlic_gaussian_conditional(C.c_void_p(y.data_ptr()), C.c_void_p(scales.data_ptr()),
-                                                        C.c_void_p(means.data_ptr()), n, C.c_void_p(y_hat.data_ptr()),
+                                                        C.c_void_p(means.data_ptr()), n,
+                                                        C.c_void_p(tab.data_ptr()) if tab is not None else None,
+                                                        C.c_void_p(y_hat.data_ptr()),
                                                         C.c_void_p(lik.data_ptr()), C.c_void_p(sym.data_ptr()),
                                                         C.c_void_p(idx.data_ptr()), C.c_void_p(st)))
     return y_hat, lik, sym, idx

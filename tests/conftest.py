@@ -1,0 +1,55 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+# name, B, H, W  (fixtures produced by oracle/make_golden.py from the unmodified reference)
+CASES = [("MLICPP_S", 2, 64, 128), ("MLICPP_L", 1, 64, 128), ("MLICPP_M_SMALL_DEC", 1, 64, 128),
+         ("MLICPP_S_VBR", 1, 64, 128), ("MLICPP_L_VBR", 1, 64, 64)]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_case(name, B, H, W):
+    """-> (golden npz, seeded state_dict incl. the scale table, input image) for one fixture."""
+    import mlic_b200
+    from oracle import weights
+    g = np.load(os.path.join(GOLDEN, f"{name}_b{B}_{H}x{W}.npz"))
+    net = mlic_b200.get_model(name)
+    sd = weights.seeded_state_dict(net.state_dict(), int(g["meta"][3]), y_gain=float(g["y_gain"]),
+                                   sigma_spread=float(g["sigma_spread"]))
+    sd["gaussian_conditional.scale_table"] = mlic_b200.get_scale_table()
+    x = weights.synthetic_image(B, H, W, seed=2024)
+    return g, sd, x
+
+
+def build_model(name, sd, device=None):
+    import mlic_b200
+    net = mlic_b200.get_model(name)
+    net.load_state_dict(sd)
+    net.update(force=True)
+    return net.to(device) if device else net
+
+
+@pytest.fixture(scope="session")
+def lib_built():
+    from mlic_b200 import build
+    return build.build()
