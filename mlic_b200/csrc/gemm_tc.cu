@@ -86,6 +86,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -147,7 +152,10 @@ struct TcParams {
     int epi_vec;            // STORE_DIRECT: 16-byte epilogue accesses are legal for every pointer involved
     int ld_vec;             // 16-byte loads of the residual / GDN operand are legal
     int store_mode;
-    int nstg;               // STORE_TMA: staging buffers (1 or 2) of 16 KB behind the stage ring
+    int nstg;               // STORE_TMA: 16 KB staging buffers behind the stage ring (ring slots x buffers per block)
+    int b_resident;         // 1: the whole weight matrix (all K chunks x BN rows, tilesN == 1) is loaded into shared
+                            //    memory once per CTA; the ring then carries only the A patches
+    int l2_prefetch;        // > 0 (1x1 convs): prefetch the A patch of the tile this many iterations ahead into L2
     int debug;              // development only: bit0 skip epilogue stores, bit1 skip TMEM loads
 };
 
@@ -211,30 +219,41 @@ struct EpiRow {
     const bf16* rp;      // residual row (at output channel 0 of this pixel) or null
     bool keep_pre, keep_post;
 };
+__device__ __forceinline__ void unpack8_bf16(const uint4 t, float v[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+// STAGED: the GDN operand / residual chunk of this thread was prefetched into the staging slot (xs / rs, shared memory)
+template <int ACT, int GDN, bool RES, bool STAGED>
 __device__ __forceinline__ void epi_math8(const Epi& e, const float* __restrict__ sBias, const EpiRow& row, int n, int oc,
-                                          float* a, bool ldvec) {
+                                          float* a, bool ldvec, const uint8_t* xs = nullptr, const uint8_t* rs = nullptr) {
     const bool full = ldvec && n + 8 <= e.N;
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = (row.keep_pre ? a[j] : 0.0f) + sBias[n + j];
-    if (row.xp) {
+    if constexpr (GDN != GDN_NONE) {
         float x[8];
-        if (full) load8_bf16(row.xp + n, x);
-        else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = (n + j < e.N) ? __bfloat162float(row.xp[n + j]) : 0.f;
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        if constexpr (STAGED) {
+            unpack8_bf16(*reinterpret_cast<const uint4*>(xs), x);
+        } else if (row.xp) {
+            if (full) load8_bf16(row.xp + n, x);
+            else {
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) if (n + j < e.N) x[j] = __bfloat162float(row.xp[n + j]);
+            }
         }
-        if (e.gdn == GDN_FWD) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = x[j] * rsqrtf(a[j]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = x[j] * sqrtf(a[j]);
-        }
+        for (int j = 0; j < 8; ++j) a[j] = x[j] * (GDN == GDN_FWD ? rsqrtf(a[j]) : sqrtf(a[j]));
     }
-    if (e.act == ACT_GELU) {
+    if constexpr (ACT == ACT_GELU) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = gelu_fast(a[j]);
-    } else if (e.act == ACT_HALF_TANH) {
+    } else if constexpr (ACT == ACT_HALF_TANH) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = 0.5f * tanhf(a[j]);
     }
@@ -242,15 +261,24 @@ __device__ __forceinline__ void epi_math8(const Epi& e, const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = 0.0f;
     }
-    if (row.rp) {
+    if constexpr (RES && STAGED) {
         float r[8];
-        if (full) load8_bf16(row.rp + oc, r);
-        else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = (n + j < e.N) ? __bfloat162float(row.rp[oc + j]) : 0.f;
-        }
+        unpack8_bf16(*reinterpret_cast<const uint4*>(rs), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] += r[j];
+    } else if constexpr (RES) {
+        if (row.rp) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = 0.f;
+            if (full) load8_bf16(row.rp + oc, r);
+            else {
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) if (n + j < e.N) r[j] = __bfloat162float(row.rp[oc + j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += r[j];
+        }
     }
 }
 
@@ -302,18 +330,36 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most `pending` of the committed store groups are still reading shared memory
+__device__ __forceinline__ void tma_store_wait_read(int pending) {
+    if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    else if (pending == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory"); }
 
 // Persistent kernel: grid = min(#tiles, #SMs); every role walks the same static tile sequence
 // t = blockIdx.x, blockIdx.x + gridDim.x, ...  (N-tile fastest, so co-running CTAs share the A patch in L2).
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e) {
+template <int ACT, int GDN, bool RES>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e,
+                                                                      unsigned long long* __restrict__ dbg) {
+    // dbg (development only, may be null): per CTA {total, producer wait-empty, mma wait-full, mma wait-acc-empty,
+    // epilogue wait-acc-full (warp 4), epilogue busy (warp 4)} in SM clocks
+    const long long t_start = clock64();
+    long long w0c = 0, w1c = 0, w2c = 0, w3c = 0;
+#define TIMED_WAIT(acc, bar, par) do { if (dbg) { long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * 128;
-    const int stage_bytes = TC_A_BYTES + b_bytes;      // multiple of 1024
-    __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_full[2], acc_empty[2];
+    const int stage_bytes = TC_A_BYTES + (p.b_resident ? 0 : b_bytes);      // multiple of 1024
+    const int ksteps_total = p.ks * p.ks * p.kchunks;
+    // layout: [resident B: ksteps x b_bytes]? [ring: stages x stage_bytes] [staging]
+    uint8_t* bres = base;
+    if (p.b_resident) base += (size_t)ksteps_total * b_bytes;
+    __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_full[2], acc_empty[2], bres_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float sBias[TC_MAX_BIAS];
 
@@ -327,7 +373,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
+        // accumulator release: one arrival per epilogue warp that reads it (TMA-store mode: 4 warps per 64-column block)
+        const uint32_t nrel = p.store_mode == STORE_TMA ? 4u * (uint32_t)((p.BN + 63) / 64) : (uint32_t)TC_EPI_WARPS;
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], nrel); }
+        mbar_init(&bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -346,20 +395,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if (p.b_resident) {              // weights once per CTA: every K chunk of the (single) N tile
+                mbar_expect_tx(&bres_bar, (uint32_t)(ksteps * b_bytes));
+                for (int k = 0; k < ksteps; ++k) {
+                    const int tap = k / p.kchunks, cc = k - tap * p.kchunks;
+                    tma_load_2d(bres + (size_t)k * b_bytes, &tm.b, &bres_bar, tap * p.Cpad + cc * 64, 0);
+                }
+            }
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
                 const int nt = t % p.tilesN, mt = t / p.tilesN;
                 const int img = mt / tiles_per_img;
                 const int trem = mt - img * tiles_per_img;
                 const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
                 const int h0 = th * p.TH, w0 = tw * p.TW, n0 = nt * p.BN;
+                if (p.l2_prefetch && nt == 0) {
+                    // HBM-bound pointwise layers: the shared-memory ring holds < 100 KB per SM, not enough bytes in flight
+                    // to cover the DRAM latency; pull the A patch of a tile several iterations ahead into L2
+                    const int tp = t + p.l2_prefetch * (int)gridDim.x;
+                    if (tp < p.ntiles) {
+                        const int mp = tp / p.tilesN;
+                        const int ip = mp / tiles_per_img;
+                        const int rp = mp - ip * tiles_per_img;
+                        const int hp = (rp / p.tilesW) * p.TH, wp = (rp % p.tilesW) * p.TW;
+                        for (int cc = 0; cc < p.kchunks; ++cc) tma_prefetch_4d(&tm.a, cc * 64, wp, hp, ip);
+                    }
+                }
                 for (int k = 0; k < ksteps; ++k) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
                     const int tap = k / p.kchunks, cc = k - tap * p.kchunks;
                     const int ky = tap / p.ks, kx = tap - ky * p.ks;
                     uint8_t* sa = base + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                     tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
-                    tma_load_2d(sa + TC_A_BYTES, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
+                    if (!p.b_resident) tma_load_2d(sa + TC_A_BYTES, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -371,17 +439,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            if (p.b_resident) { mbar_wait(&bres_bar, 0); tcgen05_fence_after(); }
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
                 const int as = it & 1;
-                mbar_wait(&acc_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                TIMED_WAIT(w2c, &acc_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t dcol = tmem_base + (uint32_t)(as * p.acc_stride);
                 for (int k = 0; k < ksteps; ++k) {
-                    mbar_wait(&full_bar[stage], phase);
+                    TIMED_WAIT(w1c, &full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
                     const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(sa + TC_A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(p.b_resident ? smem_u32(bres + (size_t)k * b_bytes) : sa + TC_A_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)      // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
                         umma_bf16(dcol, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
@@ -396,13 +465,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         // four warps per SM sub-partition hide the TMEM-load / shared-memory latencies of the short per-block chain
         const int q = warp & 3, cq = (warp - 4) >> 2;
         const int r = q * 32 + lane;
-        const bool issuer = (warp == 4 && lane == 0);
         uint8_t* stg = base + (size_t)p.stages * stage_bytes;
-        const int per = e.out2 ? 2 : 1;             // staging buffers per 64-column block (out [+ out2])
-        const uint32_t nring = (uint32_t)(p.nstg / per);
+        const int per = (e.out2 || GDN != GDN_NONE) ? 2 : 1;      // staging buffers per 64-column block (out/res [+ out2 | GDN operand])
+        const uint32_t nring = p.store_mode == STORE_TMA ? (uint32_t)(p.nstg / (((p.BN + 63) / 64) * per)) : 1u;   // slots per group
         uint32_t blk = 0;
         int it = 0;
-        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+        const bool idle = p.store_mode == STORE_TMA && cq * 64 >= p.BN;     // this warp group owns no columns
+        for (int t = blockIdx.x; t < p.ntiles && !idle; t += gridDim.x, ++it) {
             const int nt = t % p.tilesN, mt = t / p.tilesN;
             const int img = mt / tiles_per_img;
             const int trem = mt - img * tiles_per_img;
@@ -415,58 +484,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
             EpiRow row;
             row.keep_pre = parity_keep(e.premask, h, w);
             row.keep_post = parity_keep(e.postmask, h, w);
-            row.xp = (e.gdn && valid) ? reinterpret_cast<const bf16*>(e.gdn_x) + (((size_t)img * e.Hout + h) * e.Wout + w) * e.gdn_ld : nullptr;
-            mbar_wait(&acc_full[as], (uint32_t)(it >> 1) & 1u);
-            tcgen05_fence_after();
+            row.xp = (GDN != GDN_NONE && valid) ? reinterpret_cast<const bf16*>(e.gdn_x) + (((size_t)img * e.Hout + h) * e.Wout + w) * e.gdn_ld : nullptr;
+            if (p.store_mode != STORE_TMA) {         // (TMA-store mode waits after its operand prefetch)
+                TIMED_WAIT(w3c, &acc_full[as], (uint32_t)(it >> 1) & 1u);
+                tcgen05_fence_after();
+            }
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride);
             if (p.store_mode == STORE_TMA) {
-                // 64-column blocks: the two halves fill one swizzled 16 KB staging block (two with the x^2 side output),
-                // then one TMA store per block writes it out with full 128-byte lines.
-                for (int kb = 0; kb < p.BN; kb += 64) {
+                // One 64-column block per warp GROUP (4 warps = the 4 TMEM lane quarters): group cq owns columns
+                // [64 cq, 64 cq + 64) of every tile, its own swizzled 16 KB staging slot(s), its own named barrier and its
+                // own TMA-store issuer, so the blocks of a tile drain concurrently instead of one after the other.
+                const int kb = cq * 64;
+                if (kb < p.BN) {
                     int g = 0, ocb = n0 + kb;                       // the whole block lies in one pixel-shuffle group
                     if (e.shuffle) { const int Cq = e.N >> 2; g = ocb / Cq; ocb -= g * Cq; }
-                    row.rp = nullptr;
-                    if (e.res && valid) {
-                        int oh, ow, oc, OH, OW;
-                        out_coord(e, h, w, n0 + kb, oh, ow, oc, OH, OW);
-                        row.rp = reinterpret_cast<const bf16*>(e.res) + (((size_t)img * OH + oh) * OW + ow) * e.res_ld;
+                    const bool gissuer = (q == 0 && lane == 0);
+                    uint8_t* sb = stg + (size_t)((cq * nring + (blk % nring)) * per) * TC_STG_BYTES;
+                    long long tq0 = dbg ? clock64() : 0;
+                    if (nring == 1) {               // single slot: this group's previous store must have drained it
+                        if (gissuer) tma_store_wait_read(0);
+                        asm volatile("bar.sync %0, 128;" ::"r"(cq + 1) : "memory");
                     }
-                    uint8_t* sb = stg + (size_t)((blk % nring) * per) * TC_STG_BYTES;
-                    if (nring == 1) {               // single ring slot: the previous block's stores must have drained it
-                        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        epi_barrier();
+                    if constexpr (RES || GDN != GDN_NONE) {
+                        // Operand prefetch (no pixel shuffle in this mode): the warp pulls the residual / GDN-operand block of
+                        // its 32 pixels with coalesced 16-byte loads (8 lanes = one 128-byte pixel row) straight into the
+                        // staging slot, in the swizzled layout of the output block; all loads are in flight together and
+                        // complete while the warp waits for the accumulator.  The result later overwrites the residual in place.
+                        uint4 rr[8], xx[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int prow = q * 32 + i * 4 + (lane >> 3);
+                            const int ph = h0 + prow / p.TW, pw = w0 + prow % p.TW;
+                            const int col = n0 + kb + (lane & 7) * 8;
+                            const bool ok = ph < e.Hout && pw < e.Wout && col + 8 <= e.N;
+                            const size_t pix = ((size_t)img * e.Hout + ph) * e.Wout + pw;
+                            rr[i] = make_uint4(0, 0, 0, 0); xx[i] = make_uint4(0, 0, 0, 0);
+                            if (RES && ok) rr[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + pix * e.res_ld + col);
+                            if (GDN != GDN_NONE && ok) xx[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.gdn_x) + pix * e.gdn_ld + col);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int prow = q * 32 + i * 4 + (lane >> 3);
+                            const uint32_t off = (uint32_t)(prow * 128 + (((lane & 7) ^ (prow & 7)) << 4));
+                            if (RES) *reinterpret_cast<uint4*>(sb + off) = rr[i];
+                            if (GDN != GDN_NONE) *reinterpret_cast<uint4*>(sb + TC_STG_BYTES + off) = xx[i];
+                        }
+                        __syncwarp();
                     }
+                    if (dbg) { long long _t = clock64(); mbar_wait(&acc_full[as], (uint32_t)(it >> 1) & 1u); w3c += clock64() - _t; }
+                    else mbar_wait(&acc_full[as], (uint32_t)(it >> 1) & 1u);
+                    tcgen05_fence_after();
+                    long long tq1 = dbg ? clock64() : 0;
 #pragma unroll 1
-                    for (int sub = 0; sub < 2; ++sub) {
-                        const int c = kb + cq * 16 + sub * 8;
-                        uint32_t raw[8];
-                        tmem_ld8(trow + (uint32_t)c, raw);
+                    for (int pr = 0; pr < 4; ++pr) {
+                        // two 8-column groups are fetched from TMEM before any arithmetic
+                        const int c = kb + pr * 16;
+                        uint32_t raw[2][8];
+                        tmem_ld8(trow + (uint32_t)c, raw[0]);
+                        tmem_ld8(trow + (uint32_t)(c + 8), raw[1]);
                         tmem_ld_wait();
-                        float v[8];
+                        if (pr == 3) {              // accumulator fully read by this warp: hand the TMEM stage back
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[as]);
+                        }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j]);
-                        epi_math8(e, sBias, row, n0 + c, ocb + cq * 16 + sub * 8, v, p.ld_vec != 0);
-                        const int jj = cq * 2 + sub;
-                        const uint32_t off = (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4));
-                        *reinterpret_cast<uint4*>(sb + off) = pack8_bf16(v);
-                        if (e.out2) {
+                        for (int sub = 0; sub < 2; ++sub) {
+                            float v[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
-                            *reinterpret_cast<uint4*>(sb + TC_STG_BYTES + off) = pack8_bf16(v);
+                            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[sub][j]);
+                            const int jj = pr * 2 + sub;
+                            const uint32_t off = (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4));
+                            epi_math8<ACT, GDN, RES, true>(e, sBias, row, n0 + c + sub * 8, ocb + pr * 16 + sub * 8, v, true,
+                                                           sb + TC_STG_BYTES + off, sb + off);
+                            *reinterpret_cast<uint4*>(sb + off) = pack8_bf16(v);
+                            if (e.out2) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
+                                *reinterpret_cast<uint4*>(sb + TC_STG_BYTES + off) = pack8_bf16(v);
+                            }
                         }
                     }
-                    if (kb + 64 >= p.BN) {          // accumulator fully read: hand the TMEM stage back to the MMA warp
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[as]);
-                    }
+                    long long tq2 = dbg ? clock64() : 0;
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (nring > 1 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    epi_barrier();
-                    if (issuer && !(p.debug & 1)) {
+                    // two slots: after this barrier the group's OTHER slot is rewritten next tile; its store must have drained
+                    if (nring > 1 && gissuer) tma_store_wait_read(0);
+                    asm volatile("bar.sync %0, 128;" ::"r"(cq + 1) : "memory");
+                    if (gissuer && !(p.debug & 1)) {
                         tma_store_4d(&tm.o[g], sb, ocb, w0, h0, img);
                         if (e.out2) tma_store_4d(&tm.o2, sb + TC_STG_BYTES, ocb, w0, h0, img);
+                        tma_store_commit();
                     }
+                    if (dbg) { long long tq3 = clock64(); w0c += tq1 - tq0; w1c += tq2 - tq1; w2c += tq3 - tq2; }
                     ++blk;
                 }
             } else if (p.store_mode == STORE_NCHW3) {
@@ -505,12 +614,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[j]);
                         int oc = n;
                         row.rp = nullptr;
-                        if (e.res && valid) {
+                        if (RES && valid) {
                             int oh, ow, OH, OW;
                             out_coord(e, h, w, n, oh, ow, oc, OH, OW);
                             row.rp = reinterpret_cast<const bf16*>(e.res) + (((size_t)img * OH + oh) * OW + ow) * e.res_ld;
                         }
-                        epi_math8(e, sBias, row, n, oc, v, p.ld_vec != 0);
+                        epi_math8<ACT, GDN, RES, false>(e, sBias, row, n, oc, v, p.ld_vec != 0);
                         if (valid && !(p.debug & 1)) direct_store8(e, img, h, w, n, v, p.epi_vec != 0);
                     }
                 }
@@ -519,8 +628,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
             }
         }
-        if (p.store_mode == STORE_TMA && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (p.store_mode == STORE_TMA && q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    if (dbg && lane == 0) {
+        unsigned long long* d = dbg + (size_t)blockIdx.x * 8;
+        if (warp == 0) { d[0] = (unsigned long long)(clock64() - t_start); d[1] = (unsigned long long)w0c; }
+        if (warp == 1) { d[2] = (unsigned long long)w1c; d[3] = (unsigned long long)w2c; }
+        if (warp == 4) { d[4] = (unsigned long long)w3c; d[5] = (unsigned long long)(clock64() - t_start);
+                         d[6] = (unsigned long long)w0c; d[7] = (unsigned long long)w1c; dbg[(size_t)gridDim.x * 8 + blockIdx.x] = (unsigned long long)w2c; }
+    }
+#undef TIMED_WAIT
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -583,21 +700,40 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     // store mode
     p.store_mode = STORE_DIRECT;
     if (e.nchw) p.store_mode = STORE_NCHW3;
-    else if (!e.out_f32 && e.out && ok16(e.out, e.out_ld, 2) && ok16(e.out2, e.out2_ld, 2) && (!e.shuffle || (Cq % 64) == 0) && !(e.shuffle && e.out2))
+    else if (!e.out_f32 && e.out && ok16(e.out, e.out_ld, 2) && ok16(e.out2, e.out2_ld, 2) && (!e.shuffle || (Cq % 64) == 0) && !(e.shuffle && e.out2) &&
+             !(e.out2 && e.gdn) &&
+             (!(e.res || e.gdn) || (!e.shuffle && (e.N % 8) == 0 && ok16(e.res, e.res_ld, 2) && ok16(e.gdn_x, e.gdn_ld, 2))))
         p.store_mode = STORE_TMA;
     { const char* d = getenv("MLIC_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
     if (p.debug & 4) { if (p.store_mode == STORE_TMA) p.store_mode = STORE_DIRECT; }
     p.BN = pick_bn(e.N, p.store_mode == STORE_TMA ? 64 : ((e.shuffle || e.N % 32 == 0) && e.N >= 32 ? 32 : 16));
-    const int stage_bytes = TC_A_BYTES + p.BN * 128;
-    const int budget = 212 * 1024;      // dynamic shared memory (static: bias + barriers ~ 9.5 KB)
-    p.nstg = 0;
-    if (p.store_mode == STORE_TMA) {
-        const int per = e.out2 ? 2 : 1;
-        p.nstg = (budget - 1024 - 2 * per * TC_STG_BYTES) / stage_bytes >= (p.BN > 192 ? 4 : 3) ? 2 * per : per;
+    const int budget0 = 212 * 1024;     // dynamic shared memory (static: bias + barriers ~ 9.5 KB)
+    const int ksteps = p.ks * p.ks * p.kchunks;
+    const int bres_bytes = ksteps * p.BN * 128;
+    const int per = (e.out2 || e.gdn) ? 2 : 1;
+    const int nact = (p.BN + 63) / 64;          // warp groups that own a 64-column block
+    // Shared-memory plan.  Small weight matrices (the 192x192 pointwise / GDN GEMMs) may stay resident (no per-tile B
+    // reload); every active warp group owns `ring` staging slots of `per` 16 KB buffers; the rest is the operand ring.
+    const bool want_bres = p.BN >= e.N && bres_bytes <= 80 * 1024 && ksteps <= 4 && !(p.debug & 8);
+    int stage_bytes = 0;
+    bool planned = false;
+    for (int bres = want_bres ? 1 : 0; bres >= 0 && !planned; --bres) {
+        stage_bytes = TC_A_BYTES + (bres ? 0 : p.BN * 128);
+        const int budget = budget0 - 1024 - (bres ? bres_bytes : 0);
+        for (int ring = (p.store_mode == STORE_TMA ? 2 : 0); ring >= 0 && !planned; --ring) {
+            if (p.store_mode == STORE_TMA && ring == 0) break;
+            const int stg_bytes = nact * ring * per * TC_STG_BYTES;
+            const int st = (budget - stg_bytes) / stage_bytes;
+            const int need = (ring == 2) ? (p.BN > 192 ? 4 : 3) : 2;
+            if (st >= need) {
+                p.b_resident = bres; p.nstg = nact * ring * per;
+                p.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+                planned = true;
+            }
+        }
     }
-    p.stages = (budget - 1024 - p.nstg * TC_STG_BYTES) / stage_bytes;
-    if (p.stages < 2) p.stages = 2;
-    if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+    if (!planned) { snprintf(g_tc_err, sizeof g_tc_err, "no shared-memory plan for BN=%d ksteps=%d", p.BN, ksteps); return 8; }
+    p.l2_prefetch = (p.ks == 1 && !(p.debug & 16)) ? 3 : 0;
     p.acc_stride = 32;
     while (p.acc_stride < p.BN) p.acc_stride <<= 1;
     p.tilesN = (e.N + p.BN - 1) / p.BN;
@@ -658,15 +794,28 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
             if (encode_out_map(&tm.o2, e.out2, e.N, e.Wout, e.Hout, c.B, ld2, (size_t)e.Wout * ld2, (size_t)e.Hout * e.Wout * ld2, p.TW, p.TH)) return 7;
         }
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + (size_t)p.nstg * TC_STG_BYTES + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t er = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, budget + 1024);
+    const size_t smem = (size_t)(p.b_resident ? bres_bytes : 0) + (size_t)p.stages * stage_bytes + (size_t)p.nstg * TC_STG_BYTES + 1024;
+    if (smem > (size_t)budget0 + 1024) { snprintf(g_tc_err, sizeof g_tc_err, "shared-memory plan too large: %zu", smem); return 8; }
+    // one instantiation per (activation, GDN mode, residual): the epilogue only carries the code its layer needs
+    typedef void (*KernelFn)(const TcMaps, TcParams, Epi, unsigned long long*);
+    static const KernelFn table[3][3][2] = {
+        {{conv_gemm_tc_kernel<0, 0, false>, conv_gemm_tc_kernel<0, 0, true>}, {conv_gemm_tc_kernel<0, 1, false>, conv_gemm_tc_kernel<0, 1, true>},
+         {conv_gemm_tc_kernel<0, 2, false>, conv_gemm_tc_kernel<0, 2, true>}},
+        {{conv_gemm_tc_kernel<1, 0, false>, conv_gemm_tc_kernel<1, 0, true>}, {conv_gemm_tc_kernel<1, 1, false>, conv_gemm_tc_kernel<1, 1, true>},
+         {conv_gemm_tc_kernel<1, 2, false>, conv_gemm_tc_kernel<1, 2, true>}},
+        {{conv_gemm_tc_kernel<2, 0, false>, conv_gemm_tc_kernel<2, 0, true>}, {conv_gemm_tc_kernel<2, 1, false>, conv_gemm_tc_kernel<2, 1, true>},
+         {conv_gemm_tc_kernel<2, 2, false>, conv_gemm_tc_kernel<2, 2, true>}}};
+    static bool attr_set[3][3][2] = {};
+    if (e.act < 0 || e.act > 2 || e.gdn < 0 || e.gdn > 2) { snprintf(g_tc_err, sizeof g_tc_err, "bad epilogue mode"); return 9; }
+    const int ri = e.res ? 1 : 0;
+    KernelFn fn = table[e.act][e.gdn][ri];
+    if (!attr_set[e.act][e.gdn][ri]) {
+        cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, budget0 + 1024);
         if (er != cudaSuccess) {
             snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(er));
             return 4;
         }
-        attr_set = true;
+        attr_set[e.act][e.gdn][ri] = true;
     }
     static int num_sms = 0;
     if (!num_sms) {
@@ -676,7 +825,27 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         if (num_sms <= 0) num_sms = 148;
     }
     dim3 grid((unsigned)(p.ntiles < num_sms ? p.ntiles : num_sms));
-    conv_gemm_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tm, p, e);
+    unsigned long long* dbg = nullptr;
+    if (p.debug & 32) {             // development: per-role wait clocks of the first launches, printed to stderr
+        static unsigned long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc((void**)&dbuf, 148 * 9 * sizeof(unsigned long long));
+        cudaMemsetAsync(dbuf, 0, 148 * 9 * sizeof(unsigned long long), s);
+        dbg = dbuf;
+    }
+    fn<<<grid, TC_THREADS, smem, s>>>(tm, p, e, dbg);
+    if (dbg) {
+        static int printed = 0;
+        unsigned long long h[148 * 9];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
+        if (printed++ < 3) {
+            double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (unsigned i = 0; i < grid.x; ++i) { for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid.x; a[8] += (double)h[grid.x * 8 + i] / grid.x; }
+            fprintf(stderr, "[tc dbg] epilogue warp 4: drain-wait %.0f math %.0f fence+barrier+store %.0f\n", a[6], a[7], a[8]);
+            fprintf(stderr, "[tc dbg] BN=%d ksteps=%d stages=%d nstg=%d bres=%d tiles/cta=%.1f | clocks: total %.0f prod-wait-empty %.0f mma-wait-full %.0f mma-wait-accempty %.0f epi-wait-accfull %.0f epi-total %.0f\n",
+                    p.BN, ksteps, p.stages, p.nstg, p.b_resident, (double)p.ntiles / grid.x, a[0], a[1], a[2], a[3], a[4], a[5]);
+        }
+    }
     cudaError_t er = cudaGetLastError();
     if (er != cudaSuccess) {
         snprintf(g_tc_err, sizeof g_tc_err, "conv_gemm_tc launch: %s (smem %zu)", cudaGetErrorString(er), smem);
