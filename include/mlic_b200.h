@@ -92,6 +92,12 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
                      const float* bias, int N, int ks, int stride, int pad, int act, int shuffle, const void* residual,
                      void* out, int iters, float* avg_ms, void* cuda_stream);
 
+/* Stand-alone depthwise 3x3 convolution (pad 1, stride 1 | 2) + bias (+ GELU when act = 1) on an NHWC activation
+ * tensor; weight: HOST fp32 [C][1][3][3] (nn.Conv2d(groups=C) layout, modules/layers/conv.py:49-54), bias: HOST [C].
+ * Timing as mlic_conv2d_nhwc.  Kernel-level test / micro-benchmark hook. */
+int mlic_dwconv3x3_nhwc(int precision, const void* in, int B, int H, int W, int C, const float* weight, const float* bias,
+                        int stride, int act, void* out, int iters, float* avg_ms, void* cuda_stream);
+
 /* Stand-alone fused quantise / likelihood / CDF-index kernel on NCHW fp32 device tensors of one slice
  * (CompressAI GaussianConditional.forward / quantize / build_indexes; call sites models/mlicpp.py:132-134,
  * utils/ckbd.py:128-129).  y, scales, means, y_hat, lik: [n]; sym, idx: [n] (any may be NULL among outputs).

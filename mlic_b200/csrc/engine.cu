@@ -1008,6 +1008,36 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
     return 0;
 }
 
+int mlic_dwconv3x3_nhwc(int precision, const void* in, int B, int H, int W, int Cc, const float* weight, const float* bias,
+                        int stride, int act, void* out, int iters, float* avg_ms, void* cuda_stream) {
+    if (!in || !weight || !bias || !out || iters < 1 || (stride != 1 && stride != 2)) return fail("bad arguments");
+    mlic_engine e;
+    e.N = e.M = e.S = e.C = 0; e.kind = 0; e.sd = e.vbr = false; e.Me = 0; e.rc = 0;
+    HostT w, b;
+    w.shape = {Cc, 1, 3, 3}; w.v.assign(weight, weight + (size_t)Cc * 9);
+    b.shape = {Cc}; b.v.assign(bias, bias + Cc);
+    e.params["d.weight"] = w; e.params["d.bias"] = b;
+    e.pack_dw_list("d", {"d"});
+    if (e.rc) return e.rc;
+    e.bf = precision == MLIC_PREC_BF16; e.dry = false; e.st = (cudaStream_t)cuda_stream;
+    Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cc; a.ld = Cc;
+    Act o; o.p = out; o.B = B; o.H = (H - 1) / stride + 1; o.W = (W - 1) / stride + 1; o.C = Cc; o.ld = Cc;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    e.dwconv(a, "d", stride, act, o);
+    CUDA_OK(cudaEventRecord(e0, e.st));
+    for (int i = 1; i < iters; ++i) e.dwconv(a, "d", stride, act, o);
+    CUDA_OK(cudaEventRecord(e1, e.st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e.rc) return e.rc;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, const float* scale_table64,
                               float* y_hat, float* lik, int32_t* sym, int32_t* idx, void* cuda_stream) {
     static float* table = nullptr;          // utils/func.py:16-19, fp32

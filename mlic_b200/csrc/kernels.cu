@@ -179,12 +179,17 @@ __global__ void __launch_bounds__(256) pw_small_cin_kernel(const T* __restrict__
     for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int c = 0; c < 4; ++c) wr[j][c] = (n + j < e.N && c < g.Cin) ? Wt[(size_t)(n + j) * g.Cin + c] : 0.f;
-    const long long npix = (long long)g.B * g.Hout * g.Wout;
-    for (long long pix = (long long)blockIdx.x * npl + pl; pix < npix; pix += (long long)gridDim.x * npl) {
-        const int w = (int)(pix % g.Wout);
-        long long q = pix / g.Wout;
-        const int h = (int)(q % g.Hout);
-        const int b = (int)(q / g.Hout);
+    const bool simple = vec && n + 8 <= e.N && !e.res && !e.gdn && !e.premask && !e.postmask && !e.shuffle && !e.out2 &&
+                        !e.out_f32 && !e.nchw && e.act != ACT_HALF_TANH;
+    float br[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) br[j] = (e.bias && n + j < e.N) ? e.bias[n + j] : 0.f;
+    const unsigned npix = (unsigned)g.B * g.Hout * g.Wout;         // < 2^31 (host-checked): 32-bit coordinate arithmetic
+    for (unsigned pix = blockIdx.x * npl + pl; pix < npix; pix += gridDim.x * npl) {
+        const unsigned q = pix / (unsigned)g.Wout;
+        const int w = (int)(pix - q * g.Wout);
+        const int b = (int)(q / (unsigned)g.Hout);
+        const int h = (int)(q - (unsigned)b * g.Hout);
         const T* ip = in + (((size_t)b * g.H + (size_t)h * g.stride) * g.W + (size_t)w * g.stride) * g.ld;
         float x[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -197,8 +202,16 @@ __global__ void __launch_bounds__(256) pw_small_cin_kernel(const T* __restrict__
             for (int c = 0; c < 4; ++c) if (c < g.Cin) acc = fmaf(x[c], wr[j][c], acc);
             a[j] = acc;
         }
-        epi_store4<T>(e, b, h, w, n, a, vec != 0);
-        epi_store4<T>(e, b, h, w, n + 4, a + 4, vec != 0);
+        if (simple) {            // bias + optional GELU, dense NHWC store of 8 columns (16 B in bf16)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] += br[j]; if (e.act == ACT_GELU) a[j] = gelu_erf(a[j]); }
+            T* op = reinterpret_cast<T*>(e.out) + (size_t)pix * e.out_ld + n;
+            store4(op, a);
+            store4(op + 4, a + 4);
+        } else {
+            epi_store4<T>(e, b, h, w, n, a, vec != 0);
+            epi_store4<T>(e, b, h, w, n + 4, a + 4, vec != 0);
+        }
     }
 }
 
@@ -206,7 +219,7 @@ void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const floa
                            cudaStream_t s) {
     long long Mtot = (long long)g.B * g.Hout * g.Wout;
     if (Mtot == 0 || e.N == 0) return;
-    if (g.ks == 1 && g.pad == 0 && g.Cin <= 4 && e.N <= 2048) {
+    if (g.ks == 1 && g.pad == 0 && g.Cin <= 4 && e.N <= 2048 && Mtot < (1LL << 31)) {
         const int npl = 256 / ((e.N + 7) / 8);
         int blocks = (int)std::min<long long>(cdiv(Mtot, npl), 148LL * 16);
         if (bf) pw_small_cin_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)in, g, Wt, e, vec);
@@ -333,10 +346,11 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tiled_kernel(const bf16* __r
             for (int kx = 0; kx < 3; ++kx) {
                 const uint4 t = *reinterpret_cast<const uint4*>(sIn + (size_t)((oy * S + ky) * TT::IW + ox * S + kx) * 64 + cg * 8);
                 const uint32_t wv[4] = {t.x, t.y, t.z, t.w};
+                const float* wq = wr[ky * 3 + kx];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    a[2 * k] = fmaf(__uint_as_float(wv[k] << 16), wr[ky * 3 + kx][2 * k], a[2 * k]);
-                    a[2 * k + 1] = fmaf(__uint_as_float(wv[k] & 0xffff0000u), wr[ky * 3 + kx][2 * k + 1], a[2 * k + 1]);
+                    a[2 * k] = fmaf(__uint_as_float(wv[k] << 16), wq[2 * k], a[2 * k]);
+                    a[2 * k + 1] = fmaf(__uint_as_float(wv[k] & 0xffff0000u), wq[2 * k + 1], a[2 * k + 1]);
                 }
             }
         uint32_t o[4];

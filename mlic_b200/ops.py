@@ -33,6 +33,23 @@ def conv2d_nhwc(x, weight, bias=None, stride=1, pad=0, act=None, shuffle=False, 
     return out, float(ms.value)
 
 
+def dwconv3x3_nhwc(x, weight, bias, stride=1, act=None, iters=1):
+    """Depthwise 3x3 (pad 1) on a CUDA NHWC tensor (fp32 or bf16); weight [C,1,3,3], bias [C] -> (out, avg ms)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+    B, H, W, Cc = x.shape
+    w = weight.detach().to("cpu", torch.float32).contiguous()
+    b = bias.detach().to("cpu", torch.float32).contiguous()
+    out = torch.empty((B, (H - 1) // stride + 1, (W - 1) // stride + 1, Cc), dtype=x.dtype, device=x.device)
+    ms = C.c_float(0)
+    prec = _lib.PREC_BF16 if x.dtype == torch.bfloat16 else _lib.PREC_FP32
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_dwconv3x3_nhwc(prec, C.c_void_p(x.data_ptr()), B, H, W, Cc, C.c_void_p(w.data_ptr()),
+                                                  C.c_void_p(b.data_ptr()), stride, ACT[act], C.c_void_p(out.data_ptr()),
+                                                  iters, C.byref(ms), C.c_void_p(st)))
+    return out, float(ms.value)
+
+
 def gaussian_conditional(y, scales, means, scale_table=None):
     """Fused quantise / likelihood / CDF-index on flat fp32 CUDA tensors -> (y_hat, lik, symbols, indexes)."""
     n = y.numel()
