@@ -82,6 +82,7 @@ struct mlic_engine {
     std::map<std::string, HostT> params;
     bool finalized = false;
     int use_tc = 1;
+    int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
 
     std::vector<void*> dev_allocs;
     std::unordered_map<std::string, ConvW> convs;
@@ -407,10 +408,13 @@ struct mlic_engine {
     bool al4(const void* p) const { return ((uintptr_t)p % (size_t)(4 * esz())) == 0; }
 
     // out = epilogue(conv(in, W)); `out` is an activation view of w->N (or N/4 when shuffled) channels.
-    void gemm(const Act& in, const std::string& key, int stride, int pad, const Act* out, const EpiOpt& o) {
+    // prod != 0: tcgen05 kernel with a fused A-operand producer (1: depthwise 3x3 `dwp` of `in`, 2: in^2); returns false
+    // without launching anything when that kernel does not take the layer (the caller then runs the unfused sequence).
+    bool gemm(const Act& in, const std::string& key, int stride, int pad, const Act* out, const EpiOpt& o, int prod = 0,
+              const DwW* dwp = nullptr) {
         const ConvW* w = cw(key);
-        if (!w) return;
-        if (in.C != w->Cin) { if (!rc) rc = fail("gemm '%s': input has %d channels, weights expect %d", key.c_str(), in.C, w->Cin); return; }
+        if (!w) return true;
+        if (in.C != w->Cin) { if (!rc) rc = fail("gemm '%s': input has %d channels, weights expect %d", key.c_str(), in.C, w->Cin); return true; }
         Epi e;
         memset(&e, 0, sizeof e);
         e.bias = w->bias; e.act = o.act; e.premask = o.premask; e.postmask = o.postmask;
@@ -419,26 +423,32 @@ struct mlic_engine {
         e.Wout = (in.W + 2 * pad - w->ks) / stride + 1;
         bool vec = (w->N % 4 == 0);
         if (o.nchw) {
-            if (!dry && !o.out_f32) { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return; }
+            if (!dry && !o.out_f32) { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return true; }
             e.out = o.out_f32; e.out_ld = 0; e.out_f32 = 1; e.nchw = 1; vec = false;
         }
         else if (o.out_f32) { e.out = o.out_f32; e.out_ld = o.out_f32_ld; e.out_f32 = 1; vec = vec && (o.out_f32_ld % 4 == 0) && ((uintptr_t)o.out_f32 % 16 == 0); }
         else if (out) { e.out = out->p; e.out_ld = out->ld; vec = vec && (out->ld % 4 == 0) && al4(out->p); }
-        else { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return; }
+        else { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return true; }
         if (o.res) { e.res = o.res->p; e.res_ld = o.res->ld; vec = vec && (o.res->ld % 4 == 0) && al4(o.res->p); }
         if (o.gdn) { e.gdn = o.gdn; e.gdn_x = o.gdn_x->p; e.gdn_ld = o.gdn_x->ld; vec = vec && (o.gdn_x->ld % 4 == 0) && al4(o.gdn_x->p); }
         if (o.out2) { e.out2 = o.out2->p; e.out2_ld = o.out2->ld; vec = vec && (o.out2->ld % 4 == 0) && al4(o.out2->p); }
         if (w->shuffle && ((w->N / 4) % 4 != 0)) vec = false;
-        if (!go()) return;
+        if (prod && !(bf && use_tc && fuse && stride == 1)) return false;
         if (bf && use_tc && (stride == 1 || w->ks == 1)) {
             TcConv t;
+            memset(&t, 0, sizeof t);
+            t.prod = prod;
+            if (prod == 1) { t.dw_w9 = dwp->w9; t.dw_bias = dwp->bias; }
             t.in = in.p; t.B = in.B; t.Cin = in.C; t.ld = in.ld; t.ks = w->ks; t.pad = pad; t.w = w->wbf; t.Cpad = w->Cpad;
             t.H = e.Hout + (w->ks - 1) - 2 * pad;     // == in.H for stride 1
             t.W = e.Wout + (w->ks - 1) - 2 * pad;
             if (stride == 1) { t.H = in.H; t.W = in.W; }
             else { t.H = e.Hout; t.W = e.Wout; }      // 1x1 stride s: sub-sampled grid
             t.sW = in.ld * stride; t.sH = in.W * in.ld * stride; t.sB = in.H * in.W * in.ld;
-            if (tc_conv_supported(t, e)) {
+            const bool sup = tc_conv_supported(t, e);
+            if (prod && !sup) return false;
+            if (!go()) return true;
+            if (sup) {
                 cudaEvent_t ev1 = nullptr;
                 if (profile) {
                     cudaEventRecord(next_event(), st);
@@ -447,11 +457,12 @@ struct mlic_engine {
                 }
                 int r = launch_conv_gemm_tc(t, e, vec ? 1 : 0, st);
                 if (ev1) cudaEventRecord(ev1, st);
-                if (r) { if (!rc) rc = fail("tcgen05 conv '%s': %s", key.c_str(), tc_last_error()); return; }
+                if (r) { if (!rc) rc = fail("tcgen05 conv '%s': %s", key.c_str(), tc_last_error()); return true; }
                 ++launches;
-                return;
+                return true;
             }
         }
+        if (!go()) return true;
         ConvGeom g;
         g.B = in.B; g.H = in.H; g.W = in.W; g.Cin = in.C; g.ld = in.ld; g.Hout = e.Hout; g.Wout = e.Wout;
         g.ks = w->ks; g.stride = stride; g.pad = pad; g.Ktot = w->ks * w->ks * w->Cin;
@@ -459,6 +470,7 @@ struct mlic_engine {
         // the kernel's `vec` covers both the A loads and the epilogue accesses
         launch_conv_gemm_simt(bf, in.p, g, w->w32, e, (avec && vec) ? 1 : 0, st);
         after_launch(key.c_str());
+        return true;
     }
     void dwconv(const Act& in, const std::string& key, int stride, int actv, const Act& out) {
         const DwW* d = dw(key);
@@ -470,6 +482,10 @@ struct mlic_engine {
     }
     // DepthWiseConv (modules/layers/conv.py:46-63): dw3x3(stride) -> pw1x1 with epilogue
     void dsconv(const Act& in, const std::string& p, int stride, const Act* out, const EpiOpt& o) {
+        if (bf && use_tc && fuse && stride == 1 && !o.out2) {
+            const DwW* d = dw(p + ".depth_conv");
+            if (d && d->C == in.C && gemm(in, p + ".point_conv", 1, 0, out, o, 1, d)) return;
+        }
         size_t mark = ws_off;
         Act t = act(in.B, (in.H - 1) / stride + 1, (in.W - 1) / stride + 1, in.C);
         dwconv(in, p + ".depth_conv", stride, ACT_NONE, t);
@@ -493,6 +509,22 @@ struct mlic_engine {
     }
 
     // ------------------------------------------------------------------ blocks
+    // v = conv(t); out = (I)GDN(v) [+ res]: norm = conv1x1(v^2, gamma) + beta.  Fast path: the GDN GEMM squares its A
+    // operand on chip (PROD_SQ); otherwise conv's epilogue writes v^2 as a side tensor for a plain GEMM.
+    void gdn_block(const Act& t, const std::string& conv, bool dense, const Act& v, const std::string& gdn, const Act& out,
+                   const EpiOpt& og) {
+        if (bf && use_tc && fuse) {
+            size_t mark = ws_off;
+            c3(t, conv, 1, dense, &v, EpiOpt());
+            if (gemm(v, gdn, 1, 0, &out, og, 2)) { ws_off = mark; return; }
+            // (not taken by the fused kernel: recompute through the side tensor below; conv is re-run, rare path)
+            ws_off = mark;
+        }
+        Act sq = act(v.B, v.H, v.W, v.C);
+        EpiOpt o2; o2.out2 = &sq;
+        c3(t, conv, 1, dense, &v, o2);
+        gemm(sq, gdn, 1, 0, &out, og);
+    }
     // ResidualBlock (res_blk.py:142-154): GELU(conv2(GELU(conv1 x))) + skip(x)
     void rb(const Act& x, const std::string& p, bool dense, const Act& out) {
         size_t mark = ws_off;
@@ -515,13 +547,11 @@ struct mlic_engine {
         EpiOpt g; g.act = ACT_GELU;
         Act t = act(out.B, out.H, out.W, out.C);
         c3(x, p + ".conv1", 2, dense, &t, g);
-        Act v = act(out.B, out.H, out.W, out.C), sq = act(out.B, out.H, out.W, out.C);
-        EpiOpt o2; o2.out2 = &sq;
-        c3(t, p + ".conv2", 1, dense, &v, o2);
+        Act v = act(out.B, out.H, out.W, out.C);
         Act sk = act(out.B, out.H, out.W, out.C);
         gemm(x, p + ".skip", 2, 0, &sk, EpiOpt());
         EpiOpt og; og.gdn = GDN_FWD; og.gdn_x = &v; og.res = &sk;
-        gemm(sq, p + ".gdn", 1, 0, &out, og);
+        gdn_block(t, p + ".conv2", dense, v, p + ".gdn", out, og);
         ws_off = mark;
     }
     // ResidualBlockUpsample (res_blk.py:113-121): IGDN(conv(GELU(subpel x))) + upsample(x)
@@ -530,13 +560,11 @@ struct mlic_engine {
         EpiOpt g; g.act = ACT_GELU;
         Act t = act(out.B, out.H, out.W, out.C);
         gemm(x, p + ".subpel_conv.0", 1, 1, &t, g);
-        Act v = act(out.B, out.H, out.W, out.C), sq = act(out.B, out.H, out.W, out.C);
-        EpiOpt o2; o2.out2 = &sq;
-        dsconv(t, p + ".conv", 1, &v, o2);
-        Act up = t;      // t is dead after the dsconv: reuse its storage for the identity branch
+        Act v = act(out.B, out.H, out.W, out.C);
+        Act up = act(out.B, out.H, out.W, out.C);
         gemm(x, p + ".upsample.0", 1, 1, &up, EpiOpt());
         EpiOpt og; og.gdn = GDN_INV; og.gdn_x = &v; og.res = &up;
-        gemm(sq, p + ".igdn", 1, 0, &out, og);
+        gdn_block(t, p + ".conv", false, v, p + ".igdn", out, og);
         ws_off = mark;
     }
 
@@ -884,6 +912,7 @@ int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
     if (!e || !name) return fail("bad arguments");
     if (!strcmp(name, "tensor_cores")) { e->use_tc = value; return 0; }
     if (!strcmp(name, "profile")) { e->profile = value; return 0; }
+    if (!strcmp(name, "fuse")) { e->fuse = value; return 0; }
     return fail("unknown option '%s'", name);
 }
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {

@@ -155,12 +155,16 @@ struct TcParams {
     int nstg;               // STORE_TMA: 16 KB staging buffers behind the stage ring (ring slots x buffers per block)
     int b_resident;         // 1: the whole weight matrix (all K chunks x BN rows, tilesN == 1) is loaded into shared
                             //    memory once per CTA; the ring then carries only the A patches
+    int raw_bytes;          // PROD_DW: bytes of one halo patch {64 ch, TW+2, TH+2} (multiple of 128)
+    int Cin;                // PROD_DW: channels of the depthwise conv (= K of the GEMM)
+    const float* dw_w9;     // PROD_DW: depthwise weights [9][Cin] fp32
+    const float* dw_bias;   // PROD_DW: depthwise bias [Cin]
     int l2_prefetch;        // > 0 (1x1 convs): prefetch the A patch of the tile this many iterations ahead into L2
     int debug;              // development only: bit0 skip epilogue stores, bit1 skip TMEM loads
 };
 
 struct TcMaps {
-    CUtensorMap a, b;       // operands
+    CUtensorMap a, b;       // operands (PROD_DW: `a` is the halo-patch map, box {64, TW+2, TH+2, 1}, no swizzle)
     CUtensorMap o[4];       // output (one per pixel-shuffle group; o[0] when not shuffled)
     CUtensorMap o2;         // x^2 side output
 };
@@ -170,6 +174,16 @@ constexpr int TC_STG_BYTES = 128 * 128;     // one staged 128-pixel x 64-column 
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 128 + TC_EPI_WARPS * 32;
+// Fused A-operand producers (PROD template parameter): the A stage of a 1x1 GEMM is not a TMA copy of the input but
+//   PROD_DW: the depthwise 3x3 (+ bias) of the input patch, computed by 8 CUDA-core warps from a TMA-loaded halo patch
+//            -> DepthWiseConv (modules/layers/conv.py:46-63) in one kernel, the depthwise output never touches HBM;
+//   PROD_SQ: the element-wise square of the input patch (GDN / IGDN: norm = conv1x1(x^2), CompressAI GDN)
+//            -> no x^2 side tensor.
+enum { PROD_TMA = 0, PROD_DW = 1, PROD_SQ = 2 };
+constexpr int TC_PROD_WARPS = 8;                                   // warps 4..11
+constexpr int TC_FUSED_EPI_WARPS = 12;                             // warps 12..23 (N <= 192: three 64-column groups)
+constexpr int TC_FUSED_THREADS = 128 + (TC_PROD_WARPS + TC_FUSED_EPI_WARPS) * 32;
+constexpr int TC_RAW_SLOTS = 2;
 constexpr int TC_MAX_N = 2048;
 constexpr int TC_MAX_BIAS = TC_MAX_N + 256;
 
@@ -339,13 +353,15 @@ __device__ __forceinline__ void tma_store_wait_read(int pending) {
     else if (pending == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
     else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory"); }
 
 // Persistent kernel: grid = min(#tiles, #SMs); every role walks the same static tile sequence
 // t = blockIdx.x, blockIdx.x + gridDim.x, ...  (N-tile fastest, so co-running CTAs share the A patch in L2).
-template <int ACT, int GDN, bool RES>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e,
-                                                                      unsigned long long* __restrict__ dbg) {
+template <int ACT, int GDN, bool RES, int PROD>
+__global__ void __launch_bounds__(PROD == PROD_TMA ? TC_THREADS : TC_FUSED_THREADS) __maxnreg__(PROD == PROD_TMA ? 96 : 80)
+conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsigned long long* __restrict__ dbg) {
+    constexpr int NTHREADS = PROD == PROD_TMA ? TC_THREADS : TC_FUSED_THREADS;
+    constexpr int EW0 = PROD == PROD_TMA ? 4 : 4 + TC_PROD_WARPS;          // first epilogue warp (multiple of 4)
+    constexpr int NEPI = PROD == PROD_TMA ? TC_EPI_WARPS : TC_FUSED_EPI_WARPS;
     // dbg (development only, may be null): per CTA {total, producer wait-empty, mma wait-full, mma wait-acc-empty,
     // epilogue wait-acc-full (warp 4), epilogue busy (warp 4)} in SM clocks
     const long long t_start = clock64();
@@ -359,7 +375,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
     // layout: [resident B: ksteps x b_bytes]? [ring: stages x stage_bytes] [staging]
     uint8_t* bres = base;
     if (p.b_resident) base += (size_t)ksteps_total * b_bytes;
+    // fused depthwise producer: [.. ring | staging | raw ring: TC_RAW_SLOTS x raw_bytes | dw weights 9 x Cin + bias Cin (fp32)]
+    uint8_t* rawbuf = base + (size_t)p.stages * stage_bytes + (size_t)p.nstg * TC_STG_BYTES;
+    float* sDw = reinterpret_cast<float*>(rawbuf + (size_t)TC_RAW_SLOTS * p.raw_bytes);
+    (void)rawbuf; (void)sDw;
+    if constexpr (PROD == PROD_DW) {
+        for (int i = threadIdx.x; i < 9 * p.Cin; i += NTHREADS) sDw[i] = p.dw_w9[i];
+        for (int i = threadIdx.x; i < p.Cin; i += NTHREADS) sDw[9 * p.Cin + i] = p.dw_bias[i];
+    }
     __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_full[2], acc_empty[2], bres_bar;
+    __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_RAW_SLOTS];     // fused producers: TMA -> compute warps
     __shared__ uint32_t tmem_base_smem;
     __shared__ float sBias[TC_MAX_BIAS];
 
@@ -372,9 +397,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // full_bar: one arrival from the TMA producer, or one per compute warp when the A stage is produced on chip
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], PROD == PROD_TMA ? 1 : TC_PROD_WARPS); mbar_init(&empty_bar[s], 1); }
+        if (PROD != PROD_TMA) {
+            for (int s = 0; s < TC_MAX_STAGES; ++s) mbar_init(&raw_full[s], 1);
+            for (int s = 0; s < TC_RAW_SLOTS; ++s) mbar_init(&raw_empty[s], TC_PROD_WARPS);
+        }
         // accumulator release: one arrival per epilogue warp that reads it (TMA-store mode: 4 warps per 64-column block)
-        const uint32_t nrel = p.store_mode == STORE_TMA ? 4u * (uint32_t)((p.BN + 63) / 64) : (uint32_t)TC_EPI_WARPS;
+        const uint32_t nrel = p.store_mode == STORE_TMA ? 4u * (uint32_t)((p.BN + 63) / 64) : (uint32_t)NEPI;
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], nrel); }
         mbar_init(&bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -385,16 +415,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < TC_MAX_BIAS; i += TC_THREADS) sBias[i] = (e.bias && i < e.N) ? e.bias[i] : 0.0f;
+    for (int i = threadIdx.x; i < TC_MAX_BIAS; i += NTHREADS) sBias[i] = (e.bias && i < e.N) ? e.bias[i] : 0.0f;
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
+    if (warp < 4) {
+        // register re-balancing between warp groups (the fused kernel starts at 80 registers / thread for 768 threads):
+        // the control group gives registers up so that the depthwise warps can keep their 72 filter taps in registers
+        if constexpr (PROD == PROD_DW) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    }
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int rslot = 0;
+            uint32_t rphase = 0;
+            (void)rslot; (void)rphase;
             if (p.b_resident) {              // weights once per CTA: every K chunk of the (single) N tile
                 mbar_expect_tx(&bres_bar, (uint32_t)(ksteps * b_bytes));
                 for (int k = 0; k < ksteps; ++k) {
@@ -420,6 +458,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                         for (int cc = 0; cc < p.kchunks; ++cc) tma_prefetch_4d(&tm.a, cc * 64, wp, hp, ip);
                     }
                 }
+                if constexpr (PROD == PROD_DW) {
+                    // halo patches {64 ch, TW+2, TH+2} into the raw ring (the compute warps turn them into A stages)
+                    for (int k = 0; k < ksteps; ++k) {
+                        TIMED_WAIT(w0c, &raw_empty[rslot], rphase ^ 1);
+                        mbar_expect_tx(&raw_full[rslot], (uint32_t)p.raw_bytes);
+                        tma_load_4d(rawbuf + (size_t)rslot * p.raw_bytes, &tm.a, &raw_full[rslot], k * 64, w0 - 1, h0 - 1, img);
+                        if (++rslot == TC_RAW_SLOTS) { rslot = 0; rphase ^= 1; }
+                    }
+                } else if constexpr (PROD == PROD_SQ) {
+                    // the patch lands in the A stage itself; the compute warps square it in place
+                    for (int k = 0; k < ksteps; ++k) {
+                        TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = base + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&raw_full[stage], (uint32_t)TC_A_BYTES);
+                        tma_load_4d(sa, &tm.a, &raw_full[stage], k * 64, w0, h0, img);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                } else {
                 for (int k = 0; k < ksteps; ++k) {
                     TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
                     const int tap = k / p.kchunks, cc = k - tap * p.kchunks;
@@ -429,6 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                     tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
                     if (!p.b_resident) tma_load_2d(sa + TC_A_BYTES, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
                 }
             }
         }
@@ -460,10 +517,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                 tcgen05_commit(&acc_full[as]);
             }
         }
-    } else if (warp >= 4) {
-        // 16 epilogue warps: TMEM lane quarter q = warp % 4 (hardware restriction), column quarter cq = (warp - 4) / 4:
+    } else if (PROD != PROD_TMA && warp >= 4 && warp < EW0) {
+        // ---- fused A-operand producer warps (8 warps, 256 threads)
+        if constexpr (PROD == PROD_DW) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int pt = threadIdx.x - 128;                  // 0..255
+        const int cg = pt & 7;                              // 8-channel group inside the 64-channel chunk
+        int stage = 0, rslot = 0;
+        uint32_t phase = 0, rphase = 0;
+        (void)rslot; (void)rphase;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            for (int k = 0; k < ksteps; ++k) {
+                uint8_t* sa = base + (size_t)stage * stage_bytes;
+                if constexpr (PROD == PROD_DW) {
+                    TIMED_WAIT(w0c, &raw_full[rslot], rphase);         // halo patch landed
+                    TIMED_WAIT(w1c, &empty_bar[stage], phase ^ 1);     // A stage free (its MMAs retired)
+                    const bf16* raw = reinterpret_cast<const bf16*>(rawbuf + (size_t)rslot * p.raw_bytes);
+                    const float* wk = sDw + k * 64 + cg * 8;           // tap t at wk[t * Cin]
+                    const int IW = p.TW + 2;
+                    float wr[9][8];                                     // this thread's taps of the chunk stay in registers
+#pragma unroll
+                    for (int tp = 0; tp < 9; ++tp) {
+                        const float4 wa = *reinterpret_cast<const float4*>(wk + tp * p.Cin);
+                        const float4 wb = *reinterpret_cast<const float4*>(wk + tp * p.Cin + 4);
+                        wr[tp][0] = wa.x; wr[tp][1] = wa.y; wr[tp][2] = wa.z; wr[tp][3] = wa.w;
+                        wr[tp][4] = wb.x; wr[tp][5] = wb.y; wr[tp][6] = wb.z; wr[tp][7] = wb.w;
+                    }
+                    const float* bk = sDw + 9 * p.Cin + k * 64 + cg * 8;
+#pragma unroll 1
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = (pt >> 3) + 32 * i;              // pixel of the tile = A row
+                        const int oy = r / p.TW, ox = r - oy * p.TW;
+                        float a[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const uint4 tt = *reinterpret_cast<const uint4*>(raw + (size_t)((oy + ky) * IW + ox + kx) * 64 + cg * 8);
+                                const uint32_t wv[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+                                for (int q2 = 0; q2 < 4; ++q2) {
+                                    a[2 * q2] = fmaf(__uint_as_float(wv[q2] << 16), wr[ky * 3 + kx][2 * q2], a[2 * q2]);
+                                    a[2 * q2 + 1] = fmaf(__uint_as_float(wv[q2] & 0xffff0000u), wr[ky * 3 + kx][2 * q2 + 1], a[2 * q2 + 1]);
+                                }
+                            }
+                        {
+                            const float4 ba = *reinterpret_cast<const float4*>(bk);
+                            const float4 bb = *reinterpret_cast<const float4*>(bk + 4);
+                            a[0] += ba.x; a[1] += ba.y; a[2] += ba.z; a[3] += ba.w; a[4] += bb.x; a[5] += bb.y; a[6] += bb.z; a[7] += bb.w;
+                        }
+                        *reinterpret_cast<uint4*>(sa + r * 128 + ((cg ^ (r & 7)) << 4)) = pack8_bf16(a);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> UMMA (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&full_bar[stage]); mbar_arrive(&raw_empty[rslot]); }
+                    if (++rslot == TC_RAW_SLOTS) { rslot = 0; rphase ^= 1; }
+                } else {                                               // PROD_SQ: square the landed A stage in place
+                    mbar_wait(&raw_full[stage], phase);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4* q4 = reinterpret_cast<uint4*>(sa) + pt + 256 * i;      // layout-agnostic: element-wise
+                        float v[8];
+                        unpack8_bf16(*q4, v);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
+                        *q4 = pack8_bf16(v);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= EW0) {
+        // epilogue warps: TMEM lane quarter q = warp % 4 (hardware restriction), column quarter cq = (warp - EW0) / 4:
         // four warps per SM sub-partition hide the TMEM-load / shared-memory latencies of the short per-block chain
-        const int q = warp & 3, cq = (warp - 4) >> 2;
+        const int q = warp & 3, cq = (warp - EW0) >> 2;
         const int r = q * 32 + lane;
         uint8_t* stg = base + (size_t)p.stages * stage_bytes;
         const int per = (e.out2 || GDN != GDN_NONE) ? 2 : 1;      // staging buffers per 64-column block (out/res [+ out2 | GDN operand])
@@ -510,25 +641,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                         // its 32 pixels with coalesced 16-byte loads (8 lanes = one 128-byte pixel row) straight into the
                         // staging slot, in the swizzled layout of the output block; all loads are in flight together and
                         // complete while the warp waits for the accumulator.  The result later overwrites the residual in place.
-                        uint4 rr[8], xx[8];
+                        auto stage_rows = [&](const void* src, int ld, uint32_t dst_off) {
+                            uint4 rr[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int prow = q * 32 + i * 4 + (lane >> 3);
-                            const int ph = h0 + prow / p.TW, pw = w0 + prow % p.TW;
-                            const int col = n0 + kb + (lane & 7) * 8;
-                            const bool ok = ph < e.Hout && pw < e.Wout && col + 8 <= e.N;
-                            const size_t pix = ((size_t)img * e.Hout + ph) * e.Wout + pw;
-                            rr[i] = make_uint4(0, 0, 0, 0); xx[i] = make_uint4(0, 0, 0, 0);
-                            if (RES && ok) rr[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + pix * e.res_ld + col);
-                            if (GDN != GDN_NONE && ok) xx[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.gdn_x) + pix * e.gdn_ld + col);
-                        }
+                            for (int i = 0; i < 8; ++i) {
+                                const int prow = q * 32 + i * 4 + (lane >> 3);
+                                const int ph = h0 + prow / p.TW, pw = w0 + prow % p.TW;
+                                const int col = n0 + kb + (lane & 7) * 8;
+                                const bool ok = ph < e.Hout && pw < e.Wout && col + 8 <= e.N;
+                                const size_t pix = ((size_t)img * e.Hout + ph) * e.Wout + pw;
+                                rr[i] = make_uint4(0, 0, 0, 0);
+                                if (ok) rr[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(src) + pix * ld + col);
+                            }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int prow = q * 32 + i * 4 + (lane >> 3);
-                            const uint32_t off = (uint32_t)(prow * 128 + (((lane & 7) ^ (prow & 7)) << 4));
-                            if (RES) *reinterpret_cast<uint4*>(sb + off) = rr[i];
-                            if (GDN != GDN_NONE) *reinterpret_cast<uint4*>(sb + TC_STG_BYTES + off) = xx[i];
-                        }
+                            for (int i = 0; i < 8; ++i) {
+                                const int prow = q * 32 + i * 4 + (lane >> 3);
+                                *reinterpret_cast<uint4*>(sb + dst_off + (uint32_t)(prow * 128 + (((lane & 7) ^ (prow & 7)) << 4))) = rr[i];
+                            }
+                        };
+                        if constexpr (RES) stage_rows(e.res, e.res_ld, 0u);
+                        if constexpr (GDN != GDN_NONE) stage_rows(e.gdn_x, e.gdn_ld, (uint32_t)TC_STG_BYTES);
                         __syncwarp();
                     }
                     if (dbg) { long long _t = clock64(); mbar_wait(&acc_full[as], (uint32_t)(it >> 1) & 1u); w3c += clock64() - _t; }
@@ -602,7 +734,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
             } else {
                 // STORE_DIRECT: 16-column chunks are dealt to the four column quarters in turn (BN is a multiple of 16)
-                for (int c0 = cq * 16; c0 < p.BN; c0 += 64) {
+                for (int c0 = cq * 16; c0 < p.BN; c0 += 16 * (NEPI / 4)) {
 #pragma unroll 1
                     for (int sub = 0; sub < 2; ++sub) {
                         const int c = c0 + sub * 8, n = n0 + c;
@@ -634,7 +766,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_gemm_tc_kernel(const __gri
         unsigned long long* d = dbg + (size_t)blockIdx.x * 8;
         if (warp == 0) { d[0] = (unsigned long long)(clock64() - t_start); d[1] = (unsigned long long)w0c; }
         if (warp == 1) { d[2] = (unsigned long long)w1c; d[3] = (unsigned long long)w2c; }
-        if (warp == 4) { d[4] = (unsigned long long)w3c; d[5] = (unsigned long long)(clock64() - t_start);
+        if (PROD != PROD_TMA && warp == 4) { d[6] = (unsigned long long)w0c; d[7] = (unsigned long long)w1c; }
+        if (PROD != PROD_TMA && warp == EW0) { d[4] = (unsigned long long)w3c; d[5] = (unsigned long long)(clock64() - t_start); }
+        if (PROD == PROD_TMA && warp == EW0) { d[4] = (unsigned long long)w3c; d[5] = (unsigned long long)(clock64() - t_start);
                          d[6] = (unsigned long long)w0c; d[7] = (unsigned long long)w1c; dbg[(size_t)gridDim.x * 8 + blockIdx.x] = (unsigned long long)w2c; }
     }
 #undef TIMED_WAIT
@@ -662,6 +796,16 @@ bool tc_conv_supported(const TcConv& c, const Epi& e) {
     if (e.N < 8 || e.N > TC_MAX_N) return false;
     if (c.H <= 0 || c.W <= 0 || c.B <= 0) return false;
     if (e.nchw && !(e.shuffle && e.N == 12 && e.out_f32)) return false;
+    if (c.prod != PROD_TMA) {
+        // fused producers: 1x1 GEMM over a dense-stride-1 view, whole weight matrix resident, <= 3 column groups
+        if (c.ks != 1 || c.pad != 0 || (c.Cin % 64) != 0 || e.N > 192 || (e.N % 8) != 0 || e.shuffle || e.out_f32 || e.out2) return false;
+        if ((c.Cin / 64) > 4 || (size_t)(c.Cin / 64) * ((e.N + 63) / 64 * 64) * 128 > 80 * 1024) return false;
+        if (c.prod == PROD_DW && (!c.dw_w9 || !c.dw_bias)) return false;
+        if (c.prod == PROD_DW && (e.gdn || e.act == ACT_HALF_TANH)) return false;
+        if (c.prod == PROD_SQ && (!e.gdn || e.act != ACT_NONE)) return false;
+        auto ok16 = [](const void* q, int ld) { return q == nullptr || ((((uintptr_t)q) % 16 == 0) && ((ld * 2) % 16 == 0)); };
+        if (!e.out || !ok16(e.out, e.out_ld) || !ok16(e.res, e.res_ld) || !ok16(e.gdn_x, e.gdn_ld)) return false;
+    }
     return true;
 }
 
@@ -687,7 +831,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     // output patch shape: minimise the number of tiles
     const int cand[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
     long long best = -1;
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < (c.prod == PROD_DW ? 3 : 5); ++i) {       // the halo patch of the depthwise producer: compact shapes only
         long long t = (long long)((e.Hout + cand[i][0] - 1) / cand[i][0]) * ((e.Wout + cand[i][1] - 1) / cand[i][1]);
         if (best < 0 || t < best) { best = t; p.TH = cand[i][0]; p.TW = cand[i][1]; }
     }
@@ -708,18 +852,21 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     if (p.debug & 4) { if (p.store_mode == STORE_TMA) p.store_mode = STORE_DIRECT; }
     p.BN = pick_bn(e.N, p.store_mode == STORE_TMA ? 64 : ((e.shuffle || e.N % 32 == 0) && e.N >= 32 ? 32 : 16));
     const int budget0 = 212 * 1024;     // dynamic shared memory (static: bias + barriers ~ 9.5 KB)
+    p.Cin = c.Cin; p.dw_w9 = c.dw_w9; p.dw_bias = c.dw_bias;
+    p.raw_bytes = c.prod == PROD_DW ? 128 * (p.TW + 2) * (p.TH + 2) : 0;
+    const int extra_bytes = c.prod == PROD_DW ? TC_RAW_SLOTS * p.raw_bytes + 10 * c.Cin * 4 : 0;
     const int ksteps = p.ks * p.ks * p.kchunks;
     const int bres_bytes = ksteps * p.BN * 128;
     const int per = (e.out2 || e.gdn) ? 2 : 1;
     const int nact = (p.BN + 63) / 64;          // warp groups that own a 64-column block
     // Shared-memory plan.  Small weight matrices (the 192x192 pointwise / GDN GEMMs) may stay resident (no per-tile B
     // reload); every active warp group owns `ring` staging slots of `per` 16 KB buffers; the rest is the operand ring.
-    const bool want_bres = p.BN >= e.N && bres_bytes <= 80 * 1024 && ksteps <= 4 && !(p.debug & 8);
+    const bool want_bres = p.BN >= e.N && bres_bytes <= 80 * 1024 && ksteps <= 4 && (!(p.debug & 8) || c.prod != PROD_TMA);
     int stage_bytes = 0;
     bool planned = false;
-    for (int bres = want_bres ? 1 : 0; bres >= 0 && !planned; --bres) {
+    for (int bres = want_bres ? 1 : 0; bres >= (c.prod != PROD_TMA ? 1 : 0) && !planned; --bres) {
         stage_bytes = TC_A_BYTES + (bres ? 0 : p.BN * 128);
-        const int budget = budget0 - 1024 - (bres ? bres_bytes : 0);
+        const int budget = budget0 - 1024 - (bres ? bres_bytes : 0) - extra_bytes;
         for (int ring = (p.store_mode == STORE_TMA ? 2 : 0); ring >= 0 && !planned; --ring) {
             if (p.store_mode == STORE_TMA && ring == 0) break;
             const int stg_bytes = nact * ring * per * TC_STG_BYTES;
@@ -733,7 +880,8 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         }
     }
     if (!planned) { snprintf(g_tc_err, sizeof g_tc_err, "no shared-memory plan for BN=%d ksteps=%d", p.BN, ksteps); return 8; }
-    p.l2_prefetch = (p.ks == 1 && !(p.debug & 16)) ? 3 : 0;
+    p.l2_prefetch = (p.ks == 1 && c.prod == PROD_TMA && !(p.debug & 16)) ? 3 : 0;
+    if (c.prod != PROD_TMA && p.store_mode == STORE_DIRECT) p.epi_vec = p.epi_vec && p.ld_vec;
     p.acc_stride = 32;
     while (p.acc_stride < p.BN) p.acc_stride <<= 1;
     p.tilesN = (e.N + p.BN - 1) / p.BN;
@@ -751,11 +899,12 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     {
         cuuint64_t dims[4] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.B};
         cuuint64_t strides[3] = {(cuuint64_t)c.sW * 2, (cuuint64_t)c.sH * 2, (cuuint64_t)c.sB * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        const bool halo = c.prod == PROD_DW;
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.TW + (halo ? 2 : 0)), (cuuint32_t)(p.TH + (halo ? 2 : 0)), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = g_encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.in), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, halo ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d B=%d sW=%d sH=%d)", (int)r,
                      c.Cin, c.W, c.H, c.B, c.sW, c.sH);
@@ -794,28 +943,36 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
             if (encode_out_map(&tm.o2, e.out2, e.N, e.Wout, e.Hout, c.B, ld2, (size_t)e.Wout * ld2, (size_t)e.Hout * e.Wout * ld2, p.TW, p.TH)) return 7;
         }
     }
-    const size_t smem = (size_t)(p.b_resident ? bres_bytes : 0) + (size_t)p.stages * stage_bytes + (size_t)p.nstg * TC_STG_BYTES + 1024;
+    const size_t smem = (size_t)(p.b_resident ? bres_bytes : 0) + (size_t)p.stages * stage_bytes + (size_t)p.nstg * TC_STG_BYTES +
+                        (size_t)extra_bytes + 1024;
     if (smem > (size_t)budget0 + 1024) { snprintf(g_tc_err, sizeof g_tc_err, "shared-memory plan too large: %zu", smem); return 8; }
-    // one instantiation per (activation, GDN mode, residual): the epilogue only carries the code its layer needs
+    // one instantiation per (activation, GDN mode, residual[, fused producer]): the epilogue only carries the code its
+    // layer needs
     typedef void (*KernelFn)(const TcMaps, TcParams, Epi, unsigned long long*);
     static const KernelFn table[3][3][2] = {
-        {{conv_gemm_tc_kernel<0, 0, false>, conv_gemm_tc_kernel<0, 0, true>}, {conv_gemm_tc_kernel<0, 1, false>, conv_gemm_tc_kernel<0, 1, true>},
-         {conv_gemm_tc_kernel<0, 2, false>, conv_gemm_tc_kernel<0, 2, true>}},
-        {{conv_gemm_tc_kernel<1, 0, false>, conv_gemm_tc_kernel<1, 0, true>}, {conv_gemm_tc_kernel<1, 1, false>, conv_gemm_tc_kernel<1, 1, true>},
-         {conv_gemm_tc_kernel<1, 2, false>, conv_gemm_tc_kernel<1, 2, true>}},
-        {{conv_gemm_tc_kernel<2, 0, false>, conv_gemm_tc_kernel<2, 0, true>}, {conv_gemm_tc_kernel<2, 1, false>, conv_gemm_tc_kernel<2, 1, true>},
-         {conv_gemm_tc_kernel<2, 2, false>, conv_gemm_tc_kernel<2, 2, true>}}};
-    static bool attr_set[3][3][2] = {};
+        {{conv_gemm_tc_kernel<0, 0, false, 0>, conv_gemm_tc_kernel<0, 0, true, 0>}, {conv_gemm_tc_kernel<0, 1, false, 0>, conv_gemm_tc_kernel<0, 1, true, 0>},
+         {conv_gemm_tc_kernel<0, 2, false, 0>, conv_gemm_tc_kernel<0, 2, true, 0>}},
+        {{conv_gemm_tc_kernel<1, 0, false, 0>, conv_gemm_tc_kernel<1, 0, true, 0>}, {conv_gemm_tc_kernel<1, 1, false, 0>, conv_gemm_tc_kernel<1, 1, true, 0>},
+         {conv_gemm_tc_kernel<1, 2, false, 0>, conv_gemm_tc_kernel<1, 2, true, 0>}},
+        {{conv_gemm_tc_kernel<2, 0, false, 0>, conv_gemm_tc_kernel<2, 0, true, 0>}, {conv_gemm_tc_kernel<2, 1, false, 0>, conv_gemm_tc_kernel<2, 1, true, 0>},
+         {conv_gemm_tc_kernel<2, 2, false, 0>, conv_gemm_tc_kernel<2, 2, true, 0>}}};
+    static const KernelFn table_dw[2][2] = {{conv_gemm_tc_kernel<0, 0, false, PROD_DW>, conv_gemm_tc_kernel<0, 0, true, PROD_DW>},
+                                            {conv_gemm_tc_kernel<1, 0, false, PROD_DW>, conv_gemm_tc_kernel<1, 0, true, PROD_DW>}};
+    static const KernelFn table_sq[2][2] = {{conv_gemm_tc_kernel<0, 1, false, PROD_SQ>, conv_gemm_tc_kernel<0, 1, true, PROD_SQ>},
+                                            {conv_gemm_tc_kernel<0, 2, false, PROD_SQ>, conv_gemm_tc_kernel<0, 2, true, PROD_SQ>}};
+    static bool attr_set[3][3][2][3] = {};
     if (e.act < 0 || e.act > 2 || e.gdn < 0 || e.gdn > 2) { snprintf(g_tc_err, sizeof g_tc_err, "bad epilogue mode"); return 9; }
     const int ri = e.res ? 1 : 0;
     KernelFn fn = table[e.act][e.gdn][ri];
-    if (!attr_set[e.act][e.gdn][ri]) {
+    if (c.prod == PROD_DW) fn = table_dw[e.act][ri];
+    else if (c.prod == PROD_SQ) fn = table_sq[e.gdn - 1][ri];
+    if (!attr_set[e.act][e.gdn][ri][c.prod]) {
         cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, budget0 + 1024);
         if (er != cudaSuccess) {
             snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(er));
             return 4;
         }
-        attr_set[e.act][e.gdn][ri] = true;
+        attr_set[e.act][e.gdn][ri][c.prod] = true;
     }
     static int num_sms = 0;
     if (!num_sms) {
@@ -832,7 +989,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         cudaMemsetAsync(dbuf, 0, 148 * 9 * sizeof(unsigned long long), s);
         dbg = dbuf;
     }
-    fn<<<grid, TC_THREADS, smem, s>>>(tm, p, e, dbg);
+    fn<<<grid, c.prod == PROD_TMA ? TC_THREADS : TC_FUSED_THREADS, smem, s>>>(tm, p, e, dbg);
     if (dbg) {
         static int printed = 0;
         unsigned long long h[148 * 9];
@@ -841,7 +998,8 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         if (printed++ < 3) {
             double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (unsigned i = 0; i < grid.x; ++i) { for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid.x; a[8] += (double)h[grid.x * 8 + i] / grid.x; }
-            fprintf(stderr, "[tc dbg] epilogue warp 4: drain-wait %.0f math %.0f fence+barrier+store %.0f\n", a[6], a[7], a[8]);
+            if (c.prod) fprintf(stderr, "[tc dbg] prod=%d compute warp 4: wait-raw %.0f wait-stage-free %.0f\n", c.prod, a[6], a[7]);
+            else fprintf(stderr, "[tc dbg] epilogue warp 4: drain-wait %.0f math %.0f fence+barrier+store %.0f\n", a[6], a[7], a[8]);
             fprintf(stderr, "[tc dbg] BN=%d ksteps=%d stages=%d nstg=%d bres=%d tiles/cta=%.1f | clocks: total %.0f prod-wait-empty %.0f mma-wait-full %.0f mma-wait-accempty %.0f epi-wait-accfull %.0f epi-total %.0f\n",
                     p.BN, ksteps, p.stages, p.nstg, p.b_resident, (double)p.ntiles / grid.x, a[0], a[1], a[2], a[3], a[4], a[5]);
         }

@@ -72,6 +72,9 @@ struct TcConv {
     int ks, pad;                // stride-1 taps around the output pixel
     const void* w;              // bf16 [N][ks*ks*Cpad], Cpad = roundup(Cin,64), zero padded per tap
     int Cpad;
+    int prod;                   // 0: A = the input (TMA); 1: A = depthwise3x3(input) + dw bias; 2: A = input^2  (1x1 GEMMs only)
+    const float* dw_w9;         // prod 1: depthwise weights [9][Cin] fp32, bias [Cin]
+    const float* dw_bias;
 };
 bool tc_conv_supported(const TcConv& c, const Epi& e);
 // returns cudaError_t-like int (0 ok)

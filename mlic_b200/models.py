@@ -99,6 +99,7 @@ class MLICPlusPlus(nn.Module):
         self.model_name = name or self._name_for(config)
         self.precision = "bf16"          # "bf16" fast mode | "fp32" validation mode
         self.tensor_cores = True
+        self.fuse = True                 # bf16 mode: depthwise 3x3 / x^2 produced inside the GEMM kernel
         for key, ent in build_entries(self.model_name).items():
             self._place(key, _init_tensor(ent), ent.is_param)
         # attributes the reference exposes on sub-modules
@@ -237,6 +238,7 @@ class MLICPlusPlus(nn.Module):
         L = self._sync_engine(dev)
         _lib.check(L.mlic_engine_set_option(self._engine, b"tensor_cores", 1 if self.tensor_cores else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"profile", 1 if self._profile else 0))
+        _lib.check(L.mlic_engine_set_option(self._engine, b"fuse", 1 if self.fuse else 0))
         prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
         odev = "cpu" if host else dev
         h, w, hz, wz = H // 16, W // 16, H // 64, W // 64
