@@ -55,7 +55,8 @@ int mlic_engine_set_param(mlic_engine* e, const char* name, const float* host_da
 int mlic_engine_finalize(mlic_engine* e);
 
 /* Knobs: "tensor_cores" (1 = tcgen05 implicit-GEMM in bf16 mode [default], 0 = CUDA-core GEMM only);
- *        "profile" (1 = bracket every tcgen05 GEMM launch with a CUDA-event pair on the launch stream). */
+ *        "profile" (1 = bracket every tcgen05 GEMM launch with a CUDA-event pair on the launch stream);
+ *        "fuse" (1 = depthwise 3x3 / x^2 produced inside the tcgen05 GEMM [default]); "trace" (see mlic_trace_dump). */
 int mlic_engine_set_option(mlic_engine* e, const char* name, int value);
 
 /* Device workspace needed by one call of the given mode / precision / shape. */
@@ -81,6 +82,10 @@ int64_t mlic_last_launch_count(const mlic_engine* e);
 /* Live profile of the dominant kernel (the tcgen05 implicit GEMM) since the last reset:
  * out3 = { summed launch duration in ms, summed algorithmic FLOPs (2*M*N*K), launches }.  Synchronises. */
 int mlic_profile_read(mlic_engine* e, double* out3, int reset);
+
+/* Per-launch trace: with option "trace" = 1 every launch of the following calls is followed by a CUDA event on the
+ * launch stream; this writes "label<TAB>microseconds" per launch to `path` (synchronises) and clears the trace. */
+int mlic_trace_dump(mlic_engine* e, const char* path);
 
 /* Stand-alone convolution on an NHWC activation tensor (fp32 or bf16 per `precision`; weights / bias are HOST
  * fp32 in the reference's nn.Conv2d layout [N][Cin][ks][ks]): out = act(conv(in) + bias) (+ residual), optionally

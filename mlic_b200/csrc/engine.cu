@@ -124,6 +124,30 @@ struct mlic_engine {
         return 0;
     }
 
+    // per-launch trace (option "trace"): one event after every launch, labelled with the layer key
+    int trace = 0;
+    std::vector<cudaEvent_t> tr_ev;
+    std::vector<std::string> tr_lab;
+    void tr(const std::string& label) {
+        if (!trace || dry) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+        tr_ev.push_back(e); tr_lab.push_back(label);
+    }
+    int trace_dump(const char* path) {
+        FILE* f = fopen(path, "w");
+        if (!f) return fail("cannot open %s", path);
+        for (size_t i = 1; i < tr_ev.size(); ++i) {
+            float ms = 0;
+            cudaEventSynchronize(tr_ev[i]);
+            cudaEventElapsedTime(&ms, tr_ev[i - 1], tr_ev[i]);
+            fprintf(f, "%s\t%.3f\n", tr_lab[i].c_str(), ms * 1e3);
+        }
+        fclose(f);
+        for (cudaEvent_t e : tr_ev) cudaEventDestroy(e);
+        tr_ev.clear(); tr_lab.clear();
+        return 0;
+    }
+
     // host-call staging (mlic_run_host)
     void* h_ws = nullptr; size_t h_ws_bytes = 0;
     void* h_io = nullptr; size_t h_io_bytes = 0;
@@ -390,6 +414,7 @@ struct mlic_engine {
     bool go() const { return !dry && !rc; }
     void after_launch(const char* what) {
         ++launches;
+        if (trace) tr(what);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && !rc) rc = fail("%s launch: %s", what, cudaGetErrorString(e));
     }
@@ -459,6 +484,11 @@ struct mlic_engine {
                 if (ev1) cudaEventRecord(ev1, st);
                 if (r) { if (!rc) rc = fail("tcgen05 conv '%s': %s", key.c_str(), tc_last_error()); return true; }
                 ++launches;
+                if (trace) {
+                    char lab[256];
+                    snprintf(lab, sizeof lab, "%s [tc M=%d N=%d K=%dx%d prod=%d]", key.c_str(), in.B * e.Hout * e.Wout, w->N, w->ks * w->ks, w->Cin, prod);
+                    tr(lab);
+                }
                 return true;
             }
         }
@@ -771,6 +801,7 @@ struct mlic_engine {
         dry = dry_run; st = stream; rc = 0; launches = 0;
         if (!dry && profile && ev_used > 200000) { if (profile_collect()) return 1; }
         ws_base = (uint8_t*)ws; ws_size = ws_bytes; ws_off = 0; ws_peak = 0;
+        if (trace) tr("start");
         if (!dry && ((uintptr_t)ws % 256)) return fail("workspace must be 256-byte aligned");
         if (!dry && bf && use_tc && tc_init()) return fail("%s", tc_last_error());
         static const mlic_buffers none = {};
@@ -913,6 +944,7 @@ int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
     if (!strcmp(name, "tensor_cores")) { e->use_tc = value; return 0; }
     if (!strcmp(name, "profile")) { e->profile = value; return 0; }
     if (!strcmp(name, "fuse")) { e->fuse = value; return 0; }
+    if (!strcmp(name, "trace")) { e->trace = value; return 0; }
     return fail("unknown option '%s'", name);
 }
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {
@@ -936,6 +968,11 @@ int mlic_profile_read(mlic_engine* e, double* out3, int reset) {
     out3[0] = e->prof_ms; out3[1] = e->prof_flops; out3[2] = e->prof_launches;
     if (reset) { e->prof_ms = e->prof_flops = e->prof_launches = 0; }
     return 0;
+}
+
+int mlic_trace_dump(mlic_engine* e, const char* path) {
+    if (!e || !path) return fail("bad arguments");
+    return e->trace_dump(path);
 }
 
 int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* host,

@@ -421,11 +421,6 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp < 4) {
-        // register re-balancing between warp groups (the fused kernel starts at 80 registers / thread for 768 threads):
-        // the control group gives registers up so that the depthwise warps can keep their 72 filter taps in registers
-        if constexpr (PROD == PROD_DW) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    }
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
@@ -455,7 +450,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                         const int ip = mp / tiles_per_img;
                         const int rp = mp - ip * tiles_per_img;
                         const int hp = (rp / p.tilesW) * p.TH, wp = (rp % p.tilesW) * p.TW;
-                        for (int cc = 0; cc < p.kchunks; ++cc) tma_prefetch_4d(&tm.a, cc * 64, wp, hp, ip);
+                        const int ho = PROD == PROD_DW ? 1 : 0;      // the halo box starts one pixel up / left
+                        for (int cc = 0; cc < p.kchunks; ++cc) tma_prefetch_4d(&tm.a, cc * 64, wp - ho, hp - ho, ip);
                     }
                 }
                 if constexpr (PROD == PROD_DW) {
@@ -519,9 +515,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
         }
     } else if (PROD != PROD_TMA && warp >= 4 && warp < EW0) {
         // ---- fused A-operand producer warps (8 warps, 256 threads)
-        if constexpr (PROD == PROD_DW) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int pt = threadIdx.x - 128;                  // 0..255
-        const int cg = pt & 7;                              // 8-channel group inside the 64-channel chunk
+        (void)pt;
         int stage = 0, rslot = 0;
         uint32_t phase = 0, rphase = 0;
         (void)rslot; (void)rphase;
@@ -529,45 +524,50 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
             for (int k = 0; k < ksteps; ++k) {
                 uint8_t* sa = base + (size_t)stage * stage_bytes;
                 if constexpr (PROD == PROD_DW) {
+                    // Tile = 8 rows x 16 columns.  Lane l owns channels (2l, 2l+1) of the 64-channel chunk (one bf16x2 word, so
+                    // every shared-memory access of the warp is one contiguous 128-byte pixel row: conflict-free), producer
+                    // warp pw owns output columns 2pw, 2pw+1.  The 10 x 4 input words of the strip are read once each and
+                    // feed up to 9 packed fp32x2 FMAs (FFMA2) against the 9 filter taps held in registers.
                     TIMED_WAIT(w0c, &raw_full[rslot], rphase);         // halo patch landed
                     TIMED_WAIT(w1c, &empty_bar[stage], phase ^ 1);     // A stage free (its MMAs retired)
-                    const bf16* raw = reinterpret_cast<const bf16*>(rawbuf + (size_t)rslot * p.raw_bytes);
-                    const float* wk = sDw + k * 64 + cg * 8;           // tap t at wk[t * Cin]
-                    const int IW = p.TW + 2;
-                    float wr[9][8];                                     // this thread's taps of the chunk stay in registers
+                    const int pw = warp - 4;
+                    const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawbuf + (size_t)rslot * p.raw_bytes) + (2 * pw) * 32 + lane;
+                    const float* wk = sDw + k * 64 + 2 * lane;         // tap t at wk[t * Cin]
+                    float2 w2[9];
 #pragma unroll
-                    for (int tp = 0; tp < 9; ++tp) {
-                        const float4 wa = *reinterpret_cast<const float4*>(wk + tp * p.Cin);
-                        const float4 wb = *reinterpret_cast<const float4*>(wk + tp * p.Cin + 4);
-                        wr[tp][0] = wa.x; wr[tp][1] = wa.y; wr[tp][2] = wa.z; wr[tp][3] = wa.w;
-                        wr[tp][4] = wb.x; wr[tp][5] = wb.y; wr[tp][6] = wb.z; wr[tp][7] = wb.w;
-                    }
-                    const float* bk = sDw + 9 * p.Cin + k * 64 + cg * 8;
-#pragma unroll 1
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = (pt >> 3) + 32 * i;              // pixel of the tile = A row
-                        const int oy = r / p.TW, ox = r - oy * p.TW;
-                        float a[8];
+                    for (int tp = 0; tp < 9; ++tp) w2[tp] = *reinterpret_cast<const float2*>(wk + tp * p.Cin);
+                    const float2 b2 = *reinterpret_cast<const float2*>(wk + 9 * p.Cin);
+                    float2 acc[8][2];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+                    for (int oy = 0; oy < 8; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
+                    for (int iy = 0; iy < 10; ++iy) {
+                        float2 x[4];
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const uint4 tt = *reinterpret_cast<const uint4*>(raw + (size_t)((oy + ky) * IW + ox + kx) * 64 + cg * 8);
-                                const uint32_t wv[4] = {tt.x, tt.y, tt.z, tt.w};
-#pragma unroll
-                                for (int q2 = 0; q2 < 4; ++q2) {
-                                    a[2 * q2] = fmaf(__uint_as_float(wv[q2] << 16), wr[ky * 3 + kx][2 * q2], a[2 * q2]);
-                                    a[2 * q2 + 1] = fmaf(__uint_as_float(wv[q2] & 0xffff0000u), wr[ky * 3 + kx][2 * q2 + 1], a[2 * q2 + 1]);
-                                }
-                            }
-                        {
-                            const float4 ba = *reinterpret_cast<const float4*>(bk);
-                            const float4 bb = *reinterpret_cast<const float4*>(bk + 4);
-                            a[0] += ba.x; a[1] += ba.y; a[2] += ba.z; a[3] += ba.w; a[4] += bb.x; a[5] += bb.y; a[6] += bb.z; a[7] += bb.w;
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t wv = rp[(iy * 18 + j) * 32];
+                            x[j] = make_float2(__uint_as_float(wv << 16), __uint_as_float(wv & 0xffff0000u));
                         }
-                        *reinterpret_cast<uint4*>(sa + r * 128 + ((cg ^ (r & 7)) << 4)) = pack8_bf16(a);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int oy = iy - ky;
+                            if (oy >= 0 && oy < 8) {
+#pragma unroll
+                                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) acc[oy][c] = __ffma2_rn(x[c + kx], w2[ky * 3 + kx], acc[oy][c]);
+                            }
+                        }
+                        if (iy >= 2) {
+                            const int oy = iy - 2;
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int r = oy * 16 + 2 * pw + c;    // pixel of the tile = A row
+                                __nv_bfloat162 hv = __floats2bfloat162_rn(acc[oy][c].x, acc[oy][c].y);
+                                *reinterpret_cast<uint32_t*>(sa + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) =
+                                    *reinterpret_cast<uint32_t*>(&hv);
+                            }
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> UMMA (async proxy) reads
                     __syncwarp();
@@ -831,7 +831,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     // output patch shape: minimise the number of tiles
     const int cand[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
     long long best = -1;
-    for (int i = 0; i < (c.prod == PROD_DW ? 3 : 5); ++i) {       // the halo patch of the depthwise producer: compact shapes only
+    for (int i = 0; i < (c.prod == PROD_DW ? 1 : 5); ++i) {       // the depthwise producer is written for the 8 x 16 patch
         long long t = (long long)((e.Hout + cand[i][0] - 1) / cand[i][0]) * ((e.Wout + cand[i][1] - 1) / cand[i][1]);
         if (best < 0 || t < best) { best = t; p.TH = cand[i][0]; p.TW = cand[i][1]; }
     }
@@ -880,7 +880,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         }
     }
     if (!planned) { snprintf(g_tc_err, sizeof g_tc_err, "no shared-memory plan for BN=%d ksteps=%d", p.BN, ksteps); return 8; }
-    p.l2_prefetch = (p.ks == 1 && c.prod == PROD_TMA && !(p.debug & 16)) ? 3 : 0;
+    p.l2_prefetch = (p.ks == 1 && c.prod != PROD_SQ && !(p.debug & 16)) ? (c.prod == PROD_DW ? 2 : 3) : 0;
     if (c.prod != PROD_TMA && p.store_mode == STORE_DIRECT) p.epi_vec = p.epi_vec && p.ld_vec;
     p.acc_stride = 32;
     while (p.acc_stride < p.BN) p.acc_stride <<= 1;

@@ -110,6 +110,7 @@ class MLICPlusPlus(nn.Module):
         self._engine_sig = None
         self._ws = {}
         self._profile = False
+        self._trace = False
         self.last_launch_count = 0
 
     def _name_for(self, config):
@@ -186,6 +187,10 @@ class MLICPlusPlus(nn.Module):
         _lib.check(_lib.lib().mlic_profile_read(self._engine, out, 1 if reset else 0))
         return float(out[0]), float(out[1]), int(out[2])
 
+    def trace_dump(self, path):
+        """With `_trace` set, writes "label<TAB>microseconds" for every launch since the last dump (development aid)."""
+        _lib.check(_lib.lib().mlic_trace_dump(self._engine, str(path).encode()))
+
     def set_precision(self, precision):
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -239,6 +244,7 @@ class MLICPlusPlus(nn.Module):
         _lib.check(L.mlic_engine_set_option(self._engine, b"tensor_cores", 1 if self.tensor_cores else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"profile", 1 if self._profile else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"fuse", 1 if self.fuse else 0))
+        _lib.check(L.mlic_engine_set_option(self._engine, b"trace", 1 if self._trace else 0))
         prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
         odev = "cpu" if host else dev
         h, w, hz, wz = H // 16, W // 16, H // 64, W // 64
