@@ -103,6 +103,15 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
 int mlic_dwconv3x3_nhwc(int precision, const void* in, int B, int H, int W, int C, const float* weight, const float* bias,
                         int stride, int act, void* out, int iters, float* avg_ms, void* cuda_stream);
 
+/* Stand-alone DepthWiseConv (modules/layers/conv.py:46-63): depthwise 3x3 (pad 1, `stride`, bias) followed by a 1x1
+ * convolution (bias), then act / + residual, on an NHWC activation tensor.  dw_weight: HOST fp32 [Cin][1][3][3],
+ * pw_weight: HOST fp32 [N][Cin][1][1].  fuse = 1 lets the bf16 path produce the depthwise result inside the tcgen05
+ * GEMM kernel (A-operand producer) where the layer shape allows; 0 runs the two kernels back to back.  Timing as
+ * mlic_conv2d_nhwc.  Kernel-level test / micro-benchmark hook. */
+int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int W, int Cin, const float* dw_weight,
+                     const float* dw_bias, const float* pw_weight, const float* pw_bias, int N, int stride, int act,
+                     const void* residual, void* out, int iters, float* avg_ms, void* cuda_stream);
+
 /* Stand-alone fused quantise / likelihood / CDF-index kernel on NCHW fp32 device tensors of one slice
  * (CompressAI GaussianConditional.forward / quantize / build_indexes; call sites models/mlicpp.py:132-134,
  * utils/ckbd.py:128-129).  y, scales, means, y_hat, lik: [n]; sym, idx: [n] (any may be NULL among outputs).

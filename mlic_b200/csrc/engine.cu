@@ -1104,6 +1104,47 @@ int mlic_dwconv3x3_nhwc(int precision, const void* in, int B, int H, int W, int 
     return 0;
 }
 
+int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int W, int Cin, const float* dw_weight,
+                     const float* dw_bias, const float* pw_weight, const float* pw_bias, int N, int stride, int act,
+                     const void* residual, void* out, int iters, float* avg_ms, void* cuda_stream) {
+    if (!in || !dw_weight || !dw_bias || !pw_weight || !out || iters < 1 || (stride != 1 && stride != 2)) return fail("bad arguments");
+    mlic_engine e;
+    e.N = e.M = e.S = e.C = 0; e.kind = 0; e.sd = e.vbr = false; e.Me = 0; e.rc = 0;
+    HostT w, b;
+    w.shape = {Cin, 1, 3, 3}; w.v.assign(dw_weight, dw_weight + (size_t)Cin * 9);
+    b.shape = {Cin}; b.v.assign(dw_bias, dw_bias + Cin);
+    e.params["d.depth_conv.weight"] = w; e.params["d.depth_conv.bias"] = b;
+    e.pack_dw_list("d.depth_conv", {"d.depth_conv"});
+    e.pack_conv_raw("d.point_conv", pw_weight, pw_bias, N, Cin, 1, 0);
+    if (e.rc) return e.rc;
+    e.bf = precision == MLIC_PREC_BF16; e.use_tc = 1; e.fuse = fuse; e.dry = false; e.st = (cudaStream_t)cuda_stream;
+    if (e.bf && tc_init()) return fail("%s", tc_last_error());
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    void* ws = nullptr;
+    const size_t ws_bytes = (size_t)B * Ho * Wo * ((Cin + 7) / 8 * 8) * 4 + 1024;
+    CUDA_OK(cudaMalloc(&ws, ws_bytes));
+    e.dev_allocs.push_back(ws);
+    e.ws_base = (uint8_t*)ws; e.ws_size = ws_bytes; e.ws_off = 0;
+    Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin;
+    Act o; o.p = out; o.B = B; o.H = Ho; o.W = Wo; o.C = N; o.ld = N;
+    Act r = o; r.p = const_cast<void*>(residual);
+    EpiOpt eo; eo.act = act; if (residual) eo.res = &r;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    e.dsconv(a, "d", stride, &o, eo);
+    CUDA_OK(cudaEventRecord(e0, e.st));
+    for (int i = 1; i < iters; ++i) e.dsconv(a, "d", stride, &o, eo);
+    CUDA_OK(cudaEventRecord(e1, e.st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e.rc) return e.rc;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, const float* scale_table64,
                               float* y_hat, float* lik, int32_t* sym, int32_t* idx, void* cuda_stream) {
     static float* table = nullptr;          // utils/func.py:16-19, fp32

@@ -59,8 +59,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    for (;;) {
+    long long t0 = 0;
+    for (uint32_t n = 1;; ++n) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -70,7 +70,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s: fail the launch instead of hanging the GPU
+        if ((n & 0x3ffu) == 0) {                               // the clock is read once per 1024 failed polls only
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000LL) __trap();          // ~2 s: fail the launch instead of hanging the GPU
+        }
     }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
@@ -134,6 +138,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// explicit shared-state-space accesses: pointers derived from the dynamic shared-memory base are generic to the compiler,
+// and generic LD / ST to shared memory are slower than LDS / STS
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float2 lds_f2(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 enum { STORE_DIRECT = 0, STORE_TMA = 1, STORE_NCHW3 = 2 };
@@ -208,25 +226,47 @@ __device__ __forceinline__ uint4 pack8_bf16(const float v[8]) {
 }
 
 // Epilogue arithmetic for 8 consecutive GEMM columns n..n+7 of one output pixel, in the order of epi_store4
-// (common.cuh): premask, + bias, (I)GDN, activation, postmask, + residual.  bf16 activations.  The mode tests are
-// hoisted out of the element loops and the caller does not unroll across 8-column groups: the epilogue must stay a
-// few hundred instructions, or the eight epilogue warps stall on instruction fetch.
-// GELU(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below bf16 resolution):
-// one MUFU.RCP, one MUFU.EX2 and 8 FMA-class instructions instead of erff()'s ~30.  Fast (bf16) mode only; the fp32
-// validation path keeps erff.
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t, ex;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * z * z));
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float q = p * t * ex;                                     // 1 - erf(|z|)
-    const float hx = 0.5f * x;
-    return fmaf(copysignf(1.0f - q, x), hx, hx);                    // 0.5 x (1 + erf(x / sqrt 2))
+// (common.cuh): premask, + bias, (I)GDN, activation, postmask, + residual.  bf16 activations.
+// The epilogue is issue-bound (measured: 72 % issue-slot utilisation with the scalar erf form, ncu profiles/), so the
+// arithmetic runs on packed fp32 pairs (FFMA2 / FMUL2 / FADD2: one issue slot per two columns) and GELU uses ONE MUFU:
+//   GELU(x) = x Phi(x),  Phi(x) ~= 0.5 + 0.5 tanh(x (a + b t + c t^2)),  t = min(x^2, 64)
+// with (a, b, c) the minimax fit to the erf form (|error| <= 2.6e-5 with an exact tanh; tanh.approx adds <= 2^-11
+// relative on tanh, i.e. <= 2.5e-4 |x| absolute, below half a bf16 ulp of the stored result for |x| >= 0.13).  Fast
+// (bf16) mode only; the fp32 validation path keeps erff.
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+#ifndef MLIC_GELU_FORM
+#define MLIC_GELU_FORM 1
+#endif
+__device__ __forceinline__ float2 gelu2(float2 x) {
+    float2 t = __fmul2_rn(x, x);
+    t.x = fminf(t.x, 64.0f); t.y = fminf(t.y, 64.0f);
+#if MLIC_GELU_FORM == 0      // one MUFU.TANH (2^-11 relative on tanh)
+    float2 q = __ffma2_rn(t, make_float2(-3.51516790e-04f, -3.51516790e-04f), make_float2(3.70056460e-02f, 3.70056460e-02f));
+    q = __ffma2_rn(q, t, make_float2(7.97507884e-01f, 7.97507884e-01f));
+    const float2 u = __fmul2_rn(x, q);
+    const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(hx, th, hx);
+#else                        // Phi = 1 / (1 + 2^(-2 log2(e) u)): MUFU.EX2 + MUFU.RCP, both ~2^-22
+    constexpr float K = -2.0f * 1.4426950408889634f;
+    float2 q = __ffma2_rn(t, make_float2(K * -3.51516790e-04f, K * -3.51516790e-04f), make_float2(K * 3.70056460e-02f, K * 3.70056460e-02f));
+    q = __ffma2_rn(q, t, make_float2(K * 7.97507884e-01f, K * 7.97507884e-01f));
+    const float2 u = __fmul2_rn(x, q);
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(u.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(u.y));
+    const float2 d = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+    return __fmul2_rn(x, make_float2(r0, r1));
+#endif
+}
+__device__ __forceinline__ float gelu_fast(float x) { return gelu2(make_float2(x, x)).x; }
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 
 struct EpiRow {
     const bf16* xp;      // GDN operand row (at column 0) or null
@@ -244,56 +284,88 @@ __device__ __forceinline__ void unpack8_bf16(const uint4 t, float v[8]) {
 // STAGED: the GDN operand / residual chunk of this thread was prefetched into the staging slot (xs / rs, shared memory)
 template <int ACT, int GDN, bool RES, bool STAGED>
 __device__ __forceinline__ void epi_math8(const Epi& e, const float* __restrict__ sBias, const EpiRow& row, int n, int oc,
-                                          float* a, bool ldvec, const uint8_t* xs = nullptr, const uint8_t* rs = nullptr) {
+                                          float* a, bool ldvec, uint32_t xs = 0, uint32_t rs = 0) {
     const bool full = ldvec && n + 8 <= e.N;
+    float2 v[4];
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(sBias + n), b1 = *reinterpret_cast<const float4*>(sBias + n + 4);
+        if (!row.keep_pre) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = (row.keep_pre ? a[j] : 0.0f) + sBias[n + j];
+            for (int j = 0; j < 8; ++j) a[j] = 0.0f;
+        }
+        v[0] = __fadd2_rn(make_float2(a[0], a[1]), make_float2(b0.x, b0.y));
+        v[1] = __fadd2_rn(make_float2(a[2], a[3]), make_float2(b0.z, b0.w));
+        v[2] = __fadd2_rn(make_float2(a[4], a[5]), make_float2(b1.x, b1.y));
+        v[3] = __fadd2_rn(make_float2(a[6], a[7]), make_float2(b1.z, b1.w));
+    }
     if constexpr (GDN != GDN_NONE) {
-        float x[8];
+        float2 x[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        for (int j = 0; j < 4; ++j) x[j] = make_float2(0.f, 0.f);
         if constexpr (STAGED) {
-            unpack8_bf16(*reinterpret_cast<const uint4*>(xs), x);
+            const uint4 t = lds128(xs);
+            x[0] = bf2_to_f2(t.x); x[1] = bf2_to_f2(t.y); x[2] = bf2_to_f2(t.z); x[3] = bf2_to_f2(t.w);
         } else if (row.xp) {
-            if (full) load8_bf16(row.xp + n, x);
-            else {
+            if (full) {
+                const uint4 t = *reinterpret_cast<const uint4*>(row.xp + n);
+                x[0] = bf2_to_f2(t.x); x[1] = bf2_to_f2(t.y); x[2] = bf2_to_f2(t.z); x[3] = bf2_to_f2(t.w);
+            } else {
+                float xs1[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xs1[j] = 0.f;
 #pragma unroll 1
-                for (int j = 0; j < 8; ++j) if (n + j < e.N) x[j] = __bfloat162float(row.xp[n + j]);
+                for (int j = 0; j < 8; ++j) if (n + j < e.N) xs1[j] = __bfloat162float(row.xp[n + j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = make_float2(xs1[2 * j], xs1[2 * j + 1]);
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = x[j] * (GDN == GDN_FWD ? rsqrtf(a[j]) : sqrtf(a[j]));
+        for (int j = 0; j < 4; ++j) {
+            float s0, s1;
+            if constexpr (GDN == GDN_FWD) {
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(v[j].x));
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(v[j].y));
+            } else {
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(v[j].x));
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(v[j].y));
+            }
+            v[j] = __fmul2_rn(x[j], make_float2(s0, s1));
+        }
     }
     if constexpr (ACT == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = gelu_fast(a[j]);
+        for (int j = 0; j < 4; ++j) v[j] = gelu2(v[j]);
     } else if constexpr (ACT == ACT_HALF_TANH) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = 0.5f * tanhf(a[j]);
+        for (int j = 0; j < 4; ++j) v[j] = make_float2(0.5f * tanhf(v[j].x), 0.5f * tanhf(v[j].y));
     }
     if (!row.keep_post) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = 0.0f;
+        for (int j = 0; j < 4; ++j) v[j] = make_float2(0.f, 0.f);
     }
     if constexpr (RES && STAGED) {
-        float r[8];
-        unpack8_bf16(*reinterpret_cast<const uint4*>(rs), r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] += r[j];
+        const uint4 t = lds128(rs);
+        v[0] = __fadd2_rn(v[0], bf2_to_f2(t.x)); v[1] = __fadd2_rn(v[1], bf2_to_f2(t.y));
+        v[2] = __fadd2_rn(v[2], bf2_to_f2(t.z)); v[3] = __fadd2_rn(v[3], bf2_to_f2(t.w));
     } else if constexpr (RES) {
         if (row.rp) {
-            float r[8];
+            if (full) {
+                const uint4 t = *reinterpret_cast<const uint4*>(row.rp + oc);
+                v[0] = __fadd2_rn(v[0], bf2_to_f2(t.x)); v[1] = __fadd2_rn(v[1], bf2_to_f2(t.y));
+                v[2] = __fadd2_rn(v[2], bf2_to_f2(t.z)); v[3] = __fadd2_rn(v[3], bf2_to_f2(t.w));
+            } else {
+                float r[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = 0.f;
-            if (full) load8_bf16(row.rp + oc, r);
-            else {
+                for (int j = 0; j < 8; ++j) r[j] = 0.f;
 #pragma unroll 1
                 for (int j = 0; j < 8; ++j) if (n + j < e.N) r[j] = __bfloat162float(row.rp[oc + j]);
-            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] += r[j];
+                for (int j = 0; j < 4; ++j) v[j] = __fadd2_rn(v[j], make_float2(r[2 * j], r[2 * j + 1]));
+            }
         }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[2 * j] = v[j].x; a[2 * j + 1] = v[j].y; }
 }
 
 // pixel-shuffle bookkeeping of one GEMM column: group g = n / Cq -> output pixel (2h + (g >> 1), 2w + (g & 1)), channel n % Cq
@@ -386,7 +458,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_full[2], acc_empty[2], bres_bar;
     __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_RAW_SLOTS];     // fused producers: TMA -> compute warps
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float sBias[TC_MAX_BIAS];
+    __shared__ __align__(16) float sBias[TC_MAX_BIAS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tilesH * p.tilesW;
@@ -531,12 +603,13 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     TIMED_WAIT(w0c, &raw_full[rslot], rphase);         // halo patch landed
                     TIMED_WAIT(w1c, &empty_bar[stage], phase ^ 1);     // A stage free (its MMAs retired)
                     const int pw = warp - 4;
-                    const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawbuf + (size_t)rslot * p.raw_bytes) + (2 * pw) * 32 + lane;
-                    const float* wk = sDw + k * 64 + 2 * lane;         // tap t at wk[t * Cin]
+                    const uint32_t rp = smem_u32(rawbuf) + (uint32_t)(rslot * p.raw_bytes + ((2 * pw) * 32 + lane) * 4);
+                    const uint32_t wk = smem_u32(sDw) + (uint32_t)((k * 64 + 2 * lane) * 4);         // tap t at wk + t * Cin * 4
+                    const uint32_t sa_s = smem_u32(sa);
                     float2 w2[9];
 #pragma unroll
-                    for (int tp = 0; tp < 9; ++tp) w2[tp] = *reinterpret_cast<const float2*>(wk + tp * p.Cin);
-                    const float2 b2 = *reinterpret_cast<const float2*>(wk + 9 * p.Cin);
+                    for (int tp = 0; tp < 9; ++tp) w2[tp] = lds_f2(wk + (uint32_t)(tp * p.Cin * 4));
+                    const float2 b2 = lds_f2(wk + (uint32_t)(9 * p.Cin * 4));
                     float2 acc[8][2];
 #pragma unroll
                     for (int oy = 0; oy < 8; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
@@ -545,7 +618,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                         float2 x[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint32_t wv = rp[(iy * 18 + j) * 32];
+                            const uint32_t wv = lds32(rp + (uint32_t)((iy * 18 + j) * 128));
                             x[j] = make_float2(__uint_as_float(wv << 16), __uint_as_float(wv & 0xffff0000u));
                         }
 #pragma unroll
@@ -564,8 +637,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                             for (int c = 0; c < 2; ++c) {
                                 const int r = oy * 16 + 2 * pw + c;    // pixel of the tile = A row
                                 __nv_bfloat162 hv = __floats2bfloat162_rn(acc[oy][c].x, acc[oy][c].y);
-                                *reinterpret_cast<uint32_t*>(sa + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) =
-                                    *reinterpret_cast<uint32_t*>(&hv);
+                                sts32(sa_s + (uint32_t)(r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)), *reinterpret_cast<uint32_t*>(&hv));
                             }
                         }
                     }
@@ -577,12 +649,12 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     mbar_wait(&raw_full[stage], phase);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        uint4* q4 = reinterpret_cast<uint4*>(sa) + pt + 256 * i;      // layout-agnostic: element-wise
+                        const uint32_t q4 = smem_u32(sa) + (uint32_t)((pt + 256 * i) * 16);      // layout-agnostic: element-wise
                         float v[8];
-                        unpack8_bf16(*q4, v);
+                        unpack8_bf16(lds128(q4), v);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
-                        *q4 = pack8_bf16(v);
+                        sts128(q4, pack8_bf16(v));
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -631,6 +703,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     if (e.shuffle) { const int Cq = e.N >> 2; g = ocb / Cq; ocb -= g * Cq; }
                     const bool gissuer = (q == 0 && lane == 0);
                     uint8_t* sb = stg + (size_t)((cq * nring + (blk % nring)) * per) * TC_STG_BYTES;
+                    const uint32_t sb_s = smem_u32(sb);
                     long long tq0 = dbg ? clock64() : 0;
                     if (nring == 1) {               // single slot: this group's previous store must have drained it
                         if (gissuer) tma_store_wait_read(0);
@@ -656,7 +729,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int prow = q * 32 + i * 4 + (lane >> 3);
-                                *reinterpret_cast<uint4*>(sb + dst_off + (uint32_t)(prow * 128 + (((lane & 7) ^ (prow & 7)) << 4))) = rr[i];
+                                sts128(sb_s + dst_off + (uint32_t)(prow * 128 + (((lane & 7) ^ (prow & 7)) << 4)), rr[i]);
                             }
                         };
                         if constexpr (RES) stage_rows(e.res, e.res_ld, 0u);
@@ -688,12 +761,12 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                             const int jj = pr * 2 + sub;
                             const uint32_t off = (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4));
                             epi_math8<ACT, GDN, RES, true>(e, sBias, row, n0 + c + sub * 8, ocb + pr * 16 + sub * 8, v, true,
-                                                           sb + TC_STG_BYTES + off, sb + off);
-                            *reinterpret_cast<uint4*>(sb + off) = pack8_bf16(v);
+                                                           sb_s + TC_STG_BYTES + off, sb_s + off);
+                            sts128(sb_s + off, pack8_bf16(v));
                             if (e.out2) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) v[j] = v[j] * v[j];
-                                *reinterpret_cast<uint4*>(sb + TC_STG_BYTES + off) = pack8_bf16(v);
+                                sts128(sb_s + TC_STG_BYTES + off, pack8_bf16(v));
                             }
                         }
                     }

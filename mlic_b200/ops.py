@@ -50,6 +50,30 @@ def dwconv3x3_nhwc(x, weight, bias, stride=1, act=None, iters=1):
     return out, float(ms.value)
 
 
+def dsconv_nhwc(x, dw_weight, dw_bias, pw_weight, pw_bias, stride=1, act=None, residual=None, fuse=True, iters=1):
+    """DepthWiseConv (dw3x3 pad 1 + bias -> 1x1 + bias -> act -> + residual) on a CUDA NHWC tensor -> (out, avg ms)."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+    B, H, W, Cin = x.shape
+    N = pw_weight.shape[0]
+    dw = dw_weight.detach().to("cpu", torch.float32).contiguous()
+    db = dw_bias.detach().to("cpu", torch.float32).contiguous()
+    pw = pw_weight.detach().to("cpu", torch.float32).contiguous()
+    pb = pw_bias.detach().to("cpu", torch.float32).contiguous()
+    out = torch.empty((B, (H - 1) // stride + 1, (W - 1) // stride + 1, N), dtype=x.dtype, device=x.device)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == x.dtype and residual.is_contiguous()
+    ms = C.c_float(0)
+    prec = _lib.PREC_BF16 if x.dtype == torch.bfloat16 else _lib.PREC_FP32
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_dsconv_nhwc(prec, 1 if fuse else 0, C.c_void_p(x.data_ptr()), B, H, W, Cin,
+                                               C.c_void_p(dw.data_ptr()), C.c_void_p(db.data_ptr()), C.c_void_p(pw.data_ptr()),
+                                               C.c_void_p(pb.data_ptr()), N, stride, ACT[act],
+                                               C.c_void_p(residual.data_ptr()) if residual is not None else None,
+                                               C.c_void_p(out.data_ptr()), iters, C.byref(ms), C.c_void_p(st)))
+    return out, float(ms.value)
+
+
 def gaussian_conditional(y, scales, means, scale_table=None):
     """Fused quantise / likelihood / CDF-index on flat fp32 CUDA tensors -> (y_hat, lik, symbols, indexes)."""
     n = y.numel()
