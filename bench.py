@@ -221,8 +221,12 @@ def main():
     # end to end through the public API with HOST buffers: pinned x -> H2D -> forward -> D2H of x_hat and likelihoods
     e2e = None
     if not args.no_e2e:
-        for _ in range(2):
-            net(x_host)
+        # warm-up: the caller-visible outputs are fresh pinned tensors every call; holding two generations alive once puts
+        # both buffer sets in torch's pinned-memory cache, so no cudaHostAlloc lands inside the timed region
+        keep = [net(x_host) for _ in range(2)]
+        del keep
+        for _ in range(max(args.warmup - 2, 1)):
+            o = net(x_host)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):

@@ -112,6 +112,27 @@ int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int 
                      const float* dw_bias, const float* pw_weight, const float* pw_bias, int N, int stride, int act,
                      const void* residual, void* out, int iters, float* avg_ms, void* cuda_stream);
 
+/* Stand-alone LocalContext windowed attention (modules/transform/context.py:80-107; 5x5 window, 2 heads of 16, C = 32).
+ * rel_bias: DEVICE fp32 [2][25][25] (relative_position_table gathered through relative_position_index).
+ *   impl 0: fp32 CUDA-core kernel.  F: DEVICE fp32 [B*H*W][96], channels q|k|v with the reference's interleaved head
+ *           split (c = d*2 + head); O: DEVICE fp32 [B*H*W][25][32] (channel = head*16 + d), every pixel.
+ *   impl 1: as 0 with O in bf16.
+ *   impl 2: bf16 warp-level tensor-core kernel.  F: DEVICE bf16 [B*H*W][96] HEAD-MAJOR (q_h0 q_h1 k_h0 k_h1 v_h0 v_h1);
+ *           O: DEVICE bf16 [B*H*(W/2)][25][32]: the NON-ANCHOR pixels only, squeezed as utils/ckbd.py:47-59
+ *           (w = 2j + (h & 1)).
+ * Timing as mlic_conv2d_nhwc.  Kernel-level test / micro-benchmark hook. */
+int mlic_local_attn(int impl, const void* F, int B, int H, int W, const float* rel_bias, void* O, int iters, float* avg_ms,
+                    void* cuda_stream);
+
+/* Stand-alone g_a stage-0 head of the bf16 path (ResidualBlockWithStride(3 -> N, stride 2), modules/layers/res_blk.py:82-93
+ * with DepthWiseConv, conv.py:46-63): x DEVICE fp32 NCHW [B,3,H,W] ->
+ *   t_out    = GELU(point_conv(depth_conv_s2(x)))   DEVICE bf16 NHWC [B,H/2,W/2,N]
+ *   skip_out = skip_1x1_s2(x)                        DEVICE bf16 NHWC [B,H/2,W/2,N]
+ * dw_weight HOST [3][1][3][3], pw_weight / skip_weight HOST [N][3][1][1], biases HOST.  Timing as mlic_conv2d_nhwc. */
+int mlic_ga_head(const float* x, int B, int H, int W, const float* dw_weight, const float* dw_bias, const float* pw_weight,
+                 const float* pw_bias, const float* skip_weight, const float* skip_bias, int N, void* t_out, void* skip_out,
+                 int iters, float* avg_ms, void* cuda_stream);
+
 /* Stand-alone fused quantise / likelihood / CDF-index kernel on NCHW fp32 device tensors of one slice
  * (CompressAI GaussianConditional.forward / quantize / build_indexes; call sites models/mlicpp.py:132-134,
  * utils/ckbd.py:128-129).  y, scales, means, y_hat, lik: [n]; sym, idx: [n] (any may be NULL among outputs).

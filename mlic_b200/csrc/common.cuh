@@ -44,6 +44,43 @@ __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU(approxi
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// Fast GELU of the bf16 path (packed fp32x2; see the epilogue notes in gemm_tc.cu).
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#ifndef MLIC_GELU_FORM
+#define MLIC_GELU_FORM 1
+#endif
+__device__ __forceinline__ float2 gelu2(float2 x) {
+    float2 t = __fmul2_rn(x, x);
+    t.x = fminf(t.x, 64.0f); t.y = fminf(t.y, 64.0f);
+#if MLIC_GELU_FORM == 0      // one MUFU.TANH (2^-11 relative on tanh)
+    float2 q = __ffma2_rn(t, make_float2(-3.51516790e-04f, -3.51516790e-04f), make_float2(3.70056460e-02f, 3.70056460e-02f));
+    q = __ffma2_rn(q, t, make_float2(7.97507884e-01f, 7.97507884e-01f));
+    const float2 u = __fmul2_rn(x, q);
+    const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(hx, th, hx);
+#else                        // Phi = 1 / (1 + 2^(-2 log2(e) u)): MUFU.EX2 + MUFU.RCP, both ~2^-22
+    constexpr float K = -2.0f * 1.4426950408889634f;
+    float2 q = __ffma2_rn(t, make_float2(K * -3.51516790e-04f, K * -3.51516790e-04f), make_float2(K * 3.70056460e-02f, K * 3.70056460e-02f));
+    q = __ffma2_rn(q, t, make_float2(K * 7.97507884e-01f, K * 7.97507884e-01f));
+    const float2 u = __fmul2_rn(x, q);
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(u.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(u.y));
+    const float2 d = __fadd2_rn(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+    return __fmul2_rn(x, make_float2(r0, r1));
+#endif
+}
+__device__ __forceinline__ float gelu_fast(float x) { return gelu2(make_float2(x, x)).x; }
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
+
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -74,6 +75,17 @@ struct EpiOpt {
 };
 
 }  // namespace
+
+// Host-buffer call (mlic_run_host): copies are pipelined against the walk image by image.  x[b] is uploaded on `s_in`
+// while g_a works on image b-1; the likelihoods are downloaded on `s_out` while g_s runs; x_hat[b] is downloaded while
+// g_s works on image b+1.
+struct HostPipe {
+    const float* hx = nullptr;        // host x [B,3,H,W]
+    float* hx_hat = nullptr;          // host x_hat
+    float* hy_lik = nullptr;          // host y_likelihoods
+    float* hz_lik = nullptr;          // host z_likelihoods
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+};
 
 struct mlic_engine {
     int N, M, S, C, kind;
@@ -151,7 +163,14 @@ struct mlic_engine {
     // host-call staging (mlic_run_host)
     void* h_ws = nullptr; size_t h_ws_bytes = 0;
     void* h_io = nullptr; size_t h_io_bytes = 0;
-    cudaStream_t h_stream = nullptr;
+    std::map<std::array<int, 7>, size_t> ws_cache;       // mlic_workspace_bytes results
+    cudaStream_t h_stream = nullptr, h_in = nullptr, h_out = nullptr;
+    std::vector<cudaEvent_t> pipe_ev;
+    size_t pipe_used = 0;
+    cudaEvent_t pipe_event() {
+        if (pipe_used == pipe_ev.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); pipe_ev.push_back(e); }
+        return pipe_ev[pipe_used++];
+    }
 
     ~mlic_engine() {
         for (void* p : dev_allocs) cudaFree(p);
@@ -159,6 +178,9 @@ struct mlic_engine {
         if (h_ws) cudaFree(h_ws);
         if (h_io) cudaFree(h_io);
         if (h_stream) cudaStreamDestroy(h_stream);
+        if (h_in) cudaStreamDestroy(h_in);
+        if (h_out) cudaStreamDestroy(h_out);
+        for (cudaEvent_t ev : pipe_ev) cudaEventDestroy(ev);
     }
 
     // ------------------------------------------------------------------ parameter access / packing
@@ -278,7 +300,7 @@ struct mlic_engine {
 
     int finalize() {
         for (void* p : dev_allocs) cudaFree(p);
-        dev_allocs.clear(); convs.clear(); dws.clear(); lns.clear(); misc.clear();
+        dev_allocs.clear(); convs.clear(); dws.clear(); lns.clear(); misc.clear(); ws_cache.clear();
         rc = 0;
         // g_a / h_a
         std::string p = "g_a.analysis_transform.";
@@ -306,6 +328,22 @@ struct mlic_engine {
             std::string lc = "local_context." + is;
             pack_ln(lc + ".norm1"); pack_ln(lc + ".norm2");
             pack_conv(lc + ".qkv_proj"); pack_conv(lc + ".proj"); pack_conv(lc + ".mlp.fc1"); pack_conv(lc + ".mlp.fc2");
+            if (C == 32) {   // head-major copy of qkv_proj for the tensor-core attention kernel: row u*C + hh*16 + dd <- u*C + dd*2 + hh
+                const HostT* w = get(lc + ".qkv_proj.weight");
+                const HostT* b = get(lc + ".qkv_proj.bias");
+                if (w && b && w->dim(0) == 3 * C) {
+                    const int Ci = (int)w->dim(1);
+                    std::vector<float> wp((size_t)3 * C * Ci), bp(3 * C);
+                    for (int u = 0; u < 3; ++u)
+                        for (int hh = 0; hh < 2; ++hh)
+                            for (int dd = 0; dd < 16; ++dd) {
+                                const int o = u * C + dd * 2 + hh, n = u * C + hh * 16 + dd;
+                                for (int c = 0; c < Ci; ++c) wp[(size_t)n * Ci + c] = w->v[(size_t)o * Ci + c];
+                                bp[n] = b->v[o];
+                            }
+                    pack_conv_raw(lc + ".qkv_proj_hm", wp.data(), bp.data(), 3 * C, Ci, 1, 0);
+                }
+            }
             {   // fusion Conv2d(C,2C,k=5) applied to [C,5,5] windows == linear over K = tap*C + c
                 const HostT* w = get(lc + ".fusion.weight");
                 const HostT* b = get(lc + ".fusion.bias");
@@ -572,14 +610,30 @@ struct mlic_engine {
         ws_off = mark;
     }
     // ResidualBlockWithStride (res_blk.py:82-93): GDN(conv2(GELU(conv1_s2 x))) + skip_1x1_s2(x)
-    void rbws(const Act& x, const std::string& p, bool dense, const Act& out) {
+    // x_nchw != null: x is the fp32 NCHW image itself (3 channels) and conv1 + skip run as the fused head kernel.
+    bool head_fused() const { return bf && use_tc && fuse && !sd; }
+    void rbws(const Act& x, const std::string& p, bool dense, const Act& out, const float* x_nchw = nullptr, bool head = false) {
         size_t mark = ws_off;
         EpiOpt g; g.act = ACT_GELU;
         Act t = act(out.B, out.H, out.W, out.C);
-        c3(x, p + ".conv1", 2, dense, &t, g);
         Act v = act(out.B, out.H, out.W, out.C);
         Act sk = act(out.B, out.H, out.W, out.C);
-        gemm(x, p + ".skip", 2, 0, &sk, EpiOpt());
+        if (head) {
+            const DwW* d = dw(p + ".conv1.depth_conv");
+            const ConvW* w1 = cw(p + ".conv1.point_conv");
+            const ConvW* wk = cw(p + ".skip");
+            if (d && w1 && wk && go()) {
+                if (d->C != 3 || w1->Cin != 3 || wk->Cin != 3 || w1->N != out.C || wk->N != out.C || !ga_head_supported(x.H, x.W, out.C, t, sk) || !x_nchw) {
+                    if (!rc) rc = fail("g_a head: unsupported geometry");
+                } else {
+                    launch_ga_head(x_nchw, x.B, x.H, x.W, d->w9, d->bias, w1->w32, w1->bias, wk->w32, wk->bias, out.C, t, sk, st);
+                    after_launch((p + ".head").c_str());
+                }
+            }
+        } else {
+            c3(x, p + ".conv1", 2, dense, &t, g);
+            gemm(x, p + ".skip", 2, 0, &sk, EpiOpt());
+        }
         EpiOpt og; og.gdn = GDN_FWD; og.gdn_x = &v; og.res = &sk;
         gdn_block(t, p + ".conv2", dense, v, p + ".gdn", out, og);
         ws_off = mark;
@@ -599,13 +653,13 @@ struct mlic_engine {
     }
 
     // g_a (transform/analysis.py:9-17): x [B,H,W,3] -> y fp32 [pix][M]
-    void g_a(const Act& x, float* y32) {
+    void g_a(const Act& x, float* y32, const float* x_nchw = nullptr) {
         size_t mark = ws_off;
         const std::string p = "g_a.analysis_transform.";
         Act cur = x;
         for (int i : {0, 2, 4}) {
             Act a = act(cur.B, cur.H / 2, cur.W / 2, N);
-            rbws(cur, p + std::to_string(i), sd, a);
+            rbws(cur, p + std::to_string(i), sd, a, x_nchw, i == 0 && head_fused());
             Act b = act(a.B, a.H, a.W, N);
             rb(a, p + std::to_string(i + 1), sd, b);
             cur = b;
@@ -771,6 +825,30 @@ struct mlic_engine {
         const size_t npix = (size_t)x.B * x.H * x.W;
         Act t = act(x.B, x.H, x.W, Cc);
         layernorm(x, p + ".norm1", t);
+        if (bf && use_tc && fuse && Cc == 32 && (x.W % 2) == 0 && convs.count(p + ".qkv_proj_hm")) {
+            // bf16 fast path: attention on the warp-level tensor path for the non-anchor pixels only (the anchor half of the
+            // LocalContext output is never observed, mlicpp.py:146-150); the per-pixel tail runs on the squeezed matrix.
+            const int Mh = (int)(npix / 2);
+            Act Fb = act(x.B, x.H, x.W, 3 * Cc);
+            gemm(t, p + ".qkv_proj_hm", 1, 0, &Fb, EpiOpt());
+            Act O = act(1, 1, Mh, 25 * Cc);
+            if (go()) {
+                if (launch_local_attn_mma(Fb, misc[p + ".rel_bias"], O.p, st)) { if (!rc) rc = fail("local attention (mma): unsupported geometry"); }
+                after_launch("local_attn");
+            }
+            Act fu = act(1, 1, Mh, 2 * Cc), pr = act(1, 1, Mh, 2 * Cc), n2 = act(1, 1, Mh, 2 * Cc), os = act(1, 1, Mh, 2 * Cc);
+            gemm(O, p + ".fusion", 1, 0, &fu, EpiOpt());
+            gemm(fu, p + ".proj", 1, 0, &pr, EpiOpt());
+            layernorm(pr, p + ".norm2", n2);
+            Act h = act(1, 1, Mh, 4 * Cc);
+            EpiOpt g; g.act = ACT_GELU;
+            gemm(n2, p + ".mlp.fc1", 1, 0, &h, g);
+            EpiOpt o; o.res = &pr;
+            gemm(h, p + ".mlp.fc2", 1, 0, &os, o);
+            if (go()) { launch_unsqueeze_nonanchor(os, out, st); after_launch("local_unsqueeze"); }
+            ws_off = mark;
+            return;
+        }
         float* F = f32(npix * 3 * Cc);
         EpiOpt of; of.out_f32 = F; of.out_f32_ld = 3 * Cc;
         gemm(t, p + ".qkv_proj", 1, 0, nullptr, of);
@@ -793,12 +871,13 @@ struct mlic_engine {
 
     // ------------------------------------------------------------------ the whole call
     int run(int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* io, void* ws, size_t ws_bytes,
-            cudaStream_t stream, bool dry_run) {
+            cudaStream_t stream, bool dry_run, const HostPipe* hp = nullptr) {
         if (!finalized) return fail("engine not finalized");
         if (B <= 0 || H <= 0 || W <= 0 || (H % 64) || (W % 64)) return fail("B=%d H=%d W=%d: H and W must be positive multiples of 64", B, H, W);
         if (mode < 0 || mode > 2) return fail("bad mode %d", mode);
         bf = precision == MLIC_PREC_BF16;
         dry = dry_run; st = stream; rc = 0; launches = 0;
+        if (hp && !dry) pipe_used = 0;
         if (!dry && profile && ev_used > 200000) { if (profile_collect()) return 1; }
         ws_base = (uint8_t*)ws; ws_size = ws_bytes; ws_off = 0; ws_peak = 0;
         if (trace) tr("start");
@@ -824,9 +903,30 @@ struct mlic_engine {
         if (mode != MLIC_MODE_DECODER) {
             if (!dry && !io->x) return fail("x is NULL");
             size_t mark = ws_off;
-            Act x = act(B, H, W, 3);
-            if (go()) { launch_nchw_to_nhwc(bf, io->x, x, 3, st); after_launch("nchw_to_nhwc"); }
-            g_a(x, y32);
+            if (hp && hp->hx && head_fused() && !dry) {
+                // host call: upload image by image, g_a on image b as soon as it has landed
+                const size_t img = (size_t)3 * H * W;
+                std::vector<cudaEvent_t> ev(B);
+                for (int b = 0; b < B; ++b) {
+                    cudaMemcpyAsync(const_cast<float*>(io->x) + b * img, hp->hx + b * img, img * 4, cudaMemcpyHostToDevice, hp->s_in);
+                    ev[b] = pipe_event();
+                    cudaEventRecord(ev[b], hp->s_in);
+                }
+                for (int b = 0; b < B && !rc; ++b) {
+                    cudaStreamWaitEvent(st, ev[b], 0);
+                    Act x; x.p = nullptr; x.B = 1; x.H = H; x.W = W; x.C = 3; x.ld = 3;
+                    g_a(x, y32 + (size_t)b * h * w * M, io->x + b * img);
+                }
+            } else if (head_fused()) {            // the head kernel reads the NCHW image directly
+                if (hp && hp->hx && !dry) cudaMemcpyAsync(const_cast<float*>(io->x), hp->hx, (size_t)B * 3 * H * W * 4, cudaMemcpyHostToDevice, st);
+                Act x; x.p = nullptr; x.B = B; x.H = H; x.W = W; x.C = 3; x.ld = 3;
+                g_a(x, y32, io->x);
+            } else {
+                if (hp && hp->hx && !dry) cudaMemcpyAsync(const_cast<float*>(io->x), hp->hx, (size_t)B * 3 * H * W * 4, cudaMemcpyHostToDevice, st);
+                Act x = act(B, H, W, 3);
+                if (go()) { launch_nchw_to_nhwc(bf, io->x, x, 3, st); after_launch("nchw_to_nhwc"); }
+                g_a(x, y32);
+            }
             ws_off = mark;
             Act ya = act(B, h, w, M);
             if (go()) { launch_copy_f32_to_act(bf, y32, M, ya, st); after_launch("copy_y"); }
@@ -886,7 +986,24 @@ struct mlic_engine {
             after_launch("lik_nchw");
         }
         if (io->y_hat && go()) { launch_nhwc_to_nchw(bf, yhat, io->y_hat, st); after_launch("y_hat_tap"); }
-        if (io->x_hat || dry) g_s(yhat, io->x_hat);
+        if (hp && go() && mode == MLIC_MODE_FORWARD && (hp->hy_lik || hp->hz_lik)) {      // likelihoods go home while g_s runs
+            cudaEvent_t ev = pipe_event();
+            cudaEventRecord(ev, st);
+            cudaStreamWaitEvent(hp->s_out, ev, 0);
+            if (hp->hy_lik && io->y_likelihoods) cudaMemcpyAsync(hp->hy_lik, io->y_likelihoods, npix * M * 4, cudaMemcpyDeviceToHost, hp->s_out);
+            if (hp->hz_lik && io->z_likelihoods) cudaMemcpyAsync(hp->hz_lik, io->z_likelihoods, (size_t)B * hz * wz * N * 4, cudaMemcpyDeviceToHost, hp->s_out);
+        }
+        if (hp && hp->hx_hat && io->x_hat && go()) {
+            const size_t img = (size_t)3 * H * W;
+            for (int b = 0; b < B && !rc; ++b) {
+                Act yb = yhat; yb.B = 1; yb.p = (uint8_t*)yhat.p + (size_t)b * h * w * yhat.ld * esz();
+                g_s(yb, io->x_hat + b * img);
+                cudaEvent_t ev = pipe_event();
+                cudaEventRecord(ev, st);
+                cudaStreamWaitEvent(hp->s_out, ev, 0);
+                cudaMemcpyAsync(hp->hx_hat + b * img, io->x_hat + b * img, img * 4, cudaMemcpyDeviceToHost, hp->s_out);
+            }
+        } else if (io->x_hat || dry) g_s(yhat, io->x_hat);
         if (mode == MLIC_MODE_FORWARD && (io->rd_sums || dry)) {
             double* partial = (double*)ws_alloc(RD_BLOCKS * sizeof(double));
             if (go() && io->rd_sums) {
@@ -949,9 +1066,14 @@ int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
 }
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {
     if (!e || !bytes) return fail("bad arguments");
+    // the dry walk costs ~1 ms of host time: remember its result per call geometry (finalize() clears the cache)
+    const std::array<int, 7> key = {mode, precision, B, H, W, e->use_tc, e->fuse};
+    auto it = e->ws_cache.find(key);
+    if (it != e->ws_cache.end()) { *bytes = it->second; return 0; }
     int r = e->run(mode, precision, B, H, W, 1.0f, nullptr, nullptr, 0, nullptr, true);
     if (r) return r;
     *bytes = e->ws_peak + 256;
+    e->ws_cache[key] = *bytes;
     return 0;
 }
 int mlic_run(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* dev,
@@ -983,6 +1105,8 @@ int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, 
     int r = mlic_workspace_bytes(e, mode, precision, B, H, W, &need);
     if (r) return r;
     if (!e->h_stream) CUDA_OK(cudaStreamCreateWithFlags(&e->h_stream, cudaStreamNonBlocking));
+    if (!e->h_in) CUDA_OK(cudaStreamCreateWithFlags(&e->h_in, cudaStreamNonBlocking));
+    if (!e->h_out) CUDA_OK(cudaStreamCreateWithFlags(&e->h_out, cudaStreamNonBlocking));
     if (need > e->h_ws_bytes) {
         if (e->h_ws) cudaFree(e->h_ws);
         e->h_ws = nullptr; e->h_ws_bytes = 0;
@@ -1007,11 +1131,18 @@ int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, 
     cudaStream_t s = e->h_stream;
     mlic_buffers dev;
     memset(&dev, 0, sizeof dev);
+    HostPipe hp;
+    hp.s_in = e->h_in; hp.s_out = e->h_out;
     if (mode != MLIC_MODE_DECODER) {
         if (!host->x) return fail("x is NULL");
-        CUDA_OK(cudaMemcpyAsync(d + o_x, host->x, n_x * 4, cudaMemcpyHostToDevice, s));
+        hp.hx = host->x;                  // uploaded inside the walk (image by image on the copy stream)
         dev.x = (const float*)(d + o_x);
     }
+    hp.hx_hat = host->x_hat;
+    if (mode == MLIC_MODE_FORWARD) { hp.hy_lik = host->y_likelihoods; hp.hz_lik = host->z_likelihoods; }
+    const char* pe = getenv("MLIC_HOST_PIPE");       // development switch: 0 = copies and walk strictly one after the other
+    const bool piped = !(pe && atoi(pe) == 0);
+    if (!piped && hp.hx) CUDA_OK(cudaMemcpyAsync(d + o_x, host->x, n_x * 4, cudaMemcpyHostToDevice, s));
     const bool want_rd = host->rd_sums && mode == MLIC_MODE_FORWARD;
     if (host->x_hat || want_rd) dev.x_hat = (float*)(d + o_xh);
     if (mode == MLIC_MODE_FORWARD) {
@@ -1025,11 +1156,14 @@ int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, 
     }
     if (host->y) dev.y = (float*)(d + o_y);
     if (host->y_hat) dev.y_hat = (float*)(d + o_yh);
-    r = e->run(mode, precision, B, H, W, gain, &dev, e->h_ws, e->h_ws_bytes, s, false);
-    if (r) { cudaStreamSynchronize(s); return r; }
-    if (host->x_hat) CUDA_OK(cudaMemcpyAsync(host->x_hat, dev.x_hat, n_x * 4, cudaMemcpyDeviceToHost, s));
-    if (host->y_likelihoods && dev.y_likelihoods) CUDA_OK(cudaMemcpyAsync(host->y_likelihoods, dev.y_likelihoods, n_y * 4, cudaMemcpyDeviceToHost, s));
-    if (host->z_likelihoods && dev.z_likelihoods) CUDA_OK(cudaMemcpyAsync(host->z_likelihoods, dev.z_likelihoods, n_z * 4, cudaMemcpyDeviceToHost, s));
+    r = e->run(mode, precision, B, H, W, gain, &dev, e->h_ws, e->h_ws_bytes, s, false, piped ? &hp : nullptr);
+    if (!r && !piped) {
+        if (host->x_hat) CUDA_OK(cudaMemcpyAsync(host->x_hat, dev.x_hat, n_x * 4, cudaMemcpyDeviceToHost, s));
+        if (host->y_likelihoods && dev.y_likelihoods) CUDA_OK(cudaMemcpyAsync(host->y_likelihoods, dev.y_likelihoods, n_y * 4, cudaMemcpyDeviceToHost, s));
+        if (host->z_likelihoods && dev.z_likelihoods) CUDA_OK(cudaMemcpyAsync(host->z_likelihoods, dev.z_likelihoods, n_z * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (r) { cudaStreamSynchronize(s); cudaStreamSynchronize(e->h_in); cudaStreamSynchronize(e->h_out); return r; }
+    // x_hat and the likelihoods were downloaded on the copy stream inside the walk; the rest follows the walk here
     if (host->symbols && dev.symbols) CUDA_OK(cudaMemcpyAsync(host->symbols, dev.symbols, n_sym * 4, cudaMemcpyDeviceToHost, s));
     if (host->indexes && dev.indexes) CUDA_OK(cudaMemcpyAsync(host->indexes, dev.indexes, n_sym * 4, cudaMemcpyDeviceToHost, s));
     if (host->z_symbols && dev.z_symbols) CUDA_OK(cudaMemcpyAsync(host->z_symbols, dev.z_symbols, n_z * 4, cudaMemcpyDeviceToHost, s));
@@ -1037,6 +1171,8 @@ int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, 
     if (host->y_hat && dev.y_hat) CUDA_OK(cudaMemcpyAsync(host->y_hat, dev.y_hat, n_y * 4, cudaMemcpyDeviceToHost, s));
     if (want_rd) CUDA_OK(cudaMemcpyAsync(host->rd_sums, dev.rd_sums, 16, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaStreamSynchronize(e->h_out));
+    CUDA_OK(cudaStreamSynchronize(e->h_in));
     return 0;
 }
 
@@ -1141,6 +1277,65 @@ int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int 
     if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (e.rc) return e.rc;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mlic_local_attn(int impl, const void* F, int B, int H, int W, const float* rel_bias, void* O, int iters, float* avg_ms,
+                    void* cuda_stream) {
+    if (!F || !rel_bias || !O || iters < 1 || impl < 0 || impl > 2) return fail("bad arguments");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    int r = 0;
+    for (int i = 0; i < iters && !r; ++i) {
+        if (i == 1) CUDA_OK(cudaEventRecord(e0, st));
+        if (impl == 2) { Act f; f.p = const_cast<void*>(F); f.B = B; f.H = H; f.W = W; f.C = 96; f.ld = 96; r = launch_local_attn_mma(f, rel_bias, O, st); }
+        else r = launch_local_attn(impl, (const float*)F, B, H, W, 32, rel_bias, O, st);
+    }
+    if (iters == 1) CUDA_OK(cudaEventRecord(e0, st));
+    CUDA_OK(cudaEventRecord(e1, st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (r) return fail("local attention: unsupported geometry");
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mlic_ga_head(const float* x, int B, int H, int W, const float* dw_weight, const float* dw_bias, const float* pw_weight,
+                 const float* pw_bias, const float* skip_weight, const float* skip_bias, int N, void* t_out, void* skip_out,
+                 int iters, float* avg_ms, void* cuda_stream) {
+    if (!x || !dw_weight || !dw_bias || !pw_weight || !pw_bias || !skip_weight || !skip_bias || !t_out || !skip_out || iters < 1)
+        return fail("bad arguments");
+    mlic_engine e;
+    e.N = e.M = e.S = e.C = 0; e.kind = 0; e.sd = e.vbr = false; e.Me = 0; e.rc = 0;
+    std::vector<float> w9(27);
+    for (int c = 0; c < 3; ++c) for (int t = 0; t < 9; ++t) w9[t * 3 + c] = dw_weight[c * 9 + t];
+    float* d_w9 = e.upload(w9);
+    float* d_db = e.upload(std::vector<float>(dw_bias, dw_bias + 3));
+    float* d_w1 = e.upload(std::vector<float>(pw_weight, pw_weight + (size_t)N * 3));
+    float* d_b1 = e.upload(std::vector<float>(pw_bias, pw_bias + N));
+    float* d_ws = e.upload(std::vector<float>(skip_weight, skip_weight + (size_t)N * 3));
+    float* d_bs = e.upload(std::vector<float>(skip_bias, skip_bias + N));
+    if (e.rc) return e.rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Act t; t.p = t_out; t.B = B; t.H = H / 2; t.W = W / 2; t.C = N; t.ld = N;
+    Act k = t; k.p = skip_out;
+    if (!ga_head_supported(H, W, N, t, k)) return fail("g_a head: unsupported geometry");
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    launch_ga_head(x, B, H, W, d_w9, d_db, d_w1, d_b1, d_ws, d_bs, N, t, k, st);
+    CUDA_OK(cudaEventRecord(e0, st));
+    for (int i = 1; i < iters; ++i) launch_ga_head(x, B, H, W, d_w9, d_db, d_w1, d_b1, d_ws, d_bs, N, t, k, st);
+    CUDA_OK(cudaEventRecord(e1, st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

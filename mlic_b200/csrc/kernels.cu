@@ -232,6 +232,101 @@ void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const floa
 }
 
 // ------------------------------------------------------------------------------------------
+// g_a stage-0 head, bf16 fast mode (ResidualBlockWithStride(3 -> N, stride 2), res_blk.py:82-93 with
+// DepthWiseConv, conv.py:46-63): straight from the fp32 NCHW image
+//     t  = GELU(pw(dw3x3_s2(x)))      [B, H/2, W/2, N] bf16 NHWC
+//     sk = skip1x1_s2(x)              [B, H/2, W/2, N] bf16 NHWC
+// One block = 64 consecutive output pixels of one output row.  The 3 x 3 x 129 input window is staged in shared
+// memory with row-contiguous (coalesced) reads, 192 threads evaluate the 3-channel depthwise conv once per pixel, then
+// thread (pixel lane, 8-column group) keeps its 2 x 8 x 3 weights in registers and writes 16 B of each output per
+// pixel: a warp store covers whole 128-byte lines.  Store-bound: 2 * N * 2 B per output pixel, no intermediate
+// tensor (the NHWC copy of x, the depthwise output) touches HBM.
+// ------------------------------------------------------------------------------------------
+constexpr int GH_PIX = 64;
+constexpr int GH_THREADS = 192;             // warps 0-2: conv1 path (GELU), warps 3-5: skip path
+__global__ void __launch_bounds__(GH_THREADS, 6) ga_head_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ dw9,
+                                                      const float* __restrict__ dwb, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, const float* __restrict__ wsk,
+                                                      const float* __restrict__ bsk, int N, bf16* __restrict__ t, int t_ld,
+                                                      bf16* __restrict__ sk, int sk_ld) {
+    __shared__ float sx[3][3][2 * GH_PIX + 2];
+    __shared__ float4 st[2][GH_PIX];         // [0]: depthwise result, [1]: the stride-2 sample of x
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int tiles_w = (Wo + GH_PIX - 1) / GH_PIX;
+    int bid = blockIdx.x;
+    const int tw = bid % tiles_w; bid /= tiles_w;
+    const int oh = bid % Ho;
+    const int b = bid / Ho;
+    const int ow0 = tw * GH_PIX;
+    for (int rc = threadIdx.x / 32; rc < 9; rc += GH_THREADS / 32) {          // one warp per (channel, row): contiguous reads
+        const int r = rc % 3, c = rc / 3;
+        const int ih = 2 * oh - 1 + r;
+        const float* row = x + (((size_t)b * 3 + c) * H + ih) * W;
+        for (int j = threadIdx.x & 31; j < 2 * GH_PIX + 1; j += 32) {
+            const int iw = 2 * ow0 - 1 + j;
+            sx[c][r][j] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? row[iw] : 0.f;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < GH_PIX * 3) {
+        const int p = threadIdx.x / 3, c = threadIdx.x % 3;
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc = fmaf(sx[c][ky][2 * p + kx], dw9[(ky * 3 + kx) * 3 + c], acc);
+        reinterpret_cast<float*>(&st[0][p])[c] = acc + dwb[c];
+        reinterpret_cast<float*>(&st[1][p])[c] = sx[c][1][2 * p + 1];
+    }
+    __syncthreads();
+    const int role = threadIdx.x / 96, tr = threadIdx.x % 96;                 // warp-uniform role
+    const int ng = N >> 3;
+    const int g = tr % ng, pl = tr / ng, npl = 96 / ng;
+    if (pl >= npl) return;
+    const int n = g * 8;
+    const float* wsrc = role ? wsk : w1;
+    const float* bsrc = role ? bsk : b1;
+    float2 wa[4][3], ba[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) wa[j][c] = make_float2(wsrc[(size_t)(n + 2 * j) * 3 + c], wsrc[(size_t)(n + 2 * j + 1) * 3 + c]);
+        ba[j] = make_float2(bsrc[n + 2 * j], bsrc[n + 2 * j + 1]);
+    }
+    bf16* dst = role ? sk : t;
+    const int dld = role ? sk_ld : t_ld;
+    for (int p = pl; p < GH_PIX; p += npl) {
+        const int ow = ow0 + p;
+        if (ow >= Wo) break;
+        const float4 a = st[role][p];
+        uint32_t o1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 u = __fmul2_rn(make_float2(a.x, a.x), wa[j][0]);
+            u = __ffma2_rn(make_float2(a.y, a.y), wa[j][1], u);
+            u = __ffma2_rn(make_float2(a.z, a.z), wa[j][2], u);
+            u = __fadd2_rn(u, ba[j]);
+            if (role == 0) u = gelu2(u);
+            __nv_bfloat162 hu = __floats2bfloat162_rn(u.x, u.y);
+            o1[j] = *reinterpret_cast<uint32_t*>(&hu);
+        }
+        const size_t pix = ((size_t)b * Ho + oh) * Wo + ow;
+        *reinterpret_cast<uint4*>(dst + pix * dld + n) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    }
+}
+bool ga_head_supported(int H, int W, int N, const Act& t, const Act& sk) {
+    return (H % 2) == 0 && (W % 2) == 0 && N >= 8 && (N % 8) == 0 && N <= 768 && (t.ld % 8) == 0 && (sk.ld % 8) == 0 &&
+           ((uintptr_t)t.p % 16) == 0 && ((uintptr_t)sk.p % 16) == 0;
+}
+void launch_ga_head(const float* x, int B, int H, int W, const float* dw9, const float* dwb, const float* w1, const float* b1,
+                    const float* wsk, const float* bsk, int N, const Act& t, const Act& sk, cudaStream_t s) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long blocks = (long long)B * Ho * ((Wo + GH_PIX - 1) / GH_PIX);
+    if (blocks == 0) return;
+    ga_head_kernel<<<(unsigned)blocks, GH_THREADS, 0, s>>>(x, H, W, dw9, dwb, w1, b1, wsk, bsk, N, (bf16*)t.p, t.ld, (bf16*)sk.p, sk.ld);
+}
+
+// ------------------------------------------------------------------------------------------
 // Depthwise 3x3 (pad 1, stride 1|2) + bias (+ GELU), NHWC.  HBM-bound: 4 channels per thread,
 // channel-fastest thread order so every warp access is one contiguous 128..512 B segment; the
 // 9-tap reuse is served by L1/L2.  (modules/layers/conv.py:49-54)
@@ -698,6 +793,224 @@ int launch_local_attn(int bf, const float* F, int B, int H, int W, int C, const 
     else return 1;
 #undef LA_LAUNCH
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LocalContext windowed attention, bf16 fast mode, on the legacy warp-level tensor path (mma.sync m16n8k16: the
+// per-pixel problem is 25 x 25 x 16, far below a tcgen05 tile).  Same definition as local_attn_kernel above, with
+//   * F bf16 [pix][3C] in HEAD-MAJOR channel order  q_h0 | q_h1 | k_h0 | k_h1 | v_h0 | v_h1  (16 each; the qkv_proj
+//     weight rows are permuted at pack time), so the staged window is directly ldmatrix-addressable;
+//   * only NON-ANCHOR pixels are evaluated: the LocalContext output feeds the per-pixel (1x1) non-anchor
+//     EntropyParameters stack whose result is multiplied by the non-anchor mask (mlicpp.py:146-150), so the anchor half
+//     of the output is never observed;
+//   * O is written SQUEEZED, [B][H][W/2][25][C] with w = 2j + (h & 1) (utils/ckbd.py:47-59 order), and the whole
+//     fusion/proj/MLP tail of LocalContext runs on that half-size matrix.
+// One warp = one pixel: per head S = Q_w K_w^T (32x32 padded, 8 MMAs), + bias + mask, row softmax through quad
+// shuffles, O = P V_w (8 MMAs).  Block = 8 x 16 pixel tile (64 non-anchor pixels, 8 per warp) with a 2-pixel halo.
+// ------------------------------------------------------------------------------------------
+constexpr int LM_TH = 8, LM_TW = 16, LM_HH = LM_TH + 4, LM_HW = LM_TW + 4;
+constexpr int LM_PITCH = 208;                        // bytes per staged position: 96 bf16 + 16 B pad (conflict-free rows)
+constexpr int LM_F_BYTES = LM_HH * LM_HW * LM_PITCH; // 49 920
+constexpr int LM_BIAS_BYTES = 2 * 32 * 32 * 4;
+constexpr int LM_OUT_BYTES = 25 * 32 * 2;            // one pixel's [25][C] block
+constexpr int LM_SMEM = LM_F_BYTES + 16 + LM_BIAS_BYTES + 8 * LM_OUT_BYTES;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t r[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t r[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __restrict__ F, int f_ld, int H, int W,
+                                                             const float* __restrict__ rel_bias, bf16* __restrict__ O) {
+    extern __shared__ __align__(16) uint8_t lm_smem[];
+    uint8_t* sF = lm_smem;
+    uint8_t* sZero = lm_smem + LM_F_BYTES;                       // 16 zero bytes: rows of the padded taps 25..31
+    float* sB = reinterpret_cast<float*>(lm_smem + LM_F_BYTES + 16);
+    uint8_t* sO = lm_smem + LM_F_BYTES + 16 + LM_BIAS_BYTES;
+    const int b = blockIdx.z, h0 = blockIdx.y * LM_TH, w0 = blockIdx.x * LM_TW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // stage the halo window: 12 chunks of 16 B per position, zeros outside the image (Unfold pads q/k/v, context.py:80-82)
+    for (int i = threadIdx.x; i < LM_HH * LM_HW * 12; i += blockDim.x) {
+        const int ch = i % 12, pp = i / 12;
+        const int hh = h0 - 2 + pp / LM_HW, ww = w0 - 2 + pp % LM_HW;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = *reinterpret_cast<const uint4*>(F + (((size_t)b * H + hh) * W + ww) * f_ld + ch * 8);
+        *reinterpret_cast<uint4*>(sF + pp * LM_PITCH + ch * 16) = v;
+    }
+    if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(sZero)[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) {
+        const int col = i & 31, row = (i >> 5) & 31, hh = i >> 10;
+        sB[i] = (col < 25) ? ((row < 25) ? rel_bias[(hh * 25 + row) * 25 + col] : 0.0f) : -30000.0f;
+    }
+    __syncthreads();
+    const uint32_t sF_s = (uint32_t)__cvta_generic_to_shared(sF), sZ_s = (uint32_t)__cvta_generic_to_shared(sZero);
+    uint8_t* myO = sO + warp * LM_OUT_BYTES;
+    const int g = lane >> 2, t = lane & 3;
+    for (int it = 0; it < 8; ++it) {
+        // non-anchor pixel `it` of this warp's tile row: row ph = warp, column pw = 2 it + ((h0 + warp + w0) & 1)
+        const int ph = warp, gh = h0 + ph;
+        const int pw = 2 * it + ((gh + w0) & 1), gw = w0 + pw;
+        if (gh >= H || gw >= W) continue;                        // warp-uniform
+        // window taps that are in-image anchors ((row + col) odd)
+        bool anch = false;
+        if (lane < 25) {
+            const int qh = gh + lane / 5 - 2, qw = gw + lane % 5 - 2;
+            anch = qh >= 0 && qh < H && qw >= 0 && qw < W && (((qh + qw) & 1) == 1);
+        }
+        const uint32_t am = __ballot_sync(0xffffffffu, anch);
+        // per-lane ldmatrix row addresses (tap -> staged position), shared by both heads
+        auto tap_addr = [&](int tap) -> uint32_t {
+            return tap < 25 ? sF_s + (uint32_t)(((ph + tap / 5) * LM_HW + (pw + tap % 5)) * LM_PITCH) : 0u;
+        };
+        uint32_t qa[2], ka[2], va[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int qrow = 16 * i + (lane & 7) + ((lane >> 3) & 1) * 8;      // A: matrices (r0-7,k0-7) (r8-15,k0-7) (r0-7,k8-15) (r8-15,k8-15)
+            uint32_t a0 = tap_addr(qrow);
+            qa[i] = a0 ? a0 + (uint32_t)((lane >> 4) * 16) : sZ_s;
+            const int krow = 16 * i + (lane & 7) + (lane >> 4) * 8;            // B: (n0-7,k0-7) (n0-7,k8-15) (n8-15,k0-7) (n8-15,k8-15)
+            a0 = tap_addr(krow);
+            ka[i] = a0 ? a0 + (uint32_t)(64 + ((lane >> 3) & 1) * 16) : sZ_s;
+            const int vrow = 16 * i + (lane & 7) + ((lane >> 3) & 1) * 8;      // B^T: (k0-7,n0-7) (k8-15,n0-7) (k0-7,n8-15) (k8-15,n8-15)
+            a0 = tap_addr(vrow);
+            va[i] = a0 ? a0 + (uint32_t)(128 + (lane >> 4) * 16) : sZ_s;
+        }
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t hoff = (uint32_t)(hh * 32);
+            uint32_t qf[2][4], kf[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                ldsm_x4(qa[i] == sZ_s ? sZ_s : qa[i] + hoff, qf[i]);
+                ldsm_x4(ka[i] == sZ_s ? sZ_s : ka[i] + hoff, kf[i]);
+            }
+            float sc[2][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sc[mt][nt][j] = 0.f;
+                    mma_bf16_16816(sc[mt][nt], qf[mt], kf[nt >> 1][(nt & 1) * 2], kf[nt >> 1][(nt & 1) * 2 + 1]);
+                }
+            // scale, + bias, + mask; row softmax (a row lives in the 4 lanes of a quad)
+            const float* bh = sB + hh * 1024;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int row = mt * 16 + half * 8 + g;
+                    const bool qan = (am >> row) & 1u;
+                    float mx = -3.0e38f;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int col = nt * 8 + 2 * t;
+                        const float2 bb = *reinterpret_cast<const float2*>(bh + row * 32 + col);
+                        float s0 = fmaf(sc[mt][nt][half * 2], 0.25f, bb.x) + ((qan && ((am >> col) & 1u)) ? 0.0f : -100.0f);
+                        float s1 = fmaf(sc[mt][nt][half * 2 + 1], 0.25f, bb.y) + ((qan && ((am >> (col + 1)) & 1u)) ? 0.0f : -100.0f);
+                        sc[mt][nt][half * 2] = s0; sc[mt][nt][half * 2 + 1] = s1;
+                        mx = fmaxf(mx, fmaxf(s0, s1));
+                    }
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    float den = 0.f;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const float e0 = __expf(sc[mt][nt][half * 2] - mx), e1 = __expf(sc[mt][nt][half * 2 + 1] - mx);
+                        sc[mt][nt][half * 2] = e0; sc[mt][nt][half * 2 + 1] = e1;
+                        den += e0 + e1;
+                    }
+                    den += __shfl_xor_sync(0xffffffffu, den, 1);
+                    den += __shfl_xor_sync(0xffffffffu, den, 2);
+                    const float inv = 1.0f / den;
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) { sc[mt][nt][half * 2] *= inv; sc[mt][nt][half * 2 + 1] *= inv; }
+                }
+            // O = P V: k blocks of 16 key taps; P accumulators re-packed as bf16 A fragments
+            uint32_t vf[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) ldsm_x4_trans(va[i] == sZ_s ? sZ_s : va[i] + hoff, vf[i]);
+            float oc[2][2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int dn = 0; dn < 2; ++dn) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) oc[mt][dn][j] = 0.f;
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        uint32_t pf[4];
+                        pf[0] = pack_bf2(sc[mt][2 * kb][0], sc[mt][2 * kb][1]);
+                        pf[1] = pack_bf2(sc[mt][2 * kb][2], sc[mt][2 * kb][3]);
+                        pf[2] = pack_bf2(sc[mt][2 * kb + 1][0], sc[mt][2 * kb + 1][1]);
+                        pf[3] = pack_bf2(sc[mt][2 * kb + 1][2], sc[mt][2 * kb + 1][3]);
+                        mma_bf16_16816(oc[mt][dn], pf, vf[kb][dn * 2], vf[kb][dn * 2 + 1]);
+                    }
+                }
+            // rows a < 25 -> staged [25][C] block, channel = hh*16 + d  (context.py:106-107)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int row = mt * 16 + half * 8 + g;
+                    if (row < 25) {
+#pragma unroll
+                        for (int dn = 0; dn < 2; ++dn)
+                            *reinterpret_cast<uint32_t*>(myO + row * 64 + (hh * 16 + dn * 8 + 2 * t) * 2) =
+                                pack_bf2(oc[mt][dn][half * 2], oc[mt][dn][half * 2 + 1]);
+                    }
+                }
+        }
+        __syncwarp();
+        bf16* op = O + ((((size_t)b * H + gh) * (W >> 1)) + (gw >> 1)) * (25 * 32);
+        for (int i = lane; i < LM_OUT_BYTES / 16; i += 32)
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(op) + i * 16) = *reinterpret_cast<const uint4*>(myO + i * 16);
+        __syncwarp();
+    }
+}
+// F: bf16 NHWC [B,H,W,>=96] (head-major q|k|v), O: bf16 [B*H*W/2][25*32]; C must be 32, W even.
+int launch_local_attn_mma(const Act& F, const float* rel_bias, void* O, cudaStream_t s) {
+    if (F.C != 96 || (F.W & 1) || (F.ld % 8) != 0 || ((uintptr_t)F.p % 16) != 0 || ((uintptr_t)O % 16) != 0) return 1;
+    if (F.B * F.H * F.W == 0) return 0;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(local_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM); attr = true; }
+    dim3 grid(cdiv(F.W, LM_TW), cdiv(F.H, LM_TH), F.B);
+    local_attn_mma_kernel<<<grid, 256, LM_SMEM, s>>>((const bf16*)F.p, F.ld, F.H, F.W, rel_bias, (bf16*)O);
+    return 0;
+}
+
+// squeezed non-anchor rows [B][H][W/2][C] -> full NHWC view (non-anchor pixels; anchor pixels are zeroed)
+__global__ void unsqueeze_nonanchor_kernel(const bf16* __restrict__ src, int sld, bf16* __restrict__ dst, int dld, int H, int W,
+                                           int C8, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        const long long pix = i / C8;
+        const int w = (int)(pix % W);
+        const long long bh = pix / W;
+        const int h = (int)(bh % H);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (((h + w) & 1) == 0) v = *reinterpret_cast<const uint4*>(src + (bh * (W >> 1) + (w >> 1)) * sld + c * 8);
+        *reinterpret_cast<uint4*>(dst + pix * dld + c * 8) = v;
+    }
+}
+void launch_unsqueeze_nonanchor(const Act& src /*[1,1,B*H*W/2,C]*/, const Act& dst /*[B,H,W,C]*/, cudaStream_t s) {
+    const long long total = (long long)dst.B * dst.H * dst.W * (dst.C / 8);
+    if (total == 0) return;
+    int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 8);
+    unsqueeze_nonanchor_kernel<<<blocks, 256, 0, s>>>((const bf16*)src.p, src.ld, (bf16*)dst.p, dst.ld, dst.H, dst.W, dst.C / 8, total);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -17,6 +17,10 @@ void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const floa
                            cudaStream_t s);
 void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act,
                       cudaStream_t s);
+// g_a stage-0 head (bf16 mode): fp32 NCHW image -> GELU(pw(dw3x3_s2 x)) and skip1x1_s2(x), both bf16 NHWC
+bool ga_head_supported(int H, int W, int N, const Act& t, const Act& sk);
+void launch_ga_head(const float* x, int B, int H, int W, const float* dw9, const float* dwb, const float* w1, const float* b1,
+                    const float* wsk, const float* bsk, int N, const Act& t, const Act& sk, cudaStream_t s);
 void launch_nchw_to_nhwc(int bf, const float* src, const Act& dst, int Csrc, cudaStream_t s);
 void launch_nhwc_to_nchw(int bf, const Act& src, float* dst, cudaStream_t s);
 void launch_nhwc_f32_to_nchw(const float* src, int ld, int B, int H, int W, int C, float* dst, cudaStream_t s);
@@ -32,6 +36,12 @@ void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const flo
 // returns non-zero for an unsupported C.
 int launch_local_attn(int bf, const float* F, int B, int H, int W, int C, const float* rel_bias /*[2][25][25]*/,
                       void* O, cudaStream_t s);
+// bf16 fast mode: the same attention on the warp-level tensor path for the NON-ANCHOR pixels only.
+//   F: bf16 NHWC [B,H,W,96], channels head-major (q_h0 q_h1 k_h0 k_h1 v_h0 v_h1); O: bf16 [B*H*(W/2)][25*32] squeezed
+//   (w = 2j + (h & 1)).  Non-zero: unsupported geometry.
+int launch_local_attn_mma(const Act& F, const float* rel_bias, void* O, cudaStream_t s);
+// squeezed non-anchor rows [B*H*(W/2)][C] -> NHWC view [B,H,W,C]; anchor pixels are written as zeros
+void launch_unsqueeze_nonanchor(const Act& src, const Act& dst, cudaStream_t s);
 void launch_layernorm(int bf, const Act& x, const float* g, const float* b, const Act& out, cudaStream_t s);
 
 // Linear (kernelised) global attention: K softmax over positions, Q softmax over head channels.

@@ -108,6 +108,7 @@ class MLICPlusPlus(nn.Module):
             lc.attn_mask, lc.H, lc.W = None, -1, -1
         self._engine = None
         self._engine_sig = None
+        self._sig_tensors = None
         self._ws = {}
         self._profile = False
         self._trace = False
@@ -141,7 +142,7 @@ class MLICPlusPlus(nn.Module):
                 if full in state_dict and full in own and own[full].shape != state_dict[full].shape:
                     own[full].resize_(state_dict[full].shape)
         out = super().load_state_dict(state_dict, strict=strict)
-        self._engine_sig = None
+        self.invalidate_engine()
         return out
 
     def update(self, scale_table=None, force=False):
@@ -154,7 +155,7 @@ class MLICPlusPlus(nn.Module):
             return False
         gc.scale_table.resize_(len(scale_table))
         gc.scale_table.copy_(torch.as_tensor(scale_table, dtype=torch.float32))
-        self._engine_sig = None
+        self.invalidate_engine()
         return True
 
     def update_resolutions(self, H, W, device=None):
@@ -199,7 +200,21 @@ class MLICPlusPlus(nn.Module):
 
     # ------------------------------------------------------------------ engine plumbing
     def _signature(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        """(data_ptr, version) of every state tensor: in-place edits, loads and device moves re-pack the engine weights.
+        The tensor list itself is cached (walking the module tree costs ~3 ms per call for MLICPP_L); it is dropped by
+        load_state_dict / update / .to() -- after replacing a Parameter OBJECT by hand, call invalidate_engine()."""
+        if self._sig_tensors is None:
+            self._sig_tensors = list(self.state_dict(keep_vars=True).values())
+        return tuple((v.data_ptr(), v._version) for v in self._sig_tensors)
+
+    def invalidate_engine(self):
+        self._sig_tensors = None
+        self._engine_sig = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_engine()
+        return out
 
     def _sync_engine(self, device):
         if not torch.cuda.is_available():

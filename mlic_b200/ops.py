@@ -91,3 +91,41 @@ def gaussian_conditional(y, scales, means, scale_table=None):
                                                         C.c_void_p(lik.data_ptr()), C.c_void_p(sym.data_ptr()),
                                                         C.c_void_p(idx.data_ptr()), C.c_void_p(st)))
     return y_hat, lik, sym, idx
+
+
+def local_attn(F, rel_bias, impl=2, iters=1):
+    """LocalContext windowed attention (context.py:80-107) on a CUDA tensor.
+    impl 0 / 1: F fp32 [B,H,W,96] in the reference's interleaved head order -> O [B,H,W,25,32] fp32 / bf16 (all pixels);
+    impl 2: F bf16 [B,H,W,96] head-major -> O bf16 [B,H,W/2,25,32] (non-anchor pixels, squeezed).  -> (O, avg ms)"""
+    assert F.is_cuda and F.is_contiguous() and F.shape[-1] == 96
+    B, H, W, _ = F.shape
+    assert F.dtype == (torch.bfloat16 if impl == 2 else torch.float32)
+    rb = rel_bias.detach().to(F.device, torch.float32).contiguous()
+    assert rb.numel() == 2 * 625
+    if impl == 2:
+        O = torch.empty((B, H, W // 2, 25, 32), dtype=torch.bfloat16, device=F.device)
+    else:
+        O = torch.empty((B, H, W, 25, 32), dtype=torch.float32 if impl == 0 else torch.bfloat16, device=F.device)
+    ms = C.c_float(0)
+    with torch.cuda.device(F.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_local_attn(impl, C.c_void_p(F.data_ptr()), B, H, W, C.c_void_p(rb.data_ptr()),
+                                              C.c_void_p(O.data_ptr()), iters, C.byref(ms), C.c_void_p(st)))
+    return O, float(ms.value)
+
+
+def ga_head(x, dw_weight, dw_bias, pw_weight, pw_bias, skip_weight, skip_bias, iters=1):
+    """g_a stage-0 head of the bf16 path: x CUDA fp32 NCHW [B,3,H,W] -> (GELU(pw(dw_s2 x)), skip_s2(x)) bf16 NHWC, avg ms."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32 and x.shape[1] == 3
+    B, _, H, W = x.shape
+    N = pw_weight.shape[0]
+    hs = [t.detach().to("cpu", torch.float32).contiguous() for t in (dw_weight, dw_bias, pw_weight, pw_bias, skip_weight, skip_bias)]
+    t_out = torch.empty((B, H // 2, W // 2, N), dtype=torch.bfloat16, device=x.device)
+    s_out = torch.empty_like(t_out)
+    ms = C.c_float(0)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_ga_head(C.c_void_p(x.data_ptr()), B, H, W, *[C.c_void_p(h.data_ptr()) for h in hs], N,
+                                           C.c_void_p(t_out.data_ptr()), C.c_void_p(s_out.data_ptr()), iters, C.byref(ms),
+                                           C.c_void_p(st)))
+    return t_out, s_out, float(ms.value)

@@ -74,3 +74,57 @@ def test_gaussian_conditional_kernel_bit_exact_indexes_and_symbols():
     # empty input is a no-op
     e = torch.empty(0, device="cuda")
     assert ops.gaussian_conditional(e, e, e)[0].numel() == 0
+
+
+def _local_attn_torch(Fq, rel_bias):
+    """Plain PyTorch fp32 statement of LocalContext's windowed attention (context.py:80-107):
+    Fq [B,H,W,96] (q|k|v, channel c = d*2 + head) -> O [B,H,W,25,32] (channel = head*16 + d)."""
+    B, H, W, _ = Fq.shape
+    Fp = F.pad(Fq.permute(0, 3, 1, 2), (2, 2, 2, 2))                                 # zeros of q/k/v outside the image
+    win = F.unfold(Fp, 5).reshape(B, 96, 25, H, W).permute(0, 3, 4, 2, 1)             # [B,H,W,25,96]
+    q, k, v = [win[..., u * 32:(u + 1) * 32].reshape(B, H, W, 25, 16, 2).permute(0, 1, 2, 5, 3, 4) for u in range(3)]  # [B,H,W,head,25,16]
+    hh, ww = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    anch = torch.zeros(H + 4, W + 4, dtype=torch.bool)
+    anch[2:-2, 2:-2] = ((hh + ww) % 2 == 1)
+    aw = anch.unfold(0, 5, 1).unfold(1, 5, 1).reshape(H, W, 25).to(Fq.device)         # tap is an in-image anchor
+    mask = torch.where(aw[:, :, :, None] & aw[:, :, None, :], 0.0, -100.0)            # [H,W,25,25]
+    A = (q * 0.25) @ k.transpose(-1, -2) + rel_bias.to(Fq.device).reshape(1, 1, 1, 2, 25, 25) + mask[None, :, :, None]
+    o = torch.softmax(A, -1) @ v                                                       # [B,H,W,head,25,16]
+    return o.permute(0, 1, 2, 4, 3, 5).reshape(B, H, W, 25, 32)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 16), (2, 13, 22), (1, 68, 120)])
+def test_local_attention_kernels(B, H, W):
+    g = torch.Generator().manual_seed(7)
+    Fq = torch.randn(B, H, W, 96, generator=g).cuda()
+    rb = (torch.randn(2, 25, 25, generator=g) * 0.5).cuda()
+    O0, _ = ops.local_attn(Fq, rb, impl=0)
+    ref = _local_attn_torch(Fq, rb)
+    np.testing.assert_allclose(O0.cpu().numpy(), ref.cpu().numpy(), atol=2e-5, rtol=0)
+    # tensor-core kernel: bf16 inputs in head-major channel order, non-anchor pixels only, squeezed
+    Fb = Fq.to(torch.bfloat16)
+    ref_b = _local_attn_torch(Fb.float(), rb)
+    Fhm = Fb.reshape(B, H, W, 3, 16, 2).permute(0, 1, 2, 3, 5, 4).reshape(B, H, W, 96).contiguous()
+    O2, _ = ops.local_attn(Fhm, rb, impl=2)
+    hh, ww = torch.meshgrid(torch.arange(H), torch.arange(W // 2), indexing="ij")
+    wfull = 2 * ww + (hh % 2)
+    want = ref_b[:, hh, wfull]                                                          # [B,H,W/2,25,32]
+    err = (O2.float() - want).abs().max().item()
+    assert err < 3e-2, err
+    assert (O2.float() - want).abs().mean().item() < 3e-3
+
+
+def test_ga_head_kernel():
+    g = torch.Generator().manual_seed(3)
+    B, H, W, N = 2, 36, 260, 192
+    x = torch.rand(B, 3, H, W, generator=g).cuda()
+    dw, db = torch.randn(3, 1, 3, 3, generator=g) / 3, torch.randn(3, generator=g) * 0.1
+    pw, pb = torch.randn(N, 3, 1, 1, generator=g), torch.randn(N, generator=g) * 0.1
+    sw, sb = torch.randn(N, 3, 1, 1, generator=g), torch.randn(N, generator=g) * 0.1
+    t, s, _ = ops.ga_head(x, dw, db, pw, pb, sw, sb)
+    d = F.conv2d(x, dw.cuda(), db.cuda(), stride=2, padding=1, groups=3)
+    t_ref = F.gelu(F.conv2d(d, pw.cuda(), pb.cuda())).permute(0, 2, 3, 1)
+    s_ref = F.conv2d(x, sw.cuda(), sb.cuda(), stride=2).permute(0, 2, 3, 1)
+    for ours, ref in ((t, t_ref), (s, s_ref)):
+        tol = 2.0 ** -8 * ref.abs() + 2e-3                  # bf16 rounding of the stored value + fast GELU
+        assert bool(((ours.float() - ref).abs() <= tol).all()), (ours.float() - ref).abs().max().item()

@@ -163,3 +163,15 @@ def test_host_buffer_call_matches_device_call():
     assert not host["x_hat"].is_cuda
     assert torch.equal(host["x_hat"], dev["x_hat"].cpu())
     assert torch.equal(host["likelihoods"]["y_likelihoods"], dev["likelihoods"]["y_likelihoods"].cpu())
+
+
+def test_host_buffer_call_bf16_pipelined_matches_device_call():
+    """bf16 fast mode through mlic_run_host: per-image upload / g_a / g_s / download pipeline vs the batched device call."""
+    g, sd, x = load_case("MLICPP_S", 2, 64, 128)
+    net = build_model("MLICPP_S", sd, "cuda").set_precision("bf16")
+    dev = net(x.cuda())
+    host = net(x.pin_memory())
+    assert not host["x_hat"].is_cuda
+    assert torch.equal(host["x_hat"], dev["x_hat"].cpu())
+    assert torch.equal(host["likelihoods"]["y_likelihoods"], dev["likelihoods"]["y_likelihoods"].cpu())
+    assert torch.equal(host["likelihoods"]["z_likelihoods"], dev["likelihoods"]["z_likelihoods"].cpu())
