@@ -185,6 +185,7 @@ struct TcMaps {
     CUtensorMap a, b;       // operands (PROD_DW: `a` is the halo-patch map, box {64, TW+2, TH+2, 1}, no swizzle)
     CUtensorMap o[4];       // output (one per pixel-shuffle group; o[0] when not shuffled)
     CUtensorMap o2;         // x^2 side output
+    CUtensorMap r, gx;      // STORE_TMA: residual / GDN-operand blocks, fetched by TMA into the staging slot (geometry of o[0])
 };
 
 constexpr int TC_A_BYTES = 128 * 128;       // 128 rows x 64 bf16
@@ -422,6 +423,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     }
     __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_full[2], acc_empty[2], bres_bar;
     __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_RAW_SLOTS];     // fused producers: TMA -> compute warps
+    __shared__ uint64_t stg_bar[4][2];                                        // epilogue operand blocks (residual / GDN x) landed
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float sBias[TC_MAX_BIAS];
 
@@ -444,6 +446,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
         const uint32_t nrel = p.store_mode == STORE_TMA ? 4u * (uint32_t)((p.BN + 63) / 64) : (uint32_t)NEPI;
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], nrel); }
         mbar_init(&bres_bar, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&stg_bar[i >> 1][i & 1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -674,36 +677,23 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                         if (gissuer) tma_store_wait_read(0);
                         asm volatile("bar.sync %0, 128;" ::"r"(cq + 1) : "memory");
                     }
+                    uint64_t* sbar = &stg_bar[cq][blk % nring];
                     if constexpr (RES || GDN != GDN_NONE) {
-                        // Operand prefetch (no pixel shuffle in this mode): the warp pulls the residual / GDN-operand block of
-                        // its 32 pixels with coalesced 16-byte loads (8 lanes = one 128-byte pixel row) straight into the
-                        // staging slot, in the swizzled layout of the output block; all loads are in flight together and
-                        // complete while the warp waits for the accumulator.  The result later overwrites the residual in place.
-                        auto stage_rows = [&](const void* src, int ld, uint32_t dst_off) {
-                            uint4 rr[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int prow = q * 32 + i * 4 + (lane >> 3);
-                                const int ph = h0 + prow / p.TW, pw = w0 + prow % p.TW;
-                                const int col = n0 + kb + (lane & 7) * 8;
-                                const bool ok = ph < e.Hout && pw < e.Wout && col + 8 <= e.N;
-                                const size_t pix = ((size_t)img * e.Hout + ph) * e.Wout + pw;
-                                rr[i] = make_uint4(0, 0, 0, 0);
-                                if (ok) rr[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(src) + pix * ld + col);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int prow = q * 32 + i * 4 + (lane >> 3);
-                                sts128(sb_s + dst_off + (uint32_t)(prow * 128 + (((lane & 7) ^ (prow & 7)) << 4)), rr[i]);
-                            }
-                        };
-                        if constexpr (RES) stage_rows(e.res, e.res_ld, 0u);
-                        if constexpr (GDN != GDN_NONE) stage_rows(e.gdn_x, e.gdn_ld, (uint32_t)TC_STG_BYTES);
-                        __syncwarp();
+                        // Operand prefetch (no pixel shuffle in this mode): the residual / GDN-operand block of this tile is one TMA
+                        // box each, landing in the staging slot in the swizzled layout of the output block (out-of-range pixels and
+                        // columns arrive as zeros); the copy is in flight while the group waits for the accumulator.  The result
+                        // later overwrites the residual in place.  The slot is free here: its last TMA store was drained by the
+                        // issuer's wait_group.read before the barrier above (one slot) / before the previous tile's store (two).
+                        if (gissuer) {
+                            mbar_expect_tx(sbar, (uint32_t)(((RES ? 1 : 0) + (GDN != GDN_NONE ? 1 : 0)) * TC_STG_BYTES));
+                            if constexpr (RES) tma_load_4d(sb, &tm.r, sbar, n0 + kb, w0, h0, img);
+                            if constexpr (GDN != GDN_NONE) tma_load_4d(sb + TC_STG_BYTES, &tm.gx, sbar, n0 + kb, w0, h0, img);
+                        }
                     }
                     if (dbg) { long long _t = clock64(); mbar_wait(&acc_full[as], (uint32_t)(it >> 1) & 1u); w3c += clock64() - _t; }
                     else mbar_wait(&acc_full[as], (uint32_t)(it >> 1) & 1u);
                     tcgen05_fence_after();
+                    if constexpr (RES || GDN != GDN_NONE) mbar_wait(sbar, (blk / nring) & 1u);
                     long long tq1 = dbg ? clock64() : 0;
 #pragma unroll 1
                     for (int pr = 0; pr < 4; ++pr) {
@@ -976,6 +966,10 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
                 if (encode_out_map(&tm.o[g], bp, Cq, e.Wout, e.Hout, c.B, 2 * ld, 2 * OW * ld, OH * OW * ld, p.TW, p.TH)) return 7;
             }
         }
+        if (e.res && encode_out_map(&tm.r, const_cast<void*>(e.res), e.N, e.Wout, e.Hout, c.B, (size_t)e.res_ld, (size_t)e.Wout * e.res_ld,
+                                    (size_t)e.Hout * e.Wout * e.res_ld, p.TW, p.TH)) return 7;
+        if (e.gdn && encode_out_map(&tm.gx, const_cast<void*>(e.gdn_x), e.N, e.Wout, e.Hout, c.B, (size_t)e.gdn_ld, (size_t)e.Wout * e.gdn_ld,
+                                    (size_t)e.Hout * e.Wout * e.gdn_ld, p.TW, p.TH)) return 7;
         if (e.out2) {
             const size_t ld2 = (size_t)e.out2_ld;
             if (encode_out_map(&tm.o2, e.out2, e.N, e.Wout, e.Hout, c.B, ld2, (size_t)e.Wout * ld2, (size_t)e.Hout * e.Wout * ld2, p.TW, p.TH)) return 7;
