@@ -114,6 +114,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// same, with an explicit stride between 8-row groups and base offset ([49,52): phase of the 128-byte swizzle pattern when the
+// start address is not 1024-byte aligned) -- used by the halo-patch A operand, whose 8-row groups are 8 consecutive pixels
+// of one patch row and whose start address moves by whole pixels (128 B) with the filter tap.
+__device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -177,6 +190,14 @@ struct TcParams {
     int Cin;                // PROD_DW: channels of the depthwise conv (= K of the GEMM)
     const float* dw_w9;     // PROD_DW: depthwise weights [9][Cin] fp32
     const float* dw_bias;   // PROD_DW: depthwise bias [Cin]
+    int halo;               // 1 (ks > 1, weights resident): the A stage of a 64-channel chunk is ONE halo patch {64, halo_w, TH+ks-1}
+                            //    and the ks*ks taps are UMMA descriptors into it (start + (ky*halo_w + kx) pixels): the input is
+                            //    read from L2 once per chunk instead of once per tap
+    int halo_w;             // staged patch width in pixels (TW + ks - 1, optionally padded to 16)
+    int halo_h;
+    int halo_bo;            // descriptor variant: set the base-offset field from the start address
+    int acc_split;          // halo + narrow N: ks*ks independent accumulators of BN columns each (taps), summed in the epilogue
+    int a_bytes;            // bytes of the A part of a ring stage (TC_A_BYTES, or the halo patch rounded up to 1024)
     int l2_prefetch;        // > 0 (1x1 convs): prefetch the A patch of the tile this many iterations ahead into L2
     int debug;              // development only: bit0 skip epilogue stores, bit1 skip TMEM loads
 };
@@ -408,7 +429,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * 128;
-    const int stage_bytes = TC_A_BYTES + (p.b_resident ? 0 : b_bytes);      // multiple of 1024
+    const int stage_bytes = p.a_bytes + (p.b_resident ? 0 : b_bytes);      // multiple of 1024
     const int ksteps_total = p.ks * p.ks * p.kchunks;
     // layout: [resident B: ksteps x b_bytes]? [ring: stages x stage_bytes] [staging]
     uint8_t* bres = base;
@@ -511,6 +532,14 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                         tma_load_4d(sa, &tm.a, &raw_full[stage], k * 64, w0, h0, img);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
+                } else if (p.halo) {
+                    for (int cc = 0; cc < p.kchunks; ++cc) {
+                        TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = base + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)(128 * p.halo_w * p.halo_h));
+                        tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 - p.pad, h0 - p.pad, img);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
                 } else {
                 for (int k = 0; k < ksteps; ++k) {
                     TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
@@ -519,7 +548,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     uint8_t* sa = base + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                     tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
-                    if (!p.b_resident) tma_load_2d(sa + TC_A_BYTES, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
+                    if (!p.b_resident) tma_load_2d(sa + p.a_bytes, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 }
@@ -538,12 +567,36 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 TIMED_WAIT(w2c, &acc_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t dcol = tmem_base + (uint32_t)(as * p.acc_stride);
+                if (p.halo) {
+                    const int taps = p.ks * p.ks;
+                    for (int cc = 0; cc < p.kchunks; ++cc) {
+                        TIMED_WAIT(w1c, &full_bar[stage], phase);
+                        tcgen05_fence_after();
+                        const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
+                        // Measured on the final 192 -> 12 conv (N = 16): an M = 128, K = 16 MMA with A in shared memory costs ~124 clocks
+                        // whatever N is (the A-operand feed, 4 KB per instruction), ~230 when consecutive MMAs switch taps; so the four
+                        // K = 16 steps of one tap are issued back to back.  Per-tap accumulators (acc_split) do not help: the chain is
+                        // not latency- but A-feed-bound.
+                        for (int tap = 0; tap < taps; ++tap) {
+                            const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                            const uint32_t a0 = sa + (uint32_t)((ky * p.halo_w + kx) * 128);
+                            const uint64_t adesc = umma_desc_sw128_ex(a0, (uint32_t)(p.halo_w * 128), p.halo_bo ? ((a0 >> 7) & 7u) : 0u);
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(bres + (size_t)(tap * p.kchunks + cc) * b_bytes));
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16(dcol + (uint32_t)(p.acc_split ? tap * p.BN : 0), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                          p.acc_split ? ((cc | kk) ? 1u : 0u) : ((cc | tap | kk) ? 1u : 0u));
+                        }
+                        tcgen05_commit(&empty_bar[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                } else
                 for (int k = 0; k < ksteps; ++k) {
                     TIMED_WAIT(w1c, &full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
                     const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(p.b_resident ? smem_u32(bres + (size_t)k * b_bytes) : sa + TC_A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(p.b_resident ? smem_u32(bres + (size_t)k * b_bytes) : sa + (uint32_t)p.a_bytes);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)      // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
                         umma_bf16(dcol, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
@@ -581,13 +634,22 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     float2 acc[8][2];
 #pragma unroll
                     for (int oy = 0; oy < 8; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
+                    // the shared-memory accessors are volatile asm (program order is kept), so the loads of input row iy + 1 are
+                    // written BEFORE the arithmetic of row iy: their latency hides behind the 18 FFMA2 of the current row
+                    uint32_t wv[2][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) wv[0][j] = lds32(rp + (uint32_t)(j * 128));
 #pragma unroll
                     for (int iy = 0; iy < 10; ++iy) {
+                        if (iy + 1 < 10) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) wv[(iy + 1) & 1][j] = lds32(rp + (uint32_t)(((iy + 1) * 18 + j) * 128));
+                        }
                         float2 x[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint32_t wv = lds32(rp + (uint32_t)((iy * 18 + j) * 128));
-                            x[j] = make_float2(__uint_as_float(wv << 16), __uint_as_float(wv & 0xffff0000u));
+                            const uint32_t wq = wv[iy & 1][j];
+                            x[j] = make_float2(__uint_as_float(wq << 16), __uint_as_float(wq & 0xffff0000u));
                         }
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
@@ -745,6 +807,19 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     uint32_t raw[16];
                     tmem_ld16(trow, raw);
                     tmem_ld_wait();
+                    if (p.acc_split) {               // sum the per-tap partial accumulators (tap order, fixed)
+#pragma unroll 1
+                        for (int tap = 1; tap < p.ks * p.ks; ++tap) {
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {         // columns 12..15 are padding: 8 + 4 would do, 8 + 8 keeps one ld shape
+                                uint32_t part[8];
+                                tmem_ld8(trow + (uint32_t)(tap * p.BN + hf * 8), part);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) raw[hf * 8 + j] = __float_as_uint(__uint_as_float(raw[hf * 8 + j]) + __uint_as_float(part[j]));
+                            }
+                        }
+                    }
                     if (valid && !(p.debug & 1)) {
                         float* o = reinterpret_cast<float*>(e.out);
                         const int OH = 2 * e.Hout, OW = 2 * e.Wout;
@@ -863,9 +938,10 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         long long t = (long long)((e.Hout + cand[i][0] - 1) / cand[i][0]) * ((e.Wout + cand[i][1] - 1) / cand[i][1]);
         if (best < 0 || t < best) { best = t; p.TH = cand[i][0]; p.TW = cand[i][1]; }
     }
+    p.ks = c.ks; p.pad = c.pad; p.Cpad = c.Cpad; p.kchunks = c.Cpad / 64;
+    p.a_bytes = TC_A_BYTES;
     p.tilesH = (e.Hout + p.TH - 1) / p.TH;
     p.tilesW = (e.Wout + p.TW - 1) / p.TW;
-    p.ks = c.ks; p.pad = c.pad; p.Cpad = c.Cpad; p.kchunks = c.Cpad / 64;
 
     auto ok16 = [](const void* q, int ld, int esz) { return q == nullptr || ((((uintptr_t)q) % 16 == 0) && ((ld * esz) % 16 == 0)); };
     const int Cq = e.shuffle ? e.N / 4 : e.N;
@@ -879,6 +955,22 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     { const char* d = getenv("MLIC_TC_DEBUG"); p.debug = d ? atoi(d) : 0; }
     if (p.debug & 4) { if (p.store_mode == STORE_TMA) p.store_mode = STORE_DIRECT; }
     p.BN = pick_bn(e.N, p.store_mode == STORE_TMA ? 64 : ((e.shuffle || e.N % 32 == 0) && e.N >= 32 ? 32 : 16));
+    // Halo-patch A operand (ks > 1, narrow N with the whole weight matrix resident): 16 x 8 output patch, one TMA box per chunk.
+    // MLIC_HALO (development): bit0 enable, bit1 base-offset descriptor variant, bit2 pad the staged patch width to 16 pixels.
+    int halo_mode = 1;
+    { const char* hv = getenv("MLIC_HALO"); if (hv) halo_mode = atoi(hv); }
+    {
+        const long long bres_guess = (long long)c.ks * c.ks * p.kchunks * p.BN * 128;
+        if ((halo_mode & 1) && c.prod == PROD_TMA && c.ks > 1 && p.BN >= e.N && bres_guess <= 120 * 1024) {
+            p.halo = 1; p.TH = 16; p.TW = 8;
+            p.halo_w = (halo_mode & 4) ? 16 : p.TW + c.ks - 1;
+            p.halo_h = p.TH + c.ks - 1;
+            p.halo_bo = (halo_mode & 2) ? 1 : 0;
+            p.a_bytes = (128 * p.halo_w * p.halo_h + 1023) / 1024 * 1024;
+            p.tilesH = (e.Hout + p.TH - 1) / p.TH;
+            p.tilesW = (e.Wout + p.TW - 1) / p.TW;
+        }
+    }
     const int budget0 = 212 * 1024;     // dynamic shared memory (static: bias + barriers ~ 9.5 KB)
     p.Cin = c.Cin; p.dw_w9 = c.dw_w9; p.dw_bias = c.dw_bias;
     p.raw_bytes = c.prod == PROD_DW ? 128 * (p.TW + 2) * (p.TH + 2) : 0;
@@ -889,11 +981,12 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     const int nact = (p.BN + 63) / 64;          // warp groups that own a 64-column block
     // Shared-memory plan.  Small weight matrices (the 192x192 pointwise / GDN GEMMs) may stay resident (no per-tile B
     // reload); every active warp group owns `ring` staging slots of `per` 16 KB buffers; the rest is the operand ring.
-    const bool want_bres = p.BN >= e.N && bres_bytes <= 80 * 1024 && ksteps <= 4 && (!(p.debug & 8) || c.prod != PROD_TMA);
+    if (p.halo && !(p.BN >= e.N && bres_bytes <= 120 * 1024)) { snprintf(g_tc_err, sizeof g_tc_err, "halo plan: weights not resident (BN=%d)", p.BN); return 8; }
+    const bool want_bres = p.halo || (p.BN >= e.N && bres_bytes <= 80 * 1024 && ksteps <= 4 && (!(p.debug & 8) || c.prod != PROD_TMA));
     int stage_bytes = 0;
     bool planned = false;
-    for (int bres = want_bres ? 1 : 0; bres >= (c.prod != PROD_TMA ? 1 : 0) && !planned; --bres) {
-        stage_bytes = TC_A_BYTES + (bres ? 0 : p.BN * 128);
+    for (int bres = want_bres ? 1 : 0; bres >= ((c.prod != PROD_TMA || p.halo) ? 1 : 0) && !planned; --bres) {
+        stage_bytes = p.a_bytes + (bres ? 0 : p.BN * 128);
         const int budget = budget0 - 1024 - (bres ? bres_bytes : 0) - extra_bytes;
         for (int ring = (p.store_mode == STORE_TMA ? 2 : 0); ring >= 0 && !planned; --ring) {
             if (p.store_mode == STORE_TMA && ring == 0) break;
@@ -910,8 +1003,10 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     if (!planned) { snprintf(g_tc_err, sizeof g_tc_err, "no shared-memory plan for BN=%d ksteps=%d", p.BN, ksteps); return 8; }
     p.l2_prefetch = (p.ks == 1 && c.prod != PROD_SQ && !(p.debug & 16)) ? (c.prod == PROD_DW ? 2 : 3) : 0;
     if (c.prod != PROD_TMA && p.store_mode == STORE_DIRECT) p.epi_vec = p.epi_vec && p.ld_vec;
+    // (development, MLIC_HALO bit3; measured slower than the single accumulator: 420 us vs 195 us on the final 192 -> 12 conv)
+    p.acc_split = ((halo_mode & 8) && p.halo && p.store_mode == STORE_NCHW3 && p.BN == 16 && p.ks * p.ks * p.BN <= 256) ? 1 : 0;
     p.acc_stride = 32;
-    while (p.acc_stride < p.BN) p.acc_stride <<= 1;
+    while (p.acc_stride < p.BN * (p.acc_split ? p.ks * p.ks : 1)) p.acc_stride <<= 1;
     p.tilesN = (e.N + p.BN - 1) / p.BN;
     p.ntiles = c.B * p.tilesH * p.tilesW * p.tilesN;
     p.ld_vec = (ok16(e.res, e.res_ld, 2) && ok16(e.gdn_x, e.gdn_ld, 2) && (e.N % 8 == 0) && (!e.shuffle || (Cq % 32) == 0)) ? 1 : 0;
@@ -929,6 +1024,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         cuuint64_t strides[3] = {(cuuint64_t)c.sW * 2, (cuuint64_t)c.sH * 2, (cuuint64_t)c.sB * 2};
         const bool halo = c.prod == PROD_DW;
         cuuint32_t box[4] = {64, (cuuint32_t)(p.TW + (halo ? 2 : 0)), (cuuint32_t)(p.TH + (halo ? 2 : 0)), 1};
+        if (p.halo) { box[1] = (cuuint32_t)p.halo_w; box[2] = (cuuint32_t)p.halo_h; }
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = g_encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(c.in), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, halo ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,

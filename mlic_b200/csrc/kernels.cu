@@ -7,6 +7,7 @@
 // modules/transform/context.py:67-112,169-193,226-245, utils/ckbd.py:35-73,123-144, and the
 // CompressAI 1.2.6 GaussianConditional / EntropyBottleneck behaviour restated in SURVEY.md A.7/A.8.
 #include "kernels.h"
+#include <stdlib.h>
 
 #include <math.h>
 #include <algorithm>
@@ -460,8 +461,99 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tiled_kernel(const bf16* __r
     }
 }
 
+// bf16 fast path, second generation (same scheme as the fused depthwise producer of gemm_tc.cu): lane = channel pair
+// (one bf16x2 word), so every shared-memory access of a warp is one conflict-free 128-byte pixel row and every global
+// store of a warp is one full 128-byte line; warp pw owns output columns 2pw, 2pw+1 of the tile and walks the input rows
+// once, feeding packed fp32x2 FMAs against the 9 taps held in 18 registers.  ~64 registers: 4+ blocks per SM.
+template <int S>
+struct DwLane { static constexpr int TH = S == 1 ? 8 : 4, TW = 16, IH = TH * S + 2, IW = TW * S + 2, NX = 2 * S + 2 - (S - 1); };   // NX: 4 | 5
+
+template <int S>
+__global__ void __launch_bounds__(256, 3) dwconv3x3_lane2_kernel(const bf16* __restrict__ in, int H, int W, int C, int ild,
+                                                              bf16* __restrict__ out, int Ho, int Wo, int old,
+                                                              const float* __restrict__ w9, const float* __restrict__ bias,
+                                                              int act, int tilesW) {
+    using TT = DwLane<S>;
+    __shared__ __align__(16) uint32_t sIn[TT::IH * TT::IW * 32];
+    const int cb = blockIdx.y * 64;
+    const int b = blockIdx.z;
+    const int th = blockIdx.x / tilesW, tw = blockIdx.x - th * tilesW;
+    const int oh0 = th * TT::TH, ow0 = tw * TT::TW;
+    const int ih0 = oh0 * S - 1, iw0 = ow0 * S - 1;
+    {
+        const int cg = threadIdx.x & 7;
+        const bool cok = cb + cg * 8 < C;                  // C % 8 == 0 (host-checked)
+        for (int i = threadIdx.x >> 3; i < TT::IH * TT::IW; i += 32) {
+            const int py = i / TT::IW, px = i - py * TT::IW;
+            const int ih = ih0 + py, iw = iw0 + px;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (cok && ih >= 0 && ih < H && iw >= 0 && iw < W)
+                v = *reinterpret_cast<const uint4*>(in + (((size_t)b * H + ih) * W + iw) * ild + cb + cg * 8);
+            *reinterpret_cast<uint4*>(sIn + (size_t)i * 32 + cg * 4) = v;
+        }
+    }
+    const int pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = cb + 2 * lane;
+    const bool cok = c < C;
+    float2 w2[9], b2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w2[t] = cok ? make_float2(w9[t * C + c], w9[t * C + c + 1]) : make_float2(0.f, 0.f);
+    if (cok) b2 = make_float2(bias[c], bias[c + 1]);
+    __syncthreads();
+    float2 acc[TT::TH][2];
+#pragma unroll
+    for (int oy = 0; oy < TT::TH; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
+    const uint32_t* rp = sIn + (size_t)(2 * pw * S) * 32 + lane;
+#pragma unroll
+    for (int iy = 0; iy < TT::IH; ++iy) {
+        float2 x[TT::NX];
+#pragma unroll
+        for (int j = 0; j < TT::NX; ++j) x[j] = bf2_to_f2(rp[(size_t)(iy * TT::IW + j) * 32]);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            if ((iy - ky) >= 0 && ((iy - ky) % S) == 0 && (iy - ky) / S < TT::TH) {
+                const int oy = (iy - ky) / S;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) acc[oy][cc] = __ffma2_rn(x[cc * S + kx], w2[ky * 3 + kx], acc[oy][cc]);
+            }
+        }
+        if (iy >= 2 && ((iy - 2) % S) == 0) {
+            const int oy = (iy - 2) / S;
+            const int oh = oh0 + oy;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ow = ow0 + 2 * pw + cc;
+                float2 v = acc[oy][cc];
+                if (act == ACT_GELU) v = gelu2(v);
+                if (cok && oh < Ho && ow < Wo) {
+                    __nv_bfloat162 hv = __floats2bfloat162_rn(v.x, v.y);
+                    *reinterpret_cast<uint32_t*>(out + (((size_t)b * Ho + oh) * Wo + ow) * old + c) = *reinterpret_cast<uint32_t*>(&hv);
+                }
+            }
+        }
+    }
+}
+
 void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act,
                       cudaStream_t s) {
+    static const bool old_dw = getenv("MLIC_OLD_DW") != nullptr;      // development: previous tiled kernel
+    if (!old_dw && bf && (in.C % 8 == 0) && (in.ld % 8 == 0) && (out.ld % 2 == 0) && (((uintptr_t)in.p) % 16 == 0) &&
+        (((uintptr_t)out.p) % 4 == 0) && (stride == 1 || stride == 2) && out.B > 0 && out.H > 0 && out.W > 0) {
+        if (stride == 1) {
+            const int tw = cdiv(out.W, DwLane<1>::TW), th = cdiv(out.H, DwLane<1>::TH);
+            dim3 grid(tw * th, cdiv(in.C, 64), out.B);
+            dwconv3x3_lane2_kernel<1><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+                                                           out.ld, w9, bias, act, tw);
+        } else {
+            const int tw = cdiv(out.W, DwLane<2>::TW), th = cdiv(out.H, DwLane<2>::TH);
+            dim3 grid(tw * th, cdiv(in.C, 64), out.B);
+            dwconv3x3_lane2_kernel<2><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+                                                           out.ld, w9, bias, act, tw);
+        }
+        return;
+    }
     if (bf && (in.C % 8 == 0) && (in.ld % 8 == 0) && (out.ld % 8 == 0) && (((uintptr_t)in.p) % 16 == 0) &&
         (((uintptr_t)out.p) % 16 == 0) && (stride == 1 || stride == 2) && out.B > 0 && out.H > 0 && out.W > 0) {
         if (stride == 1) {
@@ -1024,6 +1116,8 @@ void launch_unsqueeze_nonanchor(const Act& src /*[1,1,B*H*W/2,C]*/, const Act& d
 //   3. reduce chunks (fixed order), normalise, apply to softmax_c(Q)
 // ------------------------------------------------------------------------------------------
 constexpr int LA_CH = 64;   // max chunks
+// Position chunks per (image, head).  The count depends on the image size only, so the (fixed-order) reduction of the chunk
+// partials is identical whatever the batch size: results are batch-invariant bit for bit.
 static inline int lin_chunks(int HW) { int n = (HW + 255) / 256; return n < 1 ? 1 : (n > LA_CH ? LA_CH : n); }
 
 size_t lin_attn_scratch_floats(int B, int heads, int hd, int HW) {
@@ -1135,15 +1229,26 @@ __global__ void __launch_bounds__(256) lin_ctx_kernel(const T* __restrict__ qkv,
 
 template <int HD>
 __global__ void lin_ctx_reduce_kernel(const float* __restrict__ pctx, int nch, float* __restrict__ ctx) {
-    // block = (head, b); ctx[b][g][c1][c2] = sum_ch pctx / sum_ch S[c1]
+    // block = (head, b, quarter of the hd*hd entries); ctx[b][g][c1][c2] = sum_ch pctx / sum_ch S[c1].  The chunk loop is
+    // unrolled by 8 with a fixed pairwise order: 8 loads in flight instead of a latency-bound chain, same result every run.
     const size_t bg = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
     const float* src = pctx + bg * nch * (HD * HD + HD);
-    for (int idx = threadIdx.x; idx < HD * HD; idx += blockDim.x) {
-        int c1 = idx / HD;
+    constexpr int ST = HD * HD + HD;
+    const int per = (HD * HD + gridDim.z - 1) / gridDim.z;
+    const int i0 = blockIdx.z * per, i1 = min(HD * HD, i0 + per);
+    for (int idx = i0 + threadIdx.x; idx < i1; idx += blockDim.x) {
+        const int c1 = idx / HD;
         float a = 0.f, sden = 0.f;
-        for (int k = 0; k < nch; ++k) {
-            a += src[(size_t)k * (HD * HD + HD) + idx];
-            sden += src[(size_t)k * (HD * HD + HD) + HD * HD + c1];
+        for (int k0 = 0; k0 < nch; k0 += 8) {
+            float t[8], u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = k0 + j < nch;
+                t[j] = ok ? src[(size_t)(k0 + j) * ST + idx] : 0.f;
+                u[j] = ok ? src[(size_t)(k0 + j) * ST + HD * HD + c1] : 0.f;
+            }
+            a += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+            sden += ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
         }
         ctx[bg * HD * HD + idx] = a / sden;
     }
@@ -1210,7 +1315,7 @@ int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv
         lin_colmax_kernel<T><<<dim3(nch, (D + 31) / 32, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax); \
         lin_ctx_kernel<T, HD><<<dim3(nch, heads, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv,   \
                                                                   pmax, pctx);                                     \
-        lin_ctx_reduce_kernel<HD><<<dim3(heads, B), 256, 0, s>>>(pctx, nch, ctx);                                  \
+        lin_ctx_reduce_kernel<HD><<<dim3(heads, B, 4), 256, 0, s>>>(pctx, nch, ctx);                                  \
         lin_out_kernel<T, HD><<<dim3(cdiv(HW, 128), heads, B), 128, 0, s>>>((const T*)qkv.p, qkv.ld, H, W, par_q,  \
                                                                             ctx, (T*)out.p, out.ld);               \
     } while (0)

@@ -128,3 +128,22 @@ def test_ga_head_kernel():
     for ours, ref in ((t, t_ref), (s, s_ref)):
         tol = 2.0 ** -8 * ref.abs() + 2e-3                  # bf16 rounding of the stored value + fast GELU
         assert bool(((ours.float() - ref).abs() <= tol).all()), (ours.float() - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W,C,stride,act", [(1, 20, 36, 192, 1, None), (2, 17, 30, 352, 1, "gelu"), (1, 37, 53, 104, 2, None),
+                                                (1, 24, 40, 192, 2, None), (1, 9, 7, 8, 1, None)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_depthwise_kernels(B, H, W, C, stride, act, dtype):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, H, W, C, generator=g).cuda().to(dtype)
+    w, b = torch.randn(C, 1, 3, 3, generator=g) * 0.3, torch.randn(C, generator=g) * 0.1
+    out, _ = ops.dwconv3x3_nhwc(x, w, b, stride, act)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.cuda(), b.cuda(), stride=stride, padding=1, groups=C)
+    if act == "gelu":
+        ref = F.gelu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-5, rtol=1e-5)
+    else:
+        tol = 2.0 ** -8 * ref.abs() + 2e-3
+        assert bool(((out.float() - ref).abs() <= tol).all()), (out.float() - ref).abs().max().item()
