@@ -112,6 +112,13 @@ int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int 
                      const float* dw_bias, const float* pw_weight, const float* pw_bias, int N, int stride, int act,
                      const void* residual, void* out, int iters, float* avg_ms, void* cuda_stream);
 
+/* Stand-alone final synthesis layer (subpel_conv3x3(C, 3, 2) of g_s, modules/transform/synthesis.py:67 with CompressAI's
+ * subpel_conv3x3 = Conv2d(C, 12, 3, pad 1) + PixelShuffle(2)) of the bf16 path: in DEVICE bf16 NHWC [B,H,W,Cin], weight HOST
+ * [12][Cin][3][3], bias HOST [12], out DEVICE fp32 NCHW [B,3,2H,2W].  impl 0: implicit-GEMM conv (halo-patch A operand);
+ * impl 1: shift-sum form (one 1x1 GEMM with 9*12 columns, the taps summed in the epilogue).  Timing as mlic_conv2d_nhwc. */
+int mlic_final_subpel(int impl, const void* in, int B, int H, int W, int Cin, const float* weight, const float* bias, float* out,
+                      int iters, float* avg_ms, void* cuda_stream);
+
 /* Stand-alone LocalContext windowed attention (modules/transform/context.py:80-107; 5x5 window, 2 heads of 16, C = 32).
  * rel_bias: DEVICE fp32 [2][25][25] (relative_position_table gathered through relative_position_index).
  *   impl 0: fp32 CUDA-core kernel.  F: DEVICE fp32 [B*H*W][96], channels q|k|v with the reference's interleaved head

@@ -320,6 +320,21 @@ struct mlic_engine {
             pack_rb(p + std::to_string(i + 1), false);
         }
         pack_conv(p + "7.0", 1);
+        {   // shift-sum form of the final subpel conv (gemm_tc.cu STORE_SS): row tap*12 + n' <- w[o][c][tap], n' = (o & 3)*3 + (o >> 2)
+            const HostT* w = get(p + "7.0.weight");
+            const HostT* b = get(p + "7.0.bias");
+            if (w && b && w->shape.size() == 4 && w->dim(0) == 12 && w->dim(2) == 3 && w->dim(3) == 3) {
+                const int Ci = (int)w->dim(1);
+                std::vector<float> ws((size_t)108 * Ci), bs(108, 0.f);
+                for (int o = 0; o < 12; ++o) {
+                    const int n = (o & 3) * 3 + (o >> 2);
+                    for (int c = 0; c < Ci; ++c)
+                        for (int t = 0; t < 9; ++t) ws[(size_t)(t * 12 + n) * Ci + c] = w->v[((size_t)o * Ci + c) * 9 + t];
+                    bs[n] = b->v[o];
+                }
+                pack_conv_raw(p + "7.0_ss", ws.data(), bs.data(), 108, Ci, 1, 0);
+            }
+        }
         p = "h_s.increase.";
         pack_ds(p + "0"); pack_conv(p + "2.0", 1); pack_ds(p + "4"); pack_conv(p + "6.0", 1); pack_ds(p + "8");
         // entropy model
@@ -540,6 +555,38 @@ struct mlic_engine {
         after_launch(key.c_str());
         return true;
     }
+    // final 3x3 subpel conv in shift-sum form (tcgen05 kernel, STORE_SS); false: not taken, nothing launched
+    bool gemm_ss(const Act& in, const std::string& key, float* xhat_nchw) {
+        const ConvW* w = cw(key);
+        if (!w || w->N != 108 || in.C != w->Cin) return false;
+        Epi e;
+        memset(&e, 0, sizeof e);
+        e.bias = w->bias; e.N = 108; e.shuffle = 1; e.Hout = in.H; e.Wout = in.W;
+        e.out = xhat_nchw; e.out_f32 = 1; e.nchw = 1;
+        TcConv t;
+        memset(&t, 0, sizeof t);
+        t.ss = 1; t.in = in.p; t.B = in.B; t.H = in.H; t.W = in.W; t.Cin = in.C; t.ld = in.ld; t.ks = 1; t.pad = 0; t.w = w->wbf; t.Cpad = w->Cpad;
+        t.sW = in.ld; t.sH = in.W * in.ld; t.sB = in.H * in.W * in.ld;
+        if (!tc_conv_supported(t, e)) return false;
+        if (!go()) return true;
+        if (!xhat_nchw) { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return true; }
+        cudaEvent_t ev1 = nullptr;
+        if (profile) {
+            cudaEventRecord(next_event(), st);
+            ev1 = next_event();
+            ev_flops.push_back(2.0 * (double)in.B * in.H * in.W * 108.0 * (double)w->Cin);
+        }
+        int r = launch_conv_gemm_tc(t, e, 0, st);
+        if (ev1) cudaEventRecord(ev1, st);
+        if (r) { if (!rc) rc = fail("tcgen05 conv '%s': %s", key.c_str(), tc_last_error()); return true; }
+        ++launches;
+        if (trace) {
+            char lab[256];
+            snprintf(lab, sizeof lab, "%s [tc shift-sum M=%d N=108 K=1x%d]", key.c_str(), in.B * in.H * in.W, w->Cin);
+            tr(lab);
+        }
+        return true;
+    }
     void dwconv(const Act& in, const std::string& key, int stride, int actv, const Act& out) {
         const DwW* d = dw(key);
         if (!d) return;
@@ -717,7 +764,8 @@ struct mlic_engine {
             cur = b;
         }
         EpiOpt o; o.out_f32 = xhat_nchw; o.nchw = 1;
-        gemm(cur, p + "7.0", 1, 1, nullptr, o);
+        if (!(bf && use_tc && fuse && convs.count(p + "7.0_ss") && gemm_ss(cur, p + "7.0_ss", xhat_nchw)))
+            gemm(cur, p + "7.0", 1, 1, nullptr, o);
         ws_off = mark;
     }
 
@@ -1270,6 +1318,46 @@ int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int 
     e.dsconv(a, "d", stride, &o, eo);
     CUDA_OK(cudaEventRecord(e0, e.st));
     for (int i = 1; i < iters; ++i) e.dsconv(a, "d", stride, &o, eo);
+    CUDA_OK(cudaEventRecord(e1, e.st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e.rc) return e.rc;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mlic_final_subpel(int impl, const void* in, int B, int H, int W, int Cin, const float* weight, const float* bias, float* out,
+                      int iters, float* avg_ms, void* cuda_stream) {
+    if (!in || !weight || !bias || !out || iters < 1 || impl < 0 || impl > 1) return fail("bad arguments");
+    mlic_engine e;
+    e.N = e.M = e.S = e.C = 0; e.kind = 0; e.sd = e.vbr = false; e.Me = 0; e.rc = 0;
+    e.pack_conv_raw("w", weight, bias, 12, Cin, 3, 1);
+    {
+        std::vector<float> ws((size_t)108 * Cin), bs(108, 0.f);
+        for (int o = 0; o < 12; ++o) {
+            const int n = (o & 3) * 3 + (o >> 2);
+            for (int c = 0; c < Cin; ++c)
+                for (int t = 0; t < 9; ++t) ws[(size_t)(t * 12 + n) * Cin + c] = weight[((size_t)o * Cin + c) * 9 + t];
+            bs[n] = bias[o];
+        }
+        e.pack_conv_raw("w_ss", ws.data(), bs.data(), 108, Cin, 1, 0);
+    }
+    if (e.rc) return e.rc;
+    e.bf = 1; e.use_tc = 1; e.dry = false; e.st = (cudaStream_t)cuda_stream;
+    if (tc_init()) return fail("%s", tc_last_error());
+    Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin;
+    EpiOpt o; o.out_f32 = out; o.nchw = 1;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    for (int i = 0; i < iters; ++i) {
+        if (i == 1) CUDA_OK(cudaEventRecord(e0, e.st));
+        if (impl == 1) { if (!e.gemm_ss(a, "w_ss", out)) return fail("shift-sum conv: unsupported geometry"); }
+        else e.gemm(a, "w", 1, 1, nullptr, o);
+    }
+    if (iters == 1) CUDA_OK(cudaEventRecord(e0, e.st));
     CUDA_OK(cudaEventRecord(e1, e.st));
     CUDA_OK(cudaEventSynchronize(e1));
     float ms = 0;

@@ -167,7 +167,7 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-enum { STORE_DIRECT = 0, STORE_TMA = 1, STORE_NCHW3 = 2 };
+enum { STORE_DIRECT = 0, STORE_TMA = 1, STORE_NCHW3 = 2, STORE_SS = 3 };
 
 struct TcParams {
     int tilesH, tilesW;     // output patches per image
@@ -190,6 +190,7 @@ struct TcParams {
     int Cin;                // PROD_DW: channels of the depthwise conv (= K of the GEMM)
     const float* dw_w9;     // PROD_DW: depthwise weights [9][Cin] fp32
     const float* dw_bias;   // PROD_DW: depthwise bias [Cin]
+    int tsh, tsw, torg;     // tile origin of tile (th, tw) = (th * tsh + torg, tw * tsw + torg); TH / TW / 0 except in shift-sum mode
     int halo;               // 1 (ks > 1, weights resident): the A stage of a 64-channel chunk is ONE halo patch {64, halo_w, TH+ks-1}
                             //    and the ks*ks taps are UMMA descriptors into it (start + (ky*halo_w + kx) pixels): the input is
                             //    read from L2 once per chunk instead of once per tap
@@ -501,7 +502,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 const int img = mt / tiles_per_img;
                 const int trem = mt - img * tiles_per_img;
                 const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
-                const int h0 = th * p.TH, w0 = tw * p.TW, n0 = nt * p.BN;
+                const int h0 = th * p.tsh + p.torg, w0 = tw * p.tsw + p.torg, n0 = nt * p.BN;
                 if (p.l2_prefetch && nt == 0) {
                     // HBM-bound pointwise layers: the shared-memory ring holds < 100 KB per SM, not enough bytes in flight
                     // to cover the DRAM latency; pull the A patch of a tile several iterations ahead into L2
@@ -510,7 +511,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                         const int mp = tp / p.tilesN;
                         const int ip = mp / tiles_per_img;
                         const int rp = mp - ip * tiles_per_img;
-                        const int hp = (rp / p.tilesW) * p.TH, wp = (rp % p.tilesW) * p.TW;
+                        const int hp = (rp / p.tilesW) * p.tsh + p.torg, wp = (rp % p.tilesW) * p.tsw + p.torg;
                         const int ho = PROD == PROD_DW ? 1 : 0;      // the halo box starts one pixel up / left
                         for (int cc = 0; cc < p.kchunks; ++cc) tma_prefetch_4d(&tm.a, cc * 64, wp - ho, hp - ho, ip);
                     }
@@ -709,7 +710,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
             const int img = mt / tiles_per_img;
             const int trem = mt - img * tiles_per_img;
             const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
-            const int h0 = th * p.TH, w0 = tw * p.TW;
+            const int h0 = th * p.tsh + p.torg, w0 = tw * p.tsw + p.torg;
             const int h = h0 + r / p.TW, w = w0 + r % p.TW;
             const int n0 = nt * p.BN;
             const bool valid = h < e.Hout && w < e.Wout;
@@ -800,6 +801,55 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     if (dbg) { long long tq3 = clock64(); w0c += tq1 - tq0; w1c += tq2 - tq1; w2c += tq3 - tq2; }
                     ++blk;
                 }
+            } else if (p.store_mode == STORE_SS) {
+                // Shift-sum 3x3 subpel conv with 12 GEMM columns per tap (the final 192 -> 3x2x2 layer).  The accumulator holds the
+                // per-tap partial products of the 16 x 8 PATCH pixels (lane = patch pixel, column = tap*12 + n); the output of an
+                // interior pixel p is sum_tap P[p + off(tap)][tap].  Phase 1: TMEM -> shared memory (fp32, odd row pitch);
+                // phase 2: the 14 x 6 interior pixels x 12 outputs are summed over the 9 taps and written as fp32 NCHW with the
+                // pixel shuffle, 12 consecutive floats of one output row per 12 consecutive threads.
+                constexpr int SSP = 109;
+                float* P = reinterpret_cast<float*>(stg) + (size_t)(it & 1) * (128 * SSP);
+                {
+                    float* prow = P + (size_t)r * SSP + cq * 28;
+                    const uint32_t tc0 = trow + (uint32_t)(cq * 28);
+                    uint32_t v0[16], v1[8], v2[8];
+                    tmem_ld16(tc0, v0);
+                    tmem_ld8(tc0 + 16u, v1);
+                    tmem_ld8(tc0 + 20u, v2);          // columns 20..27 (overlaps 20..23 of v1: one ld shape less)
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) prow[j] = __uint_as_float(v0[j]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) prow[16 + j] = __uint_as_float(v1[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (cq * 28 + 20 + j < 108) prow[20 + j] = __uint_as_float(v2[j]);
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+                asm volatile("bar.sync 9, %0;" ::"r"(NEPI * 32) : "memory");
+                if (!(p.debug & 1)) {
+                    float* o = reinterpret_cast<float*>(e.out);
+                    const int OH = 2 * e.Hout, OW = 2 * e.Wout;
+                    for (int idx = (warp - EW0) * 32 + lane; idx < 84 * 12; idx += NEPI * 32) {
+                        const int j = idx % 12, rest = idx / 12;
+                        const int py = 1 + rest % 14, cr = rest / 14;
+                        const int rr = cr & 1, ch = cr >> 1;
+                        const int px = 1 + (j >> 1), ss = j & 1;
+                        const int n = (2 * rr + ss) * 3 + ch;
+                        const int gh = h0 + py, gw = w0 + px;
+                        if (gh < e.Hout && gw < e.Wout) {
+                            float acc = sBias[n];
+                            const float* pp = P + (size_t)((py - 1) * 8 + (px - 1)) * SSP + n;
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx) acc += pp[(ky * 8 + kx) * SSP + (ky * 3 + kx) * 12];
+                            o[(((size_t)img * 3 + ch) * OH + 2 * gh + rr) * OW + 2 * gw + ss] = acc;
+                        }
+                    }
+                }
+                continue;          // (accumulator already released)
             } else if (p.store_mode == STORE_NCHW3) {
                 // final subpel conv (N = 12 -> 3 channels): column (2r+s)*3 + ch -> out[b][ch][2h+r][2w+s], fp32 NCHW;
                 // consecutive lanes hold consecutive w, so every float2 store instruction writes whole 128-byte lines.
@@ -898,6 +948,8 @@ bool tc_conv_supported(const TcConv& c, const Epi& e) {
     if (c.Cin < 8 || c.Cpad % 64 != 0) return false;
     if (e.N < 8 || e.N > TC_MAX_N) return false;
     if (c.H <= 0 || c.W <= 0 || c.B <= 0) return false;
+    if (c.ss) return c.prod == PROD_TMA && c.ks == 1 && c.pad == 0 && e.N == 108 && e.nchw && e.shuffle && e.out_f32 && !e.res && !e.gdn &&
+                     e.act == ACT_NONE && !e.premask && !e.postmask && c.Cpad <= 256;
     if (e.nchw && !(e.shuffle && e.N == 12 && e.out_f32)) return false;
     if (c.prod != PROD_TMA) {
         // fused producers: 1x1 GEMM over a dense-stride-1 view, whole weight matrix resident, <= 3 column groups
@@ -940,14 +992,17 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     }
     p.ks = c.ks; p.pad = c.pad; p.Cpad = c.Cpad; p.kchunks = c.Cpad / 64;
     p.a_bytes = TC_A_BYTES;
-    p.tilesH = (e.Hout + p.TH - 1) / p.TH;
-    p.tilesW = (e.Wout + p.TW - 1) / p.TW;
+    if (c.ss) { p.TH = 16; p.TW = 8; }                 // shift-sum mode: 16 x 8 patches stepping by 14 x 6, origin -1
+    p.tsh = c.ss ? p.TH - 2 : p.TH; p.tsw = c.ss ? p.TW - 2 : p.TW; p.torg = c.ss ? -1 : 0;
+    p.tilesH = (e.Hout + p.tsh - 1) / p.tsh;
+    p.tilesW = (e.Wout + p.tsw - 1) / p.tsw;
 
     auto ok16 = [](const void* q, int ld, int esz) { return q == nullptr || ((((uintptr_t)q) % 16 == 0) && ((ld * esz) % 16 == 0)); };
     const int Cq = e.shuffle ? e.N / 4 : e.N;
     // store mode
     p.store_mode = STORE_DIRECT;
-    if (e.nchw) p.store_mode = STORE_NCHW3;
+    if (c.ss) p.store_mode = STORE_SS;
+    else if (e.nchw) p.store_mode = STORE_NCHW3;
     else if (!e.out_f32 && e.out && ok16(e.out, e.out_ld, 2) && ok16(e.out2, e.out2_ld, 2) && (!e.shuffle || (Cq % 64) == 0) && !(e.shuffle && e.out2) &&
              !(e.out2 && e.gdn) &&
              (!(e.res || e.gdn) || (!e.shuffle && (e.N % 8) == 0 && ok16(e.res, e.res_ld, 2) && ok16(e.gdn_x, e.gdn_ld, 2))))
@@ -967,6 +1022,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
             p.halo_h = p.TH + c.ks - 1;
             p.halo_bo = (halo_mode & 2) ? 1 : 0;
             p.a_bytes = (128 * p.halo_w * p.halo_h + 1023) / 1024 * 1024;
+            p.tsh = p.TH; p.tsw = p.TW;
             p.tilesH = (e.Hout + p.TH - 1) / p.TH;
             p.tilesW = (e.Wout + p.TW - 1) / p.TW;
         }
@@ -974,7 +1030,8 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     const int budget0 = 212 * 1024;     // dynamic shared memory (static: bias + barriers ~ 9.5 KB)
     p.Cin = c.Cin; p.dw_w9 = c.dw_w9; p.dw_bias = c.dw_bias;
     p.raw_bytes = c.prod == PROD_DW ? 128 * (p.TW + 2) * (p.TH + 2) : 0;
-    const int extra_bytes = c.prod == PROD_DW ? TC_RAW_SLOTS * p.raw_bytes + 10 * c.Cin * 4 : 0;
+    const int extra_bytes = c.prod == PROD_DW ? TC_RAW_SLOTS * p.raw_bytes + 10 * c.Cin * 4
+                                              : (c.ss ? (2 * 128 * 109 * 4 + 1023) / 1024 * 1024 : 0);     // shift-sum: two fp32 partial-product buffers
     const int ksteps = p.ks * p.ks * p.kchunks;
     const int bres_bytes = ksteps * p.BN * 128;
     const int per = (e.out2 || e.gdn) ? 2 : 1;

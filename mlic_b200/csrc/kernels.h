@@ -85,6 +85,8 @@ struct TcConv {
     int prod;                   // 0: A = the input (TMA); 1: A = depthwise3x3(input) + dw bias; 2: A = input^2  (1x1 GEMMs only)
     const float* dw_w9;         // prod 1: depthwise weights [9][Cin] fp32, bias [Cin]
     const float* dw_bias;
+    int ss;                     // 1: shift-sum form of a 3x3 (pad 1) subpel conv with 12 outputs: `w` is [9*12][Cpad] (row = tap*12 + n,
+                                //    n in pixel-shuffle column order), Epi.N = 108, bias[0..11], out = fp32 NCHW [B][3][2H][2W]; ks = 1
 };
 bool tc_conv_supported(const TcConv& c, const Epi& e);
 // returns cudaError_t-like int (0 ok)

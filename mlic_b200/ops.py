@@ -129,3 +129,20 @@ def ga_head(x, dw_weight, dw_bias, pw_weight, pw_bias, skip_weight, skip_bias, i
                                            C.c_void_p(t_out.data_ptr()), C.c_void_p(s_out.data_ptr()), iters, C.byref(ms),
                                            C.c_void_p(st)))
     return t_out, s_out, float(ms.value)
+
+
+def final_subpel(x, weight, bias, impl=1, iters=1):
+    """Final g_s layer of the bf16 path: x CUDA bf16 NHWC [B,H,W,C], weight [12,C,3,3], bias [12] -> fp32 NCHW [B,3,2H,2W]
+    (impl 0: implicit-GEMM conv, impl 1: shift-sum form), avg ms."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.bfloat16
+    B, H, W, Cin = x.shape
+    w = weight.detach().to("cpu", torch.float32).contiguous()
+    b = bias.detach().to("cpu", torch.float32).contiguous()
+    out = torch.empty((B, 3, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    ms = C.c_float(0)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_final_subpel(impl, C.c_void_p(x.data_ptr()), B, H, W, Cin, C.c_void_p(w.data_ptr()),
+                                                C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), iters, C.byref(ms),
+                                                C.c_void_p(st)))
+    return out, float(ms.value)

@@ -147,3 +147,15 @@ def test_depthwise_kernels(B, H, W, C, stride, act, dtype):
     else:
         tol = 2.0 ** -8 * ref.abs() + 2e-3
         assert bool(((out.float() - ref).abs() <= tol).all()), (out.float() - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B,H,W,C", [(1, 16, 8, 64), (2, 30, 50, 192), (1, 67, 29, 192)])
+def test_final_subpel_conv(impl, B, H, W, C):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, C, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(12, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(torch.bfloat16).float()
+    b = torch.randn(12, generator=g) * 0.1
+    out, _ = ops.final_subpel(x, w, b, impl=impl)
+    ref = F.pixel_shuffle(F.conv2d(x.float().permute(0, 3, 1, 2), w.cuda(), b.cuda(), padding=1), 2)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-4, rtol=1e-4)
