@@ -705,6 +705,23 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
         uint32_t blk = 0;
         int it = 0;
         const bool idle = p.store_mode == STORE_TMA && cq * 64 >= p.BN;     // this warp group owns no columns
+        // shift-sum mode: the (interior pixel, output) pairs this thread sums in phase 2 are the same for every tile
+        // (packed into one word per pair: py[0:4) px[4:7) n[7:11) ch[11:13) rr[13] s[14] ok[15] pofs[16:32))
+        uint32_t ss_pk[2] = {0u, 0u};
+        if constexpr (ACT == ACT_NONE && GDN == GDN_NONE && !RES && PROD == PROD_TMA) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int idx = (warp - EW0) * 32 + lane + k * NEPI * 32;
+                const int j = idx % 12, rest = idx / 12;
+                const int py = 1 + rest % 14, cr = rest / 14;
+                const int rr = cr & 1, ch = cr >> 1, px = 1 + (j >> 1), sx = j & 1;
+                const int n = (2 * rr + sx) * 3 + ch;
+                const int pofs = ((py - 1) * 8 + (px - 1)) * 109 + n;
+                if (p.store_mode == STORE_SS && idx < 84 * 12)
+                    ss_pk[k] = (uint32_t)py | ((uint32_t)px << 4) | ((uint32_t)n << 7) | ((uint32_t)ch << 11) | ((uint32_t)rr << 13) |
+                               ((uint32_t)sx << 14) | (1u << 15) | ((uint32_t)pofs << 16);
+            }
+        }
         for (int t = blockIdx.x; t < p.ntiles && !idle; t += gridDim.x, ++it) {
             const int nt = t % p.tilesN, mt = t / p.tilesN;
             const int img = mt / tiles_per_img;
@@ -808,7 +825,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 // phase 2: the 14 x 6 interior pixels x 12 outputs are summed over the 9 taps and written as fp32 NCHW with the
                 // pixel shuffle, 12 consecutive floats of one output row per 12 consecutive threads.
                 constexpr int SSP = 109;
-                float* P = reinterpret_cast<float*>(stg) + (size_t)(it & 1) * (128 * SSP);
+                float* P = reinterpret_cast<float*>(stg);      // one buffer (the operand ring needs the space: two tiles of A in flight)
                 {
                     float* prow = P + (size_t)r * SSP + cq * 28;
                     const uint32_t tc0 = trow + (uint32_t)(cq * 28);
@@ -831,24 +848,23 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 if (!(p.debug & 1)) {
                     float* o = reinterpret_cast<float*>(e.out);
                     const int OH = 2 * e.Hout, OW = 2 * e.Wout;
-                    for (int idx = (warp - EW0) * 32 + lane; idx < 84 * 12; idx += NEPI * 32) {
-                        const int j = idx % 12, rest = idx / 12;
-                        const int py = 1 + rest % 14, cr = rest / 14;
-                        const int rr = cr & 1, ch = cr >> 1;
-                        const int px = 1 + (j >> 1), ss = j & 1;
-                        const int n = (2 * rr + ss) * 3 + ch;
-                        const int gh = h0 + py, gw = w0 + px;
-                        if (gh < e.Hout && gw < e.Wout) {
-                            float acc = sBias[n];
-                            const float* pp = P + (size_t)((py - 1) * 8 + (px - 1)) * SSP + n;
 #pragma unroll
-                            for (int ky = 0; ky < 3; ++ky)
+                    for (int k = 0; k < 2; ++k) {
+                        if (ss_pk[k] & (1u << 15)) {
+                            const int gh = h0 + (int)(ss_pk[k] & 15u), gw = w0 + (int)((ss_pk[k] >> 4) & 7u);
+                            if (gh < e.Hout && gw < e.Wout) {
+                                float acc = sBias[(ss_pk[k] >> 7) & 15u];
+                                const float* pp = P + (ss_pk[k] >> 16);
 #pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) acc += pp[(ky * 8 + kx) * SSP + (ky * 3 + kx) * 12];
-                            o[(((size_t)img * 3 + ch) * OH + 2 * gh + rr) * OW + 2 * gw + ss] = acc;
+                                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) acc += pp[(ky * 8 + kx) * SSP + (ky * 3 + kx) * 12];
+                                o[(((size_t)img * 3 + ((ss_pk[k] >> 11) & 3u)) * OH + 2 * gh + ((ss_pk[k] >> 13) & 1u)) * OW + 2 * gw + ((ss_pk[k] >> 14) & 1u)] = acc;
+                            }
                         }
                     }
                 }
+                asm volatile("bar.sync 9, %0;" ::"r"(NEPI * 32) : "memory");      // P is rewritten by the next tile
                 continue;          // (accumulator already released)
             } else if (p.store_mode == STORE_NCHW3) {
                 // final subpel conv (N = 12 -> 3 channels): column (2r+s)*3 + ch -> out[b][ch][2h+r][2w+s], fp32 NCHW;
@@ -1031,7 +1047,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     p.Cin = c.Cin; p.dw_w9 = c.dw_w9; p.dw_bias = c.dw_bias;
     p.raw_bytes = c.prod == PROD_DW ? 128 * (p.TW + 2) * (p.TH + 2) : 0;
     const int extra_bytes = c.prod == PROD_DW ? TC_RAW_SLOTS * p.raw_bytes + 10 * c.Cin * 4
-                                              : (c.ss ? (2 * 128 * 109 * 4 + 1023) / 1024 * 1024 : 0);     // shift-sum: two fp32 partial-product buffers
+                                              : (c.ss ? (128 * 109 * 4 + 1023) / 1024 * 1024 : 0);     // shift-sum: the fp32 partial-product buffer
     const int ksteps = p.ks * p.ks * p.kchunks;
     const int bres_bytes = ksteps * p.BN * 128;
     const int per = (e.out2 || e.gdn) ? 2 : 1;
@@ -1180,7 +1196,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         unsigned long long h[148 * 9];
         cudaStreamSynchronize(s);
         cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
-        if (printed++ < 3) {
+        if (printed++ < 3 || (p.debug & 64)) {
             double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (unsigned i = 0; i < grid.x; ++i) { for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid.x; a[8] += (double)h[grid.x * 8 + i] / grid.x; }
             if (c.prod) fprintf(stderr, "[tc dbg] prod=%d compute warp 4: wait-raw %.0f wait-stage-free %.0f\n", c.prod, a[6], a[7]);
