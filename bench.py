@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -198,7 +198,9 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    tc_ms, tc_flops, tc_launches = net.profile_read(reset=True)
+    tc_ms, tc_flops, tc_launches = net.profile_read(reset=False)
+    top_ms, top_flops, top_n = net.profile_read_top(reset=True)
+    net.profile_read(reset=True)
     net.set_profile(False)
     launches = net.last_launch_count * args.steps
     clk = clocks.stop() if rank == 0 else None
@@ -244,11 +246,21 @@ def main():
     if rank == 0:
         pk = peaks()
         tc_tflops = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel (tcgen05 implicit GEMM, all conv / 1x1 / GDN GEMMs of the step)",
-                "achieved": tc_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tc_tflops / pk["tf_sust"],
-                "peak_source": pk["src"] + " bf16_tflops_sustained", "traffic": None,
-                "launches": tc_launches, "kernel_ms_per_step": tc_ms / max(args.steps, 1),
-                "share_of_step": tc_ms / ms if ms > 0 else None,
+        top_tflops = top_flops * top_n / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
+        # DRAM traffic of that launch shape: one `ncu --set full` capture (profiles/r01_ncu_subpel_full.txt), taken at one image
+        # per launch (dram__bytes_read.sum + dram__bytes_write.sum = 196.7 MB; algorithmic 50.1 + 200.5 MB, the tail of the
+        # output is still in L2 when the kernel ends); scaled here to this run's images per launch.
+        ncu_bytes_per_image = 196.7e6
+        roof = {"bound": "tensor",
+                "kernel": "conv_gemm_tc_kernel<GELU|none> as the 3x3 192->768 sub-pixel convolution at 272x480 (g_s.5 subpel_conv / upsample): "
+                          "the heaviest launch shape, 2 launches per step",
+                "achieved": top_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": top_tflops / pk["tf_sust"],
+                "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "flops_per_launch": top_flops, "launches": top_n, "avg_launch_ms": top_ms / max(top_n, 1),
+                "traffic": ncu_bytes_per_image * B, "traffic_source": "ncu --set full at 1 image/launch x images per launch",
+                "share_of_step": top_ms / ms if ms > 0 else None,
+                "all_tcgen05_launches": {"achieved": tc_tflops, "frac": tc_tflops / pk["tf_sust"], "launches": tc_launches,
+                                         "ms_per_step": tc_ms / max(args.steps, 1), "share_of_step": tc_ms / ms if ms > 0 else None},
                 "whole_step_tflops": world * B * args.steps * FLOP_PER_IMAGE / (ms * 1e-3) / 1e12 / world}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

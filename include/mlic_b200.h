@@ -82,6 +82,9 @@ int64_t mlic_last_launch_count(const mlic_engine* e);
 /* Live profile of the dominant kernel (the tcgen05 implicit GEMM) since the last reset:
  * out3 = { summed launch duration in ms, summed algorithmic FLOPs (2*M*N*K), launches }.  Synchronises. */
 int mlic_profile_read(mlic_engine* e, double* out3, int reset);
+/* Same bracket, restricted to the launches of the heaviest GEMM shape seen since the last reset (most algorithmic FLOPs
+ * per launch; for MLICPP_L the 3x3 192 -> 768 sub-pixel convolutions): out3 = {summed ms, FLOPs PER LAUNCH, launches}. */
+int mlic_profile_read_top(mlic_engine* e, double* out3, int reset);
 
 /* Per-launch trace: with option "trace" = 1 every launch of the following calls is followed by a CUDA event on the
  * launch stream; this writes "label<TAB>microseconds" per launch to `path` (synchronises) and clears the trace. */

@@ -14,7 +14,7 @@ MODE_FORWARD, MODE_COMPRESS, MODE_DECODER = 0, 1, 2
 EXPORTS = (
     "mlic_engine_create", "mlic_engine_destroy", "mlic_engine_set_param", "mlic_engine_finalize",
     "mlic_engine_set_option", "mlic_workspace_bytes", "mlic_run", "mlic_run_host", "mlic_last_launch_count",
-    "mlic_profile_read", "mlic_trace_dump", "mlic_conv2d_nhwc", "mlic_dwconv3x3_nhwc", "mlic_dsconv_nhwc", "mlic_final_subpel", "mlic_local_attn", "mlic_ga_head", "mlic_gaussian_conditional", "mlic_last_error", "mlic_version",
+    "mlic_profile_read", "mlic_profile_read_top", "mlic_trace_dump", "mlic_conv2d_nhwc", "mlic_dwconv3x3_nhwc", "mlic_dsconv_nhwc", "mlic_final_subpel", "mlic_local_attn", "mlic_ga_head", "mlic_gaussian_conditional", "mlic_last_error", "mlic_version",
 )
 
 
@@ -55,6 +55,7 @@ def lib():
     L.mlic_last_launch_count.argtypes = [vp]
     L.mlic_last_launch_count.restype = i64
     L.mlic_profile_read.argtypes = [vp, C.POINTER(C.c_double), i32]
+    L.mlic_profile_read_top.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.mlic_trace_dump.argtypes = [vp, C.c_char_p]
     L.mlic_conv2d_nhwc.argtypes = [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32,
                                    C.POINTER(f32), vp]

@@ -120,6 +120,7 @@ struct mlic_engine {
     size_t ev_used = 0;
     std::vector<double> ev_flops;
     double prof_ms = 0, prof_flops = 0, prof_launches = 0;
+    double top_flops = 0, top_ms = 0, top_n = 0;
     cudaEvent_t next_event() {
         if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
         return ev_pool[ev_used++];
@@ -131,6 +132,10 @@ struct mlic_engine {
             if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]);
             if (e != cudaSuccess) return fail("profile: %s", cudaGetErrorString(e));
             prof_ms += ms; prof_flops += ev_flops[i / 2]; prof_launches += 1;
+            // the heaviest launch shape (most algorithmic FLOPs per launch) is tracked separately: bench.py's roofline line
+            const double f = ev_flops[i / 2];
+            if (f > top_flops * (1.0 + 1e-9)) { top_flops = f; top_ms = ms; top_n = 1; }
+            else if (f >= top_flops * (1.0 - 1e-9)) { top_ms += ms; top_n += 1; }
         }
         ev_used = 0; ev_flops.clear();
         return 0;
@@ -1137,6 +1142,14 @@ int mlic_profile_read(mlic_engine* e, double* out3, int reset) {
     if (r) return r;
     out3[0] = e->prof_ms; out3[1] = e->prof_flops; out3[2] = e->prof_launches;
     if (reset) { e->prof_ms = e->prof_flops = e->prof_launches = 0; }
+    return 0;
+}
+int mlic_profile_read_top(mlic_engine* e, double* out3, int reset) {
+    if (!e || !out3) return fail("bad arguments");
+    int r = e->profile_collect();
+    if (r) return r;
+    out3[0] = e->top_ms; out3[1] = e->top_flops; out3[2] = e->top_n;
+    if (reset) { e->top_ms = e->top_flops = e->top_n = 0; }
     return 0;
 }
 

@@ -188,6 +188,14 @@ class MLICPlusPlus(nn.Module):
         _lib.check(_lib.lib().mlic_profile_read(self._engine, out, 1 if reset else 0))
         return float(out[0]), float(out[1]), int(out[2])
 
+    def profile_read_top(self, reset=True):
+        """-> (summed ms, algorithmic FLOPs per launch, launches) of the heaviest tcgen05 GEMM shape since the last reset."""
+        if self._engine is None:
+            return 0.0, 0.0, 0
+        out = (C.c_double * 3)()
+        _lib.check(_lib.lib().mlic_profile_read_top(self._engine, out, 1 if reset else 0))
+        return float(out[0]), float(out[1]), int(out[2])
+
     def trace_dump(self, path):
         """With `_trace` set, writes "label<TAB>microseconds" for every launch since the last dump (development aid)."""
         _lib.check(_lib.lib().mlic_trace_dump(self._engine, str(path).encode()))
