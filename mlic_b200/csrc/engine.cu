@@ -72,6 +72,7 @@ struct EpiOpt {
     float* out_f32 = nullptr;   // fp32 destination [pix][out_f32_ld] instead of `out`
     int out_f32_ld = 0;
     int nchw = 0;               // out_f32 is a dense NCHW tensor (x_hat)
+    int ck = 0;                 // 1 | 2: the GEMM rows are the anchor | non-anchor pixels of `in`, squeezed (TcConv::ck); tcgen05 path only
 };
 
 }  // namespace
@@ -504,6 +505,10 @@ struct mlic_engine {
         e.N = w->N; e.shuffle = w->shuffle;
         e.Hout = (in.H + 2 * pad - w->ks) / stride + 1;
         e.Wout = (in.W + 2 * pad - w->ks) / stride + 1;
+        if (o.ck) {
+            if (!(bf && use_tc && w->ks == 1 && stride == 1 && pad == 0 && (in.W % 2) == 0 && (in.H % 2) == 0)) { if (!rc) rc = fail("gemm '%s': checkerboard rows need the tcgen05 1x1 path", key.c_str()); return true; }
+            e.Wout = in.W / 2;
+        }
         bool vec = (w->N % 4 == 0);
         if (o.nchw) {
             if (!dry && !o.out_f32) { if (!rc) rc = fail("gemm '%s': no output", key.c_str()); return true; }
@@ -528,8 +533,10 @@ struct mlic_engine {
             if (stride == 1) { t.H = in.H; t.W = in.W; }
             else { t.H = e.Hout; t.W = e.Wout; }      // 1x1 stride s: sub-sampled grid
             t.sW = in.ld * stride; t.sH = in.W * in.ld * stride; t.sB = in.H * in.W * in.ld;
+            t.ck = o.ck;
             const bool sup = tc_conv_supported(t, e);
             if (prod && !sup) return false;
+            if (o.ck && !sup) { if (!rc) rc = fail("gemm '%s': checkerboard rows not supported for this layer", key.c_str()); return true; }
             if (!go()) return true;
             if (sup) {
                 cudaEvent_t ev1 = nullptr;
@@ -775,14 +782,20 @@ struct mlic_engine {
     }
 
     // EntropyParameters (transform/entropy.py:10-29): 1x1 chain in->320->256->128->2C, GELU between; fp32 out
-    void ep(const Act& in, const std::string& p, float* out32) {
+    // ck != 0 (bf16 fast path): only the anchor (1) / non-anchor (2) pixels are evaluated -- the stack is per-pixel and its
+    // output is multiplied by that mask (mlicpp.py:112-117,148-152); out32 is then squeezed, [B*h*(w/2)][2C].
+    bool ep_squeezed(int Hh, int Ww) const { return bf && use_tc && fuse && (Hh % 2) == 0 && (Ww % 2) == 0; }
+    void ep(const Act& in, const std::string& p, float* out32, int ck = 0) {
         size_t mark = ws_off;
         EpiOpt g; g.act = ACT_GELU;
         Act cur = in;
+        const int Mh = in.B * in.H * (in.W / 2);
         for (int j : {0, 2, 4}) {
             const ConvW* w = cw(p + ".fusion." + std::to_string(j));
-            Act nx = act(in.B, in.H, in.W, w ? w->N : 0);
-            gemm(cur, p + ".fusion." + std::to_string(j), 1, 0, &nx, g);
+            Act nx = ck ? act(1, 1, Mh, w ? w->N : 0) : act(in.B, in.H, in.W, w ? w->N : 0);
+            EpiOpt gj = g;
+            if (ck && j == 0) gj.ck = ck;
+            gemm(cur, p + ".fusion." + std::to_string(j), 1, 0, &nx, gj);
             cur = nx;
         }
         EpiOpt o; o.out_f32 = out32; o.out_f32_ld = 2 * C;
@@ -1012,13 +1025,14 @@ struct mlic_engine {
                 inter_ctx(prev, "global_inter_context." + is, s_inter);
                 channel_ctx(prev, "channel_context." + is, s_chan);
             }
-            ep(ep_a, "entropy_parameters_anchor." + is, pa);
+            const bool esq = ep_squeezed(h, w);
+            ep(ep_a, "entropy_parameters_anchor." + is, pa, esq ? PAR_ANCHOR : 0);
             QuantArgs q;
             memset(&q, 0, sizeof q);
             q.y = y32 + (size_t)i * C; q.y_ld = M; q.pa = pa; q.pn = pn; q.slot = slot;
             q.B = B; q.H = h; q.W = w; q.C = C; q.mode = mode; q.vbr = use_gain; q.gain = gain; q.rgain = rgain;
             q.lik = lik ? lik + (size_t)i * C : nullptr; q.lik_ld = M;
-            q.table = scale_table; q.levels = 64;
+            q.table = scale_table; q.levels = 64; q.sq = esq ? 1 : 0;
             if (mode == MLIC_MODE_COMPRESS) {
                 if (!dry && (!io->symbols || !io->indexes)) return fail("compress needs symbols and indexes buffers");
                 q.sym = io->symbols ? io->symbols + (size_t)(2 * i) * half : nullptr;
@@ -1028,7 +1042,7 @@ struct mlic_engine {
             lrp(lrp_in, "lrp_anchor." + is, slot, PAR_ANCHOR);
             if (i) intra_ctx(view(LRPW, Me + (i - 1) * C, C), slot, "global_intra_context." + is, s_intra);
             local_ctx(slot, "local_context." + is, s_local);
-            ep(ep_n, "entropy_parameters_nonanchor." + is, pn);
+            ep(ep_n, "entropy_parameters_nonanchor." + is, pn, esq ? PAR_NONANCHOR : 0);
             if (mode == MLIC_MODE_COMPRESS) { q.sym += half; q.idx += half; }
             if (go()) { launch_quant_nonanchor(bf, q, st); after_launch("quant_nonanchor"); }
             lrp(lrp_in, "lrp_nonanchor." + is, slot, PAR_NONANCHOR);

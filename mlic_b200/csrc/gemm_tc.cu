@@ -84,6 +84,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -190,6 +197,7 @@ struct TcParams {
     int Cin;                // PROD_DW: channels of the depthwise conv (= K of the GEMM)
     const float* dw_w9;     // PROD_DW: depthwise weights [9][Cin] fp32
     const float* dw_bias;   // PROD_DW: depthwise bias [Cin]
+    int ck;                 // checkerboard-squeezed A operand: `a` is a 5-D map (c, j, h & 1, h >> 1, b), box {64, TW, 2, TH/2, 1}
     int tsh, tsw, torg;     // tile origin of tile (th, tw) = (th * tsh + torg, tw * tsw + torg); TH / TW / 0 except in shift-sum mode
     int halo;               // 1 (ks > 1, weights resident): the A stage of a 64-channel chunk is ONE halo patch {64, halo_w, TH+ks-1}
                             //    and the ks*ks taps are UMMA descriptors into it (start + (ky*halo_w + kx) pixels): the input is
@@ -548,7 +556,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     const int ky = tap / p.ks, kx = tap - ky * p.ks;
                     uint8_t* sa = base + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                    tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                    if (p.ck) tma_load_5d(sa, &tm.a, &full_bar[stage], cc * 64, w0, 0, h0 >> 1, img);
+                    else tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
                     if (!p.b_resident) tma_load_2d(sa + p.a_bytes, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -964,6 +973,8 @@ bool tc_conv_supported(const TcConv& c, const Epi& e) {
     if (c.Cin < 8 || c.Cpad % 64 != 0) return false;
     if (e.N < 8 || e.N > TC_MAX_N) return false;
     if (c.H <= 0 || c.W <= 0 || c.B <= 0) return false;
+    if (c.ck && !(c.prod == PROD_TMA && c.ks == 1 && c.pad == 0 && !c.ss && (c.H % 2) == 0 && (c.W % 2) == 0 && e.Hout == c.H && e.Wout == c.W / 2 &&
+                  c.sW == c.ld && c.sH == c.W * c.ld)) return false;
     if (c.ss) return c.prod == PROD_TMA && c.ks == 1 && c.pad == 0 && e.N == 108 && e.nchw && e.shuffle && e.out_f32 && !e.res && !e.gdn &&
                      e.act == ACT_NONE && !e.premask && !e.postmask && c.Cpad <= 256;
     if (e.nchw && !(e.shuffle && e.N == 12 && e.out_f32)) return false;
@@ -1002,7 +1013,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     // output patch shape: minimise the number of tiles
     const int cand[5][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {1, 128}};
     long long best = -1;
-    for (int i = 0; i < (c.prod == PROD_DW ? 1 : 5); ++i) {       // the depthwise producer is written for the 8 x 16 patch
+    for (int i = 0; i < (c.prod == PROD_DW ? 1 : (c.ck ? 4 : 5)); ++i) {       // the depthwise producer is written for the 8 x 16 patch; ck: even TH
         long long t = (long long)((e.Hout + cand[i][0] - 1) / cand[i][0]) * ((e.Wout + cand[i][1] - 1) / cand[i][1]);
         if (best < 0 || t < best) { best = t; p.TH = cand[i][0]; p.TW = cand[i][1]; }
     }
@@ -1074,7 +1085,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         }
     }
     if (!planned) { snprintf(g_tc_err, sizeof g_tc_err, "no shared-memory plan for BN=%d ksteps=%d", p.BN, ksteps); return 8; }
-    p.l2_prefetch = (p.ks == 1 && c.prod != PROD_SQ && !(p.debug & 16)) ? (c.prod == PROD_DW ? 2 : 3) : 0;
+    p.l2_prefetch = (p.ks == 1 && c.prod != PROD_SQ && !c.ck && !(p.debug & 16)) ? (c.prod == PROD_DW ? 2 : 3) : 0;
     if (c.prod != PROD_TMA && p.store_mode == STORE_DIRECT) p.epi_vec = p.epi_vec && p.ld_vec;
     // (development, MLIC_HALO bit3; measured slower than the single accumulator: 420 us vs 195 us on the final 192 -> 12 conv)
     p.acc_split = ((halo_mode & 8) && p.halo && p.store_mode == STORE_NCHW3 && p.BN == 16 && p.ks * p.ks * p.BN <= 256) ? 1 : 0;
@@ -1092,7 +1103,24 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
 
     TcMaps tm;
     memset(&tm, 0, sizeof tm);
-    {
+    p.ck = c.ck;
+    if (c.ck) {
+        // anchor (ck 1): row h keeps w = 2j + 1 - (h & 1); non-anchor (ck 2): w = 2j + (h & 1)   (anchor = (h + w) odd)
+        const size_t ld = (size_t)c.ld;
+        const bf16* basep = reinterpret_cast<const bf16*>(c.in) + (c.ck == 1 ? ld : 0);
+        const size_t hp_stride = c.ck == 1 ? ((size_t)c.W - 1) * ld : ((size_t)c.W + 1) * ld;
+        cuuint64_t dims[5] = {(cuuint64_t)c.Cin, (cuuint64_t)(c.W / 2), 2, (cuuint64_t)(c.H / 2), (cuuint64_t)c.B};
+        cuuint64_t strides[4] = {(cuuint64_t)(2 * ld) * 2, (cuuint64_t)hp_stride * 2, (cuuint64_t)(2 * (size_t)c.W * ld) * 2, (cuuint64_t)c.sB * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)p.TW, 2, (cuuint32_t)(p.TH / 2), 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = g_encode(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(basep), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(A, checkerboard) failed: %d (C=%d W=%d H=%d B=%d)", (int)r, c.Cin, c.W, c.H, c.B);
+            return 2;
+        }
+    } else {
         cuuint64_t dims[4] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.B};
         cuuint64_t strides[3] = {(cuuint64_t)c.sW * 2, (cuuint64_t)c.sH * 2, (cuuint64_t)c.sB * 2};
         const bool halo = c.prod == PROD_DW;

@@ -1115,6 +1115,11 @@ void launch_unsqueeze_nonanchor(const Act& src /*[1,1,B*H*W/2,C]*/, const Act& d
 //   2. per-chunk sum exp(K-max), sum exp(K-max) V^T   -> pctx[B][heads][nch][hd*hd + hd]
 //   3. reduce chunks (fixed order), normalise, apply to softmax_c(Q)
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8_bf16_k(const uint4 t, float v[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
 constexpr int LA_CH = 64;   // max chunks
 // Position chunks per (image, head).  The count depends on the image size only, so the (fixed-order) reduction of the chunk
 // partials is identical whatever the batch size: results are batch-invariant bit for bit.
@@ -1156,12 +1161,14 @@ __global__ void __launch_bounds__(256) lin_colmax_kernel(const T* __restrict__ q
     }
 }
 
-// block = (chunk, head, b); 256 threads; thread t owns ctx entries (c1 = t / (hd/ (hd*hd/256)) ...) generic: loops.
+// block = (chunk, head, b); 256 threads.  TP positions are staged per step (bf16: 16-byte loads, all of a step's loads in
+// flight together, so a 255-position chunk is two latency rounds instead of eight); thread t then owns PER_T entries
+// (c1, c2) of the hd x hd context and sums exp(K[p][c1] - max) * V[p][c2] over the staged positions in position order.
 template <typename T, int HD>
 __global__ void __launch_bounds__(256) lin_ctx_kernel(const T* __restrict__ qkv, int ld, int D, int H, int W, int nch,
                                                       int par, const float* __restrict__ pmax,
                                                       float* __restrict__ pctx) {
-    constexpr int TP = 32;               // positions staged per step
+    constexpr int TP = 128;              // positions staged per step
     __shared__ float sE[TP][HD + 1];
     __shared__ float sV[TP][HD + 1];
     __shared__ float sMax[HD];
@@ -1181,25 +1188,40 @@ __global__ void __launch_bounds__(256) lin_ctx_kernel(const T* __restrict__ qkv,
 #pragma unroll
     for (int j = 0; j < PER_T; ++j) acc[j] = 0.f;
     float ssum = 0.f;      // threads < HD accumulate sum exp for channel threadIdx.x
+    constexpr int VEC = sizeof(T) == 2 ? 8 : 4;          // elements per 16-byte load
+    constexpr int CG = HD / VEC;                         // 16-byte groups per position and array
+    const bool vec_ok = (ld % VEC) == 0 && ((D % VEC) == 0) && (((uintptr_t)qkv) % 16 == 0);
     for (int ps = p0; ps < p1; ps += TP) {
-        for (int i = threadIdx.x; i < TP * HD; i += blockDim.x) {
-            int pp = i / HD, c = i - pp * HD;
-            int p = ps + pp;
-            float e = 0.f, v = 0.f;
-            if (p < p1) {
-                bool keep = true;
-                if (par != PAR_NONE) {
-                    int h = p / W, w = p - h * W;
-                    keep = parity_keep(par, h, w);
-                }
-                if (keep) {
-                    const T* base = qkv + ((size_t)b * HW + p) * ld + g * HD + c;
-                    e = expf(to_f<T>(base[D]) - sMax[c]);
-                    v = to_f<T>(base[2 * D]);
-                }
+        for (int i = threadIdx.x; i < TP * CG; i += blockDim.x) {
+            const int pp = i / CG, c = (i - pp * CG) * VEC;
+            const int p = ps + pp;
+            float e[VEC], v[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { e[k] = 0.f; v[k] = 0.f; }
+            bool keep = p < p1;
+            if (keep && par != PAR_NONE) {
+                int h = p / W, w = p - h * W;
+                keep = parity_keep(par, h, w);
             }
-            sE[pp][c] = e;
-            sV[pp][c] = v;
+            if (keep) {
+                const T* base = qkv + ((size_t)b * HW + p) * ld + g * HD + c;
+                if (vec_ok) {
+                    if constexpr (sizeof(T) == 2) {
+                        unpack8_bf16_k(*reinterpret_cast<const uint4*>(base + D), e);
+                        unpack8_bf16_k(*reinterpret_cast<const uint4*>(base + 2 * D), v);
+                    } else {
+                        load4(reinterpret_cast<const float*>(base + D), e);
+                        load4(reinterpret_cast<const float*>(base + 2 * D), v);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) { e[k] = to_f<T>(base[D + k]); v[k] = to_f<T>(base[2 * D + k]); }
+                }
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) e[k] = expf(e[k] - sMax[c + k]);
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { sE[pp][c + k] = e[k]; sV[pp][c + k] = v[k]; }
         }
         __syncthreads();
 #pragma unroll
@@ -1359,8 +1381,9 @@ __global__ void quant_anchor_kernel(QuantArgs a) {
         int b = (int)(q / a.H);
         T* slot = reinterpret_cast<T*>(a.slot.p) + p * a.slot.ld + c;
         if (((h + w) & 1) == 0) { *slot = from_f<T>(0.f); continue; }
-        const float sigma = a.pa[p * 2 * C + c];
-        const float mu = a.pa[p * 2 * C + C + c];
+        const long long pe = a.sq ? (q * (a.W >> 1) + (w >> 1)) : p;       // row of this pixel in the entropy-parameter buffer
+        const float sigma = a.pa[pe * 2 * C + c];
+        const float mu = a.pa[pe * 2 * C + C + c];
         float out;
         if (a.mode == 2) {
             out = mu;
@@ -1395,8 +1418,9 @@ __global__ void quant_nonanchor_kernel(QuantArgs a) {
         const bool anchor = ((h + w) & 1) == 1;
         T* slot = reinterpret_cast<T*>(a.slot.p) + p * a.slot.ld + c;
         const float* pp = anchor ? a.pa : a.pn;
-        const float sigma = pp[p * 2 * C + c];
-        const float mu = pp[p * 2 * C + C + c];
+        const long long pe = a.sq ? (q * (a.W >> 1) + (w >> 1)) : p;
+        const float sigma = pp[pe * 2 * C + c];
+        const float mu = pp[pe * 2 * C + C + c];
         if (a.mode == 2) {           // decoder walk: both halves take means_anchor (mlicpp.py:405,418)
             if (anchor) *slot = from_f<T>(to_f<T>(*slot) + mu);
             continue;

@@ -62,6 +62,7 @@ struct QuantArgs {
     float* lik; int lik_ld;         // forward: likelihood slice inside the fp32 NHWC [pix][M] buffer
     int32_t* sym; int32_t* idx;     // compress: base of this half-slice (flattened over [B,C,H,W/2])
     const float* table; int levels; // scale table (fp32, as stored in gaussian_conditional.scale_table)
+    int sq;                         // 1: pa / pn hold only the anchor / non-anchor pixels, squeezed ([B][H][W/2][2C])
 };
 void launch_quant_anchor(int bf, const QuantArgs& a, cudaStream_t s);
 void launch_quant_nonanchor(int bf, const QuantArgs& a, cudaStream_t s);
@@ -85,6 +86,9 @@ struct TcConv {
     int prod;                   // 0: A = the input (TMA); 1: A = depthwise3x3(input) + dw bias; 2: A = input^2  (1x1 GEMMs only)
     const float* dw_w9;         // prod 1: depthwise weights [9][Cin] fp32, bias [Cin]
     const float* dw_bias;
+    int ck;                     // 1 | 2 (1x1 GEMMs): the GEMM rows are only the ANCHOR | NON-ANCHOR pixels of the input view, in the squeezed
+                                //    order of utils/ckbd.py:47-59 ([B][H][W/2], w = 2j + ((h + ck) & 1)); H / W describe the FULL view, Epi.Hout = H,
+                                //    Epi.Wout = W / 2.  The gather is one 5-D TMA map (c, j, h & 1, h >> 1, b): no squeezed copy of the input exists.
     int ss;                     // 1: shift-sum form of a 3x3 (pad 1) subpel conv with 12 outputs: `w` is [9*12][Cpad] (row = tap*12 + n,
                                 //    n in pixel-shuffle column order), Epi.N = 108, bias[0..11], out = fp32 NCHW [B][3][2H][2W]; ks = 1
 };
