@@ -20,6 +20,7 @@
 #include "kernels.h"
 
 #include <cuda.h>
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -957,6 +958,134 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.acc_stride))
                      : "memory");
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone depthwise 3x3 (pad 1, stride 1 | 2) + bias (+ GELU), bf16 NHWC, TMA-fed and persistent.
+// Same arithmetic scheme as the fused producer above (lane = channel pair, FFMA2 against 9 taps in registers, warp pw owns
+// output columns 2pw, 2pw+1), but the halo patch {64 ch, TW*S+2, TH*S+2} of every (tile, 64-channel chunk) item arrives
+// through a ring of TMA boxes (zero fill = conv padding and channel tail), so loads of the next items are in flight while
+// the 8 compute warps work, and results go straight to global memory (one full 128-byte line per warp store).
+// ------------------------------------------------------------------------------------------
+template <int S> struct DwT { static constexpr int TH = S == 1 ? 8 : 4, TW = 16, IH = TH * S + 2, IW = TW * S + 2, NX = S == 1 ? 4 : 5,
+                                                   SLOTS = S == 1 ? 4 : 2, BYTES = IH * IW * 128; };
+template <int S>
+__global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, int C, bf16* __restrict__ out, int Ho,
+                                                            int Wo, int old, const float* __restrict__ w9, const float* __restrict__ bias,
+                                                            int act, int tilesW, int tilesH, int chunks, int nitems) {
+    using TT = DwT<S>;
+    extern __shared__ uint8_t dw_smem_raw[];
+    uint8_t* ring = (uint8_t*)(((uintptr_t)dw_smem_raw + 127) & ~(uintptr_t)127);
+    __shared__ uint64_t full_bar[TT::SLOTS], empty_bar[TT::SLOTS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TT::SLOTS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    __syncthreads();
+    const int tiles_per_img = tilesW * tilesH;
+    if (warp == 8) {
+        if (lane == 0) {
+            int n = 0;
+            for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+                const int slot = n % TT::SLOTS;
+                const uint32_t ph = (uint32_t)(n / TT::SLOTS) & 1u;
+                mbar_wait(&empty_bar[slot], ph ^ 1u);
+                const int cc = it % chunks, tile = it / chunks;
+                const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+                const int th = tr / tilesW, tw = tr - th * tilesW;
+                mbar_expect_tx(&full_bar[slot], (uint32_t)TT::BYTES);
+                tma_load_4d(ring + (size_t)slot * TT::BYTES, &tmap, &full_bar[slot], cc * 64, tw * TT::TW * S - 1, th * TT::TH * S - 1, b);
+            }
+        }
+        return;
+    }
+    const int pw = warp;
+    int n = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+        const int slot = n % TT::SLOTS;
+        const uint32_t ph = (uint32_t)(n / TT::SLOTS) & 1u;
+        const int cc = it % chunks, tile = it / chunks;
+        const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+        const int th = tr / tilesW, tw = tr - th * tilesW;
+        const int oh0 = th * TT::TH, ow0 = tw * TT::TW;
+        const int c = cc * 64 + 2 * lane;
+        const bool cok = c < C;
+        float2 w2[9], b2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w2[t] = cok ? make_float2(w9[t * C + c], w9[t * C + c + 1]) : make_float2(0.f, 0.f);
+        if (cok) b2 = make_float2(bias[c], bias[c + 1]);
+        mbar_wait(&full_bar[slot], ph);
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * TT::BYTES) + (size_t)(2 * pw * S) * 32 + lane;
+        float2 acc[TT::TH][2];
+#pragma unroll
+        for (int oy = 0; oy < TT::TH; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
+#pragma unroll
+        for (int iy = 0; iy < TT::IH; ++iy) {
+            float2 x[TT::NX];
+#pragma unroll
+            for (int j = 0; j < TT::NX; ++j) x[j] = bf2_to_f2(rp[(size_t)(iy * TT::IW + j) * 32]);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                if ((iy - ky) >= 0 && ((iy - ky) % S) == 0 && (iy - ky) / S < TT::TH) {
+                    const int oy = (iy - ky) / S;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) acc[oy][q] = __ffma2_rn(x[q * S + kx], w2[ky * 3 + kx], acc[oy][q]);
+                }
+            }
+            if (iy >= 2 && ((iy - 2) % S) == 0) {
+                const int oy = (iy - 2) / S;
+                const int oh = oh0 + oy;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int ow = ow0 + 2 * pw + q;
+                    float2 v = acc[oy][q];
+                    if (act == ACT_GELU) v = gelu2(v);
+                    if (cok && oh < Ho && ow < Wo) {
+                        __nv_bfloat162 hv = __floats2bfloat162_rn(v.x, v.y);
+                        *reinterpret_cast<uint32_t*>(out + (((size_t)b * Ho + oh) * Wo + ow) * old + c) = *reinterpret_cast<uint32_t*>(&hv);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
+    }
+}
+
+template <int S>
+static int launch_dw_tma(const Act& in, const Act& out, const float* w9, const float* bias, int act, cudaStream_t s) {
+    using TT = DwT<S>;
+    CUtensorMap tmap;
+    cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.B};
+    cuuint64_t strides[3] = {(cuuint64_t)in.ld * 2, (cuuint64_t)in.W * in.ld * 2, (cuuint64_t)in.H * in.W * in.ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TT::IW, (cuuint32_t)TT::IH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(dw) failed: %d", (int)r); return 2; }
+    const int tilesW = (out.W + TT::TW - 1) / TT::TW, tilesH = (out.H + TT::TH - 1) / TT::TH, chunks = (in.C + 63) / 64;
+    const long long nitems = (long long)out.B * tilesW * tilesH * chunks;
+    if (nitems <= 0 || nitems > 0x7fffffffLL) return 3;
+    const int smem = TT::SLOTS * TT::BYTES + 128;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(dwconv3x3_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int grid = (int)std::min<long long>(nitems, 2LL * num_sms);
+    dwconv3x3_tma_kernel<S><<<grid, 288, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
+    return cudaGetLastError() == cudaSuccess ? 0 : 4;
+}
+// bf16 NHWC depthwise 3x3 through the TMA-fed kernel; non-zero: not taken (the caller falls back to the staged kernel)
+int launch_dwconv3x3_tma(const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act, cudaStream_t s) {
+    if (tc_init()) return 1;
+    if ((in.C % 8) != 0 || (in.ld % 8) != 0 || (out.ld % 2) != 0 || ((uintptr_t)in.p % 16) != 0 || ((uintptr_t)out.p % 4) != 0) return 1;
+    if (stride == 1) return launch_dw_tma<1>(in, out, w9, bias, act, s);
+    if (stride == 2) return launch_dw_tma<2>(in, out, w9, bias, act, s);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------ host side

@@ -538,7 +538,9 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_lane2_kernel(const bf16* __r
 
 void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act,
                       cudaStream_t s) {
-    static const bool old_dw = getenv("MLIC_OLD_DW") != nullptr;      // development: previous tiled kernel
+    static const int dw_mode = getenv("MLIC_DW") ? atoi(getenv("MLIC_DW")) : 2;      // development: 0 tiled, 1 lane-pair, 2 TMA-fed (default)
+    const bool old_dw = dw_mode == 0;
+    if (dw_mode == 2 && bf && out.B > 0 && out.H > 0 && out.W > 0 && launch_dwconv3x3_tma(in, out, w9, bias, stride, act, s) == 0) return;
     if (!old_dw && bf && (in.C % 8 == 0) && (in.ld % 8 == 0) && (out.ld % 2 == 0) && (((uintptr_t)in.p) % 16 == 0) &&
         (((uintptr_t)out.p) % 4 == 0) && (stride == 1 || stride == 2) && out.B > 0 && out.H > 0 && out.W > 0) {
         if (stride == 1) {

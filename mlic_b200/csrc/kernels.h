@@ -92,6 +92,8 @@ struct TcConv {
     int ss;                     // 1: shift-sum form of a 3x3 (pad 1) subpel conv with 12 outputs: `w` is [9*12][Cpad] (row = tap*12 + n,
                                 //    n in pixel-shuffle column order), Epi.N = 108, bias[0..11], out = fp32 NCHW [B][3][2H][2W]; ks = 1
 };
+// TMA-fed persistent depthwise 3x3 (bf16 NHWC); non-zero: not taken
+int launch_dwconv3x3_tma(const Act& in, const Act& out, const float* w9, const float* bias, int stride, int act, cudaStream_t s);
 bool tc_conv_supported(const TcConv& c, const Epi& e);
 // returns cudaError_t-like int (0 ok)
 int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s);
