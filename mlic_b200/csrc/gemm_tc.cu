@@ -58,18 +58,35 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// suspend-time hint of try_wait: a waiting warp is parked by the hardware until the phase completes (or this many ns pass)
+// instead of re-issuing the poll loop every ~170 clocks: polling was 15 % of the warp instructions of the fused
+// DepthWiseConv kernel (profiles/r01_ncu_dsconv_full.txt), competing with the producer warps for issue slots
+#ifndef MLIC_MBAR_SUSPEND_NS
+#define MLIC_MBAR_SUSPEND_NS 20000u
+#endif
+template <bool PARK = true>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     long long t0 = 0;
     for (uint32_t n = 1;; ++n) {
         uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
+        if constexpr (PARK) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity), "r"(MLIC_MBAR_SUSPEND_NS)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity)
+                : "memory");
+        }
         if (done) return;
         if ((n & 0x3ffu) == 0) {                               // the clock is read once per 1024 failed polls only
             const long long t = clock64();
@@ -436,6 +453,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     const long long t_start = clock64();
     long long w0c = 0, w1c = 0, w2c = 0, w3c = 0;
 #define TIMED_WAIT(acc, bar, par) do { if (dbg) { long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
+#define TIMED_SPIN(acc, bar, par) do { if (dbg) { long long _t = clock64(); mbar_wait<false>(bar, par); acc += clock64() - _t; } else mbar_wait<false>(bar, par); } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * 128;
@@ -528,7 +546,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 if constexpr (PROD == PROD_DW) {
                     // halo patches {64 ch, TW+2, TH+2} into the raw ring (the compute warps turn them into A stages)
                     for (int k = 0; k < ksteps; ++k) {
-                        TIMED_WAIT(w0c, &raw_empty[rslot], rphase ^ 1);
+                        TIMED_SPIN(w0c, &raw_empty[rslot], rphase ^ 1);
                         mbar_expect_tx(&raw_full[rslot], (uint32_t)p.raw_bytes);
                         tma_load_4d(rawbuf + (size_t)rslot * p.raw_bytes, &tm.a, &raw_full[rslot], k * 64, w0 - 1, h0 - 1, img);
                         if (++rslot == TC_RAW_SLOTS) { rslot = 0; rphase ^= 1; }
@@ -536,7 +554,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 } else if constexpr (PROD == PROD_SQ) {
                     // the patch lands in the A stage itself; the compute warps square it in place
                     for (int k = 0; k < ksteps; ++k) {
-                        TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
+                        TIMED_SPIN(w0c, &empty_bar[stage], phase ^ 1);
                         uint8_t* sa = base + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&raw_full[stage], (uint32_t)TC_A_BYTES);
                         tma_load_4d(sa, &tm.a, &raw_full[stage], k * 64, w0, h0, img);
@@ -544,7 +562,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     }
                 } else if (p.halo) {
                     for (int cc = 0; cc < p.kchunks; ++cc) {
-                        TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
+                        TIMED_SPIN(w0c, &empty_bar[stage], phase ^ 1);
                         uint8_t* sa = base + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&full_bar[stage], (uint32_t)(128 * p.halo_w * p.halo_h));
                         tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 - p.pad, h0 - p.pad, img);
@@ -552,7 +570,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     }
                 } else {
                 for (int k = 0; k < ksteps; ++k) {
-                    TIMED_WAIT(w0c, &empty_bar[stage], phase ^ 1);
+                    TIMED_SPIN(w0c, &empty_bar[stage], phase ^ 1);
                     const int tap = k / p.kchunks, cc = k - tap * p.kchunks;
                     const int ky = tap / p.ks, kx = tap - ky * p.ks;
                     uint8_t* sa = base + (size_t)stage * stage_bytes;
@@ -575,13 +593,13 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
             if (p.b_resident) { mbar_wait(&bres_bar, 0); tcgen05_fence_after(); }
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
                 const int as = it & 1;
-                TIMED_WAIT(w2c, &acc_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                TIMED_SPIN(w2c, &acc_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t dcol = tmem_base + (uint32_t)(as * p.acc_stride);
                 if (p.halo) {
                     const int taps = p.ks * p.ks;
                     for (int cc = 0; cc < p.kchunks; ++cc) {
-                        TIMED_WAIT(w1c, &full_bar[stage], phase);
+                        TIMED_SPIN(w1c, &full_bar[stage], phase);
                         tcgen05_fence_after();
                         const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
                         // Measured on the final 192 -> 12 conv (N = 16): an M = 128, K = 16 MMA with A in shared memory costs ~124 clocks
@@ -603,7 +621,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     }
                 } else
                 for (int k = 0; k < ksteps; ++k) {
-                    TIMED_WAIT(w1c, &full_bar[stage], phase);
+                    TIMED_SPIN(w1c, &full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
                     const uint64_t adesc = umma_desc_sw128(sa);
@@ -951,6 +969,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                          d[6] = (unsigned long long)w0c; d[7] = (unsigned long long)w1c; dbg[(size_t)gridDim.x * 8 + blockIdx.x] = (unsigned long long)w2c; }
     }
 #undef TIMED_WAIT
+#undef TIMED_SPIN
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) {

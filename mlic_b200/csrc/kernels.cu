@@ -1251,6 +1251,104 @@ __global__ void __launch_bounds__(256) lin_ctx_kernel(const T* __restrict__ qkv,
     if (threadIdx.x < HD) dst[HD * HD + threadIdx.x] = ssum;
 }
 
+// bf16 fast mode: the same chunk partial on the warp-level tensor path.  ctx[c1][c2] = sum_p E[p][c1] V[p][c2] is an
+// HD x HD x positions GEMM: E = exp(K - max) (rounded to bf16; the normaliser sums the SAME rounded values) and V are staged
+// position-major, both fragments come from ldmatrix.trans, accumulation is fp32 in position order.  HD = 32: one 16x8
+// output tile per warp; HD = 16: two tiles x four position quarters, summed in a fixed order.
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+template <int HD>
+__global__ void __launch_bounds__(256) lin_ctx_mma_kernel(const bf16* __restrict__ qkv, int ld, int D, int H, int W, int nch, int par,
+                                                          const float* __restrict__ pmax, float* __restrict__ pctx) {
+    constexpr int TP = 256;                       // positions staged per step
+    constexpr int PITCH = HD + 8;                 // bf16 elements per staged row (16-byte aligned, conflict-free ldmatrix rows)
+    constexpr int CG = HD / 8;
+    constexpr int TILES = (HD / 16) * (HD / 8), KPARTS = 8 / TILES, KLEN = TP / KPARTS;
+    __shared__ __align__(16) bf16 sE[TP * PITCH];
+    __shared__ __align__(16) bf16 sV[TP * PITCH];
+    __shared__ float sMax[HD];
+    __shared__ float sPart[KPARTS > 1 ? KPARTS * HD * HD : 1];
+    const int ch = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const int heads = gridDim.y;
+    const int HW = H * W;
+    const int per = (HW + nch - 1) / nch;
+    const int p0 = ch * per, p1 = min(HW, p0 + per);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < HD) {
+        float m = -INFINITY;
+        for (int k = 0; k < nch; ++k) m = fmaxf(m, pmax[((size_t)b * nch + k) * D + g * HD + threadIdx.x]);
+        sMax[threadIdx.x] = m;
+    }
+    __syncthreads();
+    const int tile = warp % TILES, kpart = warp / TILES;
+    const int mt = tile / (HD / 8), nt = tile % (HD / 8);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float ssum = 0.f;
+    const uint32_t sE_s = (uint32_t)__cvta_generic_to_shared(sE), sV_s = (uint32_t)__cvta_generic_to_shared(sV);
+    for (int ps = p0; ps < p1; ps += TP) {
+        for (int i = threadIdx.x; i < TP * CG; i += blockDim.x) {
+            const int pp = i / CG, c = (i - pp * CG) * 8;
+            const int p = ps + pp;
+            uint4 ev = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            bool keep = p < p1;
+            if (keep && par != PAR_NONE) {
+                int h = p / W, w = p - h * W;
+                keep = parity_keep(par, h, w);
+            }
+            if (keep) {
+                const bf16* base = qkv + ((size_t)b * HW + p) * ld + g * HD + c;
+                float e[8];
+                unpack8_bf16_k(*reinterpret_cast<const uint4*>(base + D), e);
+                vv = *reinterpret_cast<const uint4*>(base + 2 * D);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = __expf(e[k] - sMax[c + k]);
+                ev = make_uint4(pack_bf2(e[0], e[1]), pack_bf2(e[2], e[3]), pack_bf2(e[4], e[5]), pack_bf2(e[6], e[7]));
+            }
+            *reinterpret_cast<uint4*>(sE + (size_t)pp * PITCH + c) = ev;
+            *reinterpret_cast<uint4*>(sV + (size_t)pp * PITCH + c) = vv;
+        }
+        __syncthreads();
+        if (threadIdx.x < HD) {
+            for (int pp = 0; pp < TP; ++pp) ssum += __bfloat162float(sE[(size_t)pp * PITCH + threadIdx.x]);
+        }
+#pragma unroll 4
+        for (int k0 = kpart * KLEN; k0 < (kpart + 1) * KLEN; k0 += 16) {
+            uint32_t a[4], b0, b1;
+            {   // A = E^T tile: matrices (m 0-7, k 0-7) (m 8-15, k 0-7) (m 0-7, k 8-15) (m 8-15, k 8-15), each stored k-major -> .trans
+                const int j = lane >> 3;
+                const int pr = k0 + (j >> 1) * 8 + (lane & 7), cc = mt * 16 + (j & 1) * 8;
+                ldsm_x4_trans(sE_s + (uint32_t)((pr * PITCH + cc) * 2), a);
+            }
+            {   // B = V tile (k x 8): matrices (k 0-7), (k 8-15)
+                const int pr = k0 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                ldsm_x2_trans(sV_s + (uint32_t)((pr * PITCH + nt * 8) * 2), b0, b1);
+            }
+            mma_bf16_16816(acc, a, b0, b1);
+        }
+        __syncthreads();
+    }
+    float* dst = pctx + (((size_t)b * heads + g) * nch + ch) * (HD * HD + HD);
+    const int gq = lane >> 2, tq = lane & 3;
+    const int r0 = mt * 16 + gq, c0 = nt * 8 + 2 * tq;
+    if constexpr (KPARTS == 1) {
+        dst[r0 * HD + c0] = acc[0]; dst[r0 * HD + c0 + 1] = acc[1];
+        dst[(r0 + 8) * HD + c0] = acc[2]; dst[(r0 + 8) * HD + c0 + 1] = acc[3];
+    } else {
+        float* sp = sPart + kpart * HD * HD;
+        sp[r0 * HD + c0] = acc[0]; sp[r0 * HD + c0 + 1] = acc[1];
+        sp[(r0 + 8) * HD + c0] = acc[2]; sp[(r0 + 8) * HD + c0 + 1] = acc[3];
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < HD * HD; idx += blockDim.x) {
+            float a2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < KPARTS; ++k) a2 += sPart[k * HD * HD + idx];
+            dst[idx] = a2;
+        }
+    }
+    if (threadIdx.x < HD) dst[HD * HD + threadIdx.x] = ssum;
+}
+
 template <int HD>
 __global__ void lin_ctx_reduce_kernel(const float* __restrict__ pctx, int nch, float* __restrict__ ctx) {
     // block = (head, b, quarter of the hd*hd entries); ctx[b][g][c1][c2] = sum_ch pctx / sum_ch S[c1].  The chunk loop is
@@ -1337,6 +1435,9 @@ int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv
 #define LIN_LAUNCH(T, HD)                                                                                          \
     do {                                                                                                           \
         lin_colmax_kernel<T><<<dim3(nch, (D + 31) / 32, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax); \
+        if (sizeof(T) == 2 && (qkv.ld % 8) == 0 && (D % 8) == 0 && (((uintptr_t)qkv.p) % 16) == 0 && !getenv("MLIC_LIN_SIMT"))                  \
+            lin_ctx_mma_kernel<HD><<<dim3(nch, heads, B), 256, 0, s>>>((const bf16*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax, pctx); \
+        else                                                                                                       \
         lin_ctx_kernel<T, HD><<<dim3(nch, heads, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv,   \
                                                                   pmax, pctx);                                     \
         lin_ctx_reduce_kernel<HD><<<dim3(heads, B, 4), 256, 0, s>>>(pctx, nch, ctx);                                  \
