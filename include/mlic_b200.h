@@ -36,8 +36,8 @@ typedef struct {
     int32_t* symbols;        /* out: [2*slices][B,C,H/16,W/32] flat, order A0,N0,A1,N1,...   (compress)           */
     int32_t* indexes;        /* out: same shape: CDF indexes into the 64-entry scale table   (compress)           */
     int32_t* z_symbols;      /* out: [B,N,H/64,W/64] round(z - median)                       (compress)           */
-    float* y;                /* out (optional tap): g_a output [B,M,H/16,W/16]                                    */
-    float* y_hat;            /* out (optional tap): quantised latent after LRP [B,M,H/16,W/16]                    */
+    float* y;                /* out (optional tap): g_a output [B,M,H/16,W/16]; INPUT when option "stages" has no g_a */
+    float* y_hat;            /* out (optional tap): quantised latent after LRP [B,M,H/16,W/16]; INPUT for stages = 4 */
     double* rd_sums;         /* out (optional, forward): [2] = { sum log2(likelihoods), sum (x - x_hat)^2 }       */
 } mlic_buffers;
 
@@ -56,7 +56,11 @@ int mlic_engine_finalize(mlic_engine* e);
 
 /* Knobs: "tensor_cores" (1 = tcgen05 implicit-GEMM in bf16 mode [default], 0 = CUDA-core GEMM only);
  *        "profile" (1 = bracket every tcgen05 GEMM launch with a CUDA-event pair on the launch stream);
- *        "fuse" (1 = depthwise 3x3 / x^2 produced inside the tcgen05 GEMM [default]); "trace" (see mlic_trace_dump). */
+ *        "fuse" (1 = depthwise 3x3 / x^2 produced inside the tcgen05 GEMM [default]); "trace" (see mlic_trace_dump);
+ *        "stages" (bit mask, default 7): 1 = g_a, 2 = h_a + EntropyBottleneck + h_s + the slice loop, 4 = g_s.  Row-band
+ *        sharding of one large image runs the three apart:  stages 1: x band -> `y` (H a multiple of 16);
+ *        stages 2 | 6: `y` is an INPUT (the gathered bands), outputs as usual plus the `y_hat` tap; stages 4: `y_hat` is an
+ *        INPUT (a band of latent rows, H = 16 x rows) -> x_hat band.  Stage subsets take device buffers (mlic_run) only. */
 int mlic_engine_set_option(mlic_engine* e, const char* name, int value);
 
 /* Device workspace needed by one call of the given mode / precision / shape. */

@@ -95,6 +95,7 @@ struct mlic_engine {
     std::map<std::string, HostT> params;
     bool finalized = false;
     int use_tc = 1;
+    int stages = 7;          // bit 0: g_a, bit 1: h_a + EntropyBottleneck + h_s + slice loop, bit 2: g_s (row-band sharding runs them apart)
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
 
     std::vector<void*> dev_allocs;
@@ -169,7 +170,7 @@ struct mlic_engine {
     // host-call staging (mlic_run_host)
     void* h_ws = nullptr; size_t h_ws_bytes = 0;
     void* h_io = nullptr; size_t h_io_bytes = 0;
-    std::map<std::array<int, 7>, size_t> ws_cache;       // mlic_workspace_bytes results
+    std::map<std::array<int, 8>, size_t> ws_cache;       // mlic_workspace_bytes results
     cudaStream_t h_stream = nullptr, h_in = nullptr, h_out = nullptr;
     std::vector<cudaEvent_t> pipe_ev;
     size_t pipe_used = 0;
@@ -939,8 +940,13 @@ struct mlic_engine {
     int run(int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* io, void* ws, size_t ws_bytes,
             cudaStream_t stream, bool dry_run, const HostPipe* hp = nullptr) {
         if (!finalized) return fail("engine not finalized");
-        if (B <= 0 || H <= 0 || W <= 0 || (H % 64) || (W % 64)) return fail("B=%d H=%d W=%d: H and W must be positive multiples of 64", B, H, W);
         if (mode < 0 || mode > 2) return fail("bad mode %d", mode);
+        // stage subsets (row bands): g_a alone ends at the `y` tap; without g_a `y` is an INPUT; g_s alone reads `y_hat`
+        const int stg = (mode == MLIC_MODE_DECODER && stages != 4) ? (stages | 1) : stages;   // the decoder walk has no g_a
+        if (stg != 7 && stg != 1 && stg != 6 && stg != 2 && stg != 4 && stg != 3) return fail("bad stage mask %d", stages);
+        if (stg != 7 && hp) return fail("stage subsets take device buffers (mlic_run)");
+        const int hmul = (stg & 2) ? 64 : 16;         // a band of g_a / g_s rows only has to keep the 16x sampling phase
+        if (B <= 0 || H <= 0 || W <= 0 || (H % hmul) || (W % 64)) return fail("B=%d H=%d W=%d: H must be a positive multiple of %d and W of 64", B, H, W, hmul);
         bf = precision == MLIC_PREC_BF16;
         dry = dry_run; st = stream; rc = 0; launches = 0;
         if (hp && !dry) pipe_used = 0;
@@ -966,10 +972,20 @@ struct mlic_engine {
         Act hyper = view(EPW, 10 * C, 2 * Me);
         Act yhat = view(LRPW, Me, M);
 
+        if (stg == 4) {                                   // g_s alone: the quantised latent comes from the caller
+            if (!dry && !io->y_hat) return fail("stage g_s alone needs y_hat as input");
+            if (go()) { launch_nchw_to_nhwc(bf, io->y_hat, yhat, M, st); after_launch("y_hat_in"); }
+            g_s(yhat, io->x_hat);
+            return rc;
+        }
         if (mode != MLIC_MODE_DECODER) {
-            if (!dry && !io->x) return fail("x is NULL");
             size_t mark = ws_off;
-            if (hp && hp->hx && head_fused() && !dry) {
+            if (!(stg & 1)) {                             // g_a ran elsewhere (its row bands were gathered): y is an input
+                if (!dry && !io->y) return fail("stages without g_a need y as input");
+                Act yin; yin.p = y32; yin.B = B; yin.H = h; yin.W = w; yin.C = M; yin.ld = M;
+                if (go()) { launch_nchw_to_nhwc(0, io->y, yin, M, st); after_launch("y_in"); }
+            } else if (!dry && !io->x) { return fail("x is NULL");
+            } else if (hp && hp->hx && head_fused() && !dry) {
                 // host call: upload image by image, g_a on image b as soon as it has landed
                 const size_t img = (size_t)3 * H * W;
                 std::vector<cudaEvent_t> ev(B);
@@ -994,6 +1010,8 @@ struct mlic_engine {
                 g_a(x, y32);
             }
             ws_off = mark;
+            if ((stg & 1) && io->y && go()) { launch_nhwc_f32_to_nchw(y32, M, B, h, w, M, io->y, st); after_launch("y_tap"); }
+            if (!(stg & 2)) return rc;                    // g_a alone
             Act ya = act(B, h, w, M);
             if (go()) { launch_copy_f32_to_act(bf, y32, M, ya, st); after_launch("copy_y"); }
             Act z = act(B, hz, wz, N);
@@ -1004,7 +1022,6 @@ struct mlic_engine {
                 after_launch("entropy_bottleneck");
             }
             ws_off = mark;
-            if (io->y && go()) { launch_nhwc_f32_to_nchw(y32, M, B, h, w, M, io->y, st); after_launch("y_tap"); }
         } else if (go()) {
             launch_fill_zero(zh.p, (size_t)B * hz * wz * zh.ld * esz(), st);      // z_hat = 0 (mlicpp.py:390-394)
         }
@@ -1060,7 +1077,7 @@ struct mlic_engine {
             if (hp->hy_lik && io->y_likelihoods) cudaMemcpyAsync(hp->hy_lik, io->y_likelihoods, npix * M * 4, cudaMemcpyDeviceToHost, hp->s_out);
             if (hp->hz_lik && io->z_likelihoods) cudaMemcpyAsync(hp->hz_lik, io->z_likelihoods, (size_t)B * hz * wz * N * 4, cudaMemcpyDeviceToHost, hp->s_out);
         }
-        if (hp && hp->hx_hat && io->x_hat && go()) {
+        if (hp && hp->hx_hat && io->x_hat && go()) {          // (hp implies all stages)
             const size_t img = (size_t)3 * H * W;
             for (int b = 0; b < B && !rc; ++b) {
                 Act yb = yhat; yb.B = 1; yb.p = (uint8_t*)yhat.p + (size_t)b * h * w * yhat.ld * esz();
@@ -1070,8 +1087,8 @@ struct mlic_engine {
                 cudaStreamWaitEvent(hp->s_out, ev, 0);
                 cudaMemcpyAsync(hp->hx_hat + b * img, io->x_hat + b * img, img * 4, cudaMemcpyDeviceToHost, hp->s_out);
             }
-        } else if (io->x_hat || dry) g_s(yhat, io->x_hat);
-        if (mode == MLIC_MODE_FORWARD && (io->rd_sums || dry)) {
+        } else if ((stg & 4) && (io->x_hat || dry)) g_s(yhat, io->x_hat);
+        if (mode == MLIC_MODE_FORWARD && (stg & 4) && (io->rd_sums || dry)) {
             double* partial = (double*)ws_alloc(RD_BLOCKS * sizeof(double));
             if (go() && io->rd_sums) {
                 if (!io->x_hat || !io->y_likelihoods || !io->z_likelihoods) return fail("rd_sums needs x_hat and both likelihood buffers");
@@ -1129,12 +1146,13 @@ int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
     if (!strcmp(name, "profile")) { e->profile = value; return 0; }
     if (!strcmp(name, "fuse")) { e->fuse = value; return 0; }
     if (!strcmp(name, "trace")) { e->trace = value; return 0; }
+    if (!strcmp(name, "stages")) { e->stages = value & 7; return 0; }
     return fail("unknown option '%s'", name);
 }
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {
     if (!e || !bytes) return fail("bad arguments");
     // the dry walk costs ~1 ms of host time: remember its result per call geometry (finalize() clears the cache)
-    const std::array<int, 7> key = {mode, precision, B, H, W, e->use_tc, e->fuse};
+    const std::array<int, 8> key = {mode, precision, B, H, W, e->use_tc, e->fuse, e->stages};
     auto it = e->ws_cache.find(key);
     if (it != e->ws_cache.end()) { *bytes = it->second; return 0; }
     int r = e->run(mode, precision, B, H, W, 1.0f, nullptr, nullptr, 0, nullptr, true);

@@ -255,24 +255,32 @@ class MLICPlusPlus(nn.Module):
     def _gain(self, stage, s, inputscale, absolute=False):
         return 0.0
 
-    def _run(self, mode, x, B, H, W, gain=0.0, want=()):
-        """One engine call.  x: CUDA tensor (device path) or CPU tensor (host path through mlic_run_host)."""
-        if H % 64 or W % 64:
+    def _run(self, mode, x, B, H, W, gain=0.0, want=(), stages=7, y=None, y_hat=None):
+        """One engine call.  x: CUDA tensor (device path) or CPU tensor (host path through mlic_run_host).
+        stages: bit mask of include/mlic_b200.h option "stages" (1 g_a | 2 entropy model | 4 g_s); `y` / `y_hat` are the
+        device INPUTS of the calls that start after g_a / at g_s (row-band sharding, mlic_b200/dist.py)."""
+        hmul = 64 if stages & 2 else 16
+        if H % hmul or W % 64:
             raise ValueError("H and W must be multiples of 64 (the reference pads, utils/testing.py:130-137)")
         if not torch.cuda.is_available():
             raise _lib.MlicError("mlic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         host = x is not None and not x.is_cuda
-        dev = torch.device("cuda", torch.cuda.current_device()) if (host or x is None) else x.device
+        src = x if x is not None else (y if y is not None else y_hat)
+        dev = torch.device("cuda", torch.cuda.current_device()) if (host or src is None) else src.device
+        if stages != 7 and host:
+            raise _lib.MlicError("stage subsets run on device tensors")
         L = self._sync_engine(dev)
         _lib.check(L.mlic_engine_set_option(self._engine, b"tensor_cores", 1 if self.tensor_cores else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"profile", 1 if self._profile else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"fuse", 1 if self.fuse else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"trace", 1 if self._trace else 0))
+        _lib.check(L.mlic_engine_set_option(self._engine, b"stages", int(stages)))
         prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
         odev = "cpu" if host else dev
         h, w, hz, wz = H // 16, W // 16, H // 64, W // 64
         out = {}
         buf = _lib.Buffers()
+        keep = []
         if x is not None:
             x = x.detach().to(torch.float32).contiguous()
             buf.x = x.data_ptr()
@@ -282,20 +290,33 @@ class MLICPlusPlus(nn.Module):
             out[name] = t
             setattr(buf, name, t.data_ptr())
 
-        new("x_hat", (B, 3, H, W))
-        if mode == _lib.MODE_FORWARD:
+        def given(name, t):
+            t = t.detach().to(dev, torch.float32).contiguous()
+            if tuple(t.shape) != (B, self.M, h, w):
+                raise ValueError(f"{name} must be [{B},{self.M},{h},{w}], got {tuple(t.shape)}")
+            keep.append(t)
+            setattr(buf, name, t.data_ptr())
+
+        if stages & 4:
+            new("x_hat", (B, 3, H, W))
+        if mode == _lib.MODE_FORWARD and stages & 2:
             new("y_likelihoods", (B, self.M, h, w))
             new("z_likelihoods", (B, self.N, hz, wz))
-            if "rd_sums" in want:
+            if "rd_sums" in want and stages == 7:
                 new("rd_sums", (2,), torch.float64)
-        if mode == _lib.MODE_COMPRESS:
+        if mode == _lib.MODE_COMPRESS and stages & 2:
             n = 2 * self.slice_num * B * self.slice_ch * h * (w // 2)
             new("symbols", (n,), torch.int32)
             new("indexes", (n,), torch.int32)
             new("z_symbols", (B, self.N, hz, wz), torch.int32)
-        for tap in ("y", "y_hat"):
-            if tap in want:
-                new(tap, (B, self.M, h, w))
+        if y is not None:
+            given("y", y)
+        elif "y" in want:
+            new("y", (B, self.M, h, w))
+        if y_hat is not None:
+            given("y_hat", y_hat)
+        elif "y_hat" in want:
+            new("y_hat", (B, self.M, h, w))
         with torch.cuda.device(dev):
             if host:
                 _lib.check(L.mlic_run_host(self._engine, mode, prec, B, H, W, float(gain), C.byref(buf), 1))
@@ -309,10 +330,36 @@ class MLICPlusPlus(nn.Module):
                     ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
                     self._ws[key] = ws
                 stream = torch.cuda.current_stream(dev).cuda_stream
-                _lib.check(L.mlic_run(self._engine, mode, prec, B, H, W, float(gain), C.byref(buf), C.c_void_p(ws.data_ptr()),
-                                      ws.numel(), C.c_void_p(stream)))
+                try:
+                    _lib.check(L.mlic_run(self._engine, mode, prec, B, H, W, float(gain), C.byref(buf), C.c_void_p(ws.data_ptr()),
+                                          ws.numel(), C.c_void_p(stream)))
+                finally:
+                    if stages != 7:
+                        L.mlic_engine_set_option(self._engine, b"stages", 7)
+                for t in keep:                       # the inputs are read by kernels queued on this stream
+                    t.record_stream(torch.cuda.current_stream(dev))
         self.last_launch_count = int(L.mlic_last_launch_count(self._engine))
         return out
+
+    # row-band stage calls (mlic_b200/dist.py).  H is the height of the band in image rows.
+    @torch.no_grad()
+    def analysis_band(self, x):
+        """g_a alone on a band of image rows (a multiple of 16) -> y [B,M,rows/16,W/16] fp32."""
+        B, _, H, W = x.shape
+        return self._run(_lib.MODE_FORWARD, x, B, H, W, 0.0, ("y",), stages=1)["y"]
+
+    @torch.no_grad()
+    def entropy_from_y(self, y, gain=0.0):
+        """h_a, EntropyBottleneck, h_s and the slice loop on a whole latent -> (likelihoods dict, y_hat)."""
+        B, _, h, w = y.shape
+        o = self._run(_lib.MODE_FORWARD, None, B, 16 * h, 16 * w, gain, ("y_hat",), stages=2, y=y)
+        return {"y_likelihoods": o["y_likelihoods"], "z_likelihoods": o["z_likelihoods"]}, o["y_hat"]
+
+    @torch.no_grad()
+    def synthesis_band(self, y_hat):
+        """g_s alone on a band of latent rows -> x_hat [B,3,16*rows,16*w]."""
+        B, _, h, w = y_hat.shape
+        return self._run(_lib.MODE_FORWARD, None, B, 16 * h, 16 * w, 0.0, (), stages=4, y_hat=y_hat)["x_hat"]
 
     # ------------------------------------------------------------------ the reference's public methods
     @torch.no_grad()
