@@ -35,7 +35,7 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("MLIC_NVCC_EXTRA", "").split()   # development: -D switches
     objs = []
     procs = []
     for src in SOURCES:

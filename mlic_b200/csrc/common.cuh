@@ -51,7 +51,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return y;
 }
 #ifndef MLIC_GELU_FORM
-#define MLIC_GELU_FORM 1
+#define MLIC_GELU_FORM 0
 #endif
 __device__ __forceinline__ float2 gelu2(float2 x) {
     float2 t = __fmul2_rn(x, x);

@@ -208,6 +208,7 @@ struct TcParams {
     int epi_vec;            // STORE_DIRECT: 16-byte epilogue accesses are legal for every pointer involved
     int ld_vec;             // 16-byte loads of the residual / GDN operand are legal
     int store_mode;
+    int esplit;             // STORE_TMA: epilogue warp groups per 64-column block (narrow GEMMs: 4 or 2 groups share a block, 16 or 32 columns each)
     int nstg;               // STORE_TMA: 16 KB staging buffers behind the stage ring (ring slots x buffers per block)
     int b_resident;         // 1: the whole weight matrix (all K chunks x BN rows, tilesN == 1) is loaded into shared
                             //    memory once per CTA; the ring then carries only the A patches
@@ -351,7 +352,7 @@ __device__ __forceinline__ void epi_math8(const Epi& e, const float* __restrict_
         for (int j = 0; j < 4; ++j) v[j] = gelu2(v[j]);
     } else if constexpr (ACT == ACT_HALF_TANH) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = make_float2(0.5f * tanhf(v[j].x), 0.5f * tanhf(v[j].y));
+        for (int j = 0; j < 4; ++j) v[j] = make_float2(0.5f * tanh_approx(v[j].x), 0.5f * tanh_approx(v[j].y));      // MUFU.TANH, 2^-11 relative: below the bf16 rounding of the LRP output
     }
     if (!row.keep_post) {
 #pragma unroll
@@ -453,7 +454,10 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     const long long t_start = clock64();
     long long w0c = 0, w1c = 0, w2c = 0, w3c = 0;
 #define TIMED_WAIT(acc, bar, par) do { if (dbg) { long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
-#define TIMED_SPIN(acc, bar, par) do { if (dbg) { long long _t = clock64(); mbar_wait<false>(bar, par); acc += clock64() - _t; } else mbar_wait<false>(bar, par); } while (0)
+    // single-thread roles (TMA issue, MMA issue): spin where the tensor pipe is the pace (plain GEMMs: wake-up latency counts), park
+    // in the fused-producer kernels, which are issue-slot bound (the two polling loops were 20 % of their warp instructions)
+    constexpr bool SPIN_PARKS = PROD != PROD_TMA;
+#define TIMED_SPIN(acc, bar, par) do { if (dbg) { long long _t = clock64(); mbar_wait<SPIN_PARKS>(bar, par); acc += clock64() - _t; } else mbar_wait<SPIN_PARKS>(bar, par); } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * 128;
@@ -492,7 +496,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
             for (int s = 0; s < TC_RAW_SLOTS; ++s) mbar_init(&raw_empty[s], TC_PROD_WARPS);
         }
         // accumulator release: one arrival per epilogue warp that reads it (TMA-store mode: 4 warps per 64-column block)
-        const uint32_t nrel = p.store_mode == STORE_TMA ? 4u * (uint32_t)((p.BN + 63) / 64) : (uint32_t)NEPI;
+        const uint32_t nrel = p.store_mode == STORE_TMA ? 4u * (uint32_t)((p.BN + 63) / 64) * (uint32_t)p.esplit : (uint32_t)NEPI;
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], nrel); }
         mbar_init(&bres_bar, 1);
         for (int i = 0; i < 8; ++i) mbar_init(&stg_bar[i >> 1][i & 1], 1);
@@ -732,7 +736,12 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
         const uint32_t nring = p.store_mode == STORE_TMA ? (uint32_t)(p.nstg / (((p.BN + 63) / 64) * per)) : 1u;   // slots per group
         uint32_t blk = 0;
         int it = 0;
-        const bool idle = p.store_mode == STORE_TMA && cq * 64 >= p.BN;     // this warp group owns no columns
+        // narrow GEMMs (BN <= 128): `esplit` warp groups share one 64-column block (its staging slot, named barrier and store issuer),
+        // each taking 64 / esplit columns, so all 16 epilogue warps work instead of 4 or 8 (the epilogue of a 128 x 64 tile was
+        // 2.9 k clocks on 4 warps against 1 k clocks of MMA: tools/em_bench.py)
+        const int esplit = p.store_mode == STORE_TMA ? p.esplit : 1;
+        const int eb = cq / esplit, esub = cq - eb * esplit;                // 64-column block of this group, its share of it
+        const bool idle = p.store_mode == STORE_TMA && eb * 64 >= p.BN;     // this warp group owns no columns
         // shift-sum mode: the (interior pixel, output) pairs this thread sums in phase 2 are the same for every tile
         // (packed into one word per pair: py[0:4) px[4:7) n[7:11) ch[11:13) rr[13] s[14] ok[15] pofs[16:32))
         uint32_t ss_pk[2] = {0u, 0u};
@@ -773,19 +782,21 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 // One 64-column block per warp GROUP (4 warps = the 4 TMEM lane quarters): group cq owns columns
                 // [64 cq, 64 cq + 64) of every tile, its own swizzled 16 KB staging slot(s), its own named barrier and its
                 // own TMA-store issuer, so the blocks of a tile drain concurrently instead of one after the other.
-                const int kb = cq * 64;
+                const int kb = eb * 64;
                 if (kb < p.BN) {
                     int g = 0, ocb = n0 + kb;                       // the whole block lies in one pixel-shuffle group
                     if (e.shuffle) { const int Cq = e.N >> 2; g = ocb / Cq; ocb -= g * Cq; }
-                    const bool gissuer = (q == 0 && lane == 0);
-                    uint8_t* sb = stg + (size_t)((cq * nring + (blk % nring)) * per) * TC_STG_BYTES;
+                    const bool gissuer = (esub == 0 && q == 0 && lane == 0);
+                    const int gthreads = 128 * esplit;
+                    const int pr0 = esub * (4 / esplit), pr1 = pr0 + 4 / esplit;
+                    uint8_t* sb = stg + (size_t)((eb * nring + (blk % nring)) * per) * TC_STG_BYTES;
                     const uint32_t sb_s = smem_u32(sb);
                     long long tq0 = dbg ? clock64() : 0;
                     if (nring == 1) {               // single slot: this group's previous store must have drained it
                         if (gissuer) tma_store_wait_read(0);
-                        asm volatile("bar.sync %0, 128;" ::"r"(cq + 1) : "memory");
+                        asm volatile("bar.sync %0, %1;" ::"r"(eb + 1), "r"(gthreads) : "memory");
                     }
-                    uint64_t* sbar = &stg_bar[cq][blk % nring];
+                    uint64_t* sbar = &stg_bar[eb][blk % nring];
                     if constexpr (RES || GDN != GDN_NONE) {
                         // Operand prefetch (no pixel shuffle in this mode): the residual / GDN-operand block of this tile is one TMA
                         // box each, landing in the staging slot in the swizzled layout of the output block (out-of-range pixels and
@@ -804,14 +815,14 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     if constexpr (RES || GDN != GDN_NONE) mbar_wait(sbar, (blk / nring) & 1u);
                     long long tq1 = dbg ? clock64() : 0;
 #pragma unroll 1
-                    for (int pr = 0; pr < 4; ++pr) {
+                    for (int pr = pr0; pr < pr1; ++pr) {
                         // two 8-column groups are fetched from TMEM before any arithmetic
                         const int c = kb + pr * 16;
                         uint32_t raw[2][8];
                         tmem_ld8(trow + (uint32_t)c, raw[0]);
                         tmem_ld8(trow + (uint32_t)(c + 8), raw[1]);
                         tmem_ld_wait();
-                        if (pr == 3) {              // accumulator fully read by this warp: hand the TMEM stage back
+                        if (pr == pr1 - 1) {        // accumulator fully read by this warp: hand the TMEM stage back
                             tcgen05_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -837,7 +848,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     // two slots: after this barrier the group's OTHER slot is rewritten next tile; its store must have drained
                     if (nring > 1 && gissuer) tma_store_wait_read(0);
-                    asm volatile("bar.sync %0, 128;" ::"r"(cq + 1) : "memory");
+                    asm volatile("bar.sync %0, %1;" ::"r"(eb + 1), "r"(gthreads) : "memory");
                     if (gissuer && !(p.debug & 1)) {
                         tma_store_4d(&tm.o[g], sb, ocb, w0, h0, img);
                         if (e.out2) tma_store_4d(&tm.o2, sb + TC_STG_BYTES, ocb, w0, h0, img);
@@ -1210,7 +1221,11 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     const int ksteps = p.ks * p.ks * p.kchunks;
     const int bres_bytes = ksteps * p.BN * 128;
     const int per = (e.out2 || e.gdn) ? 2 : 1;
-    const int nact = (p.BN + 63) / 64;          // warp groups that own a 64-column block
+    const int nact = (p.BN + 63) / 64;          // 64-column blocks of a tile (each owned by `esplit` warp groups)
+    {
+        static const int es_mode = getenv("MLIC_ESPLIT") ? atoi(getenv("MLIC_ESPLIT")) : 1;      // development: 0 = one group per block
+        p.esplit = (es_mode && c.prod == PROD_TMA && p.store_mode == STORE_TMA) ? (nact == 1 ? 4 : (nact == 2 ? 2 : 1)) : 1;
+    }
     // Shared-memory plan.  Small weight matrices (the 192x192 pointwise / GDN GEMMs) may stay resident (no per-tile B
     // reload); every active warp group owns `ring` staging slots of `per` 16 KB buffers; the rest is the operand ring.
     if (p.halo && !(p.BN >= e.N && bres_bytes <= 120 * 1024)) { snprintf(g_tc_err, sizeof g_tc_err, "halo plan: weights not resident (BN=%d)", p.BN); return 8; }
