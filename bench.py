@@ -276,9 +276,15 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            mps, times = cpu_forward_mps((576, 960), 1, threads)
+            # bounded sample: one whole 1920x1088 image of the workload, run until ~15 s of CPU time are spent (at least twice)
+            mps, times = cpu_forward_mps((H, W), 2, threads)
+            while sum(times) < 15.0 and len(times) < 8:
+                m2, t2 = cpu_forward_mps((H, W), 1, threads)
+                times += t2
+                mps = max(mps, m2)
             cpu = {"value": mps, "unit": "MP/s", "cores": threads, "kind": "port",
-                   "sample": f"1 image 960x576 (crop of the 1920x1088 workload), 1 run of {times[0]:.1f} s, fp32 torch CPU"}
+                   "sample": f"1 image 1920x1088 of the workload per run, best of {len(times)} runs ({sum(times):.1f} s of CPU work), "
+                             f"fp32 torch CPU, {threads} threads"}
         line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",

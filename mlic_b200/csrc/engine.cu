@@ -936,6 +936,14 @@ struct mlic_engine {
         ws_off = mark;
     }
 
+    // host-buffer calls: images per upload / g_a / g_s / download group (copies of group k overlap the kernels of group k -+ 1; one
+    // image per group keeps the copy engines busiest but runs the transforms at their least efficient launch size)
+    static int pipe_group(int B) {
+        static const int forced = getenv("MLIC_PIPE_GROUP") ? atoi(getenv("MLIC_PIPE_GROUP")) : 0;
+        if (forced > 0) return std::min(forced, B);
+        return B >= 16 ? 4 : (B >= 8 ? 2 : 1);
+    }
+
     // ------------------------------------------------------------------ the whole call
     int run(int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* io, void* ws, size_t ws_bytes,
             cudaStream_t stream, bool dry_run, const HostPipe* hp = nullptr) {
@@ -986,17 +994,20 @@ struct mlic_engine {
                 if (go()) { launch_nchw_to_nhwc(0, io->y, yin, M, st); after_launch("y_in"); }
             } else if (!dry && !io->x) { return fail("x is NULL");
             } else if (hp && hp->hx && head_fused() && !dry) {
-                // host call: upload image by image, g_a on image b as soon as it has landed
+                // host call: upload in groups of `pg` images, g_a on a group as soon as it has landed
                 const size_t img = (size_t)3 * H * W;
-                std::vector<cudaEvent_t> ev(B);
-                for (int b = 0; b < B; ++b) {
-                    cudaMemcpyAsync(const_cast<float*>(io->x) + b * img, hp->hx + b * img, img * 4, cudaMemcpyHostToDevice, hp->s_in);
-                    ev[b] = pipe_event();
-                    cudaEventRecord(ev[b], hp->s_in);
+                const int pg = pipe_group(B);
+                std::vector<cudaEvent_t> ev;
+                for (int b = 0; b < B; b += pg) {
+                    const int nb = std::min(pg, B - b);
+                    cudaMemcpyAsync(const_cast<float*>(io->x) + b * img, hp->hx + b * img, nb * img * 4, cudaMemcpyHostToDevice, hp->s_in);
+                    ev.push_back(pipe_event());
+                    cudaEventRecord(ev.back(), hp->s_in);
                 }
-                for (int b = 0; b < B && !rc; ++b) {
-                    cudaStreamWaitEvent(st, ev[b], 0);
-                    Act x; x.p = nullptr; x.B = 1; x.H = H; x.W = W; x.C = 3; x.ld = 3;
+                for (int b = 0, gi = 0; b < B && !rc; b += pg, ++gi) {
+                    const int nb = std::min(pg, B - b);
+                    cudaStreamWaitEvent(st, ev[gi], 0);
+                    Act x; x.p = nullptr; x.B = nb; x.H = H; x.W = W; x.C = 3; x.ld = 3;
                     g_a(x, y32 + (size_t)b * h * w * M, io->x + b * img);
                 }
             } else if (head_fused()) {            // the head kernel reads the NCHW image directly
@@ -1079,13 +1090,15 @@ struct mlic_engine {
         }
         if (hp && hp->hx_hat && io->x_hat && go()) {          // (hp implies all stages)
             const size_t img = (size_t)3 * H * W;
-            for (int b = 0; b < B && !rc; ++b) {
-                Act yb = yhat; yb.B = 1; yb.p = (uint8_t*)yhat.p + (size_t)b * h * w * yhat.ld * esz();
+            const int pg = pipe_group(B);
+            for (int b = 0; b < B && !rc; b += pg) {
+                const int nb = std::min(pg, B - b);
+                Act yb = yhat; yb.B = nb; yb.p = (uint8_t*)yhat.p + (size_t)b * h * w * yhat.ld * esz();
                 g_s(yb, io->x_hat + b * img);
                 cudaEvent_t ev = pipe_event();
                 cudaEventRecord(ev, st);
                 cudaStreamWaitEvent(hp->s_out, ev, 0);
-                cudaMemcpyAsync(hp->hx_hat + b * img, io->x_hat + b * img, img * 4, cudaMemcpyDeviceToHost, hp->s_out);
+                cudaMemcpyAsync(hp->hx_hat + b * img, io->x_hat + b * img, nb * img * 4, cudaMemcpyDeviceToHost, hp->s_out);
             }
         } else if ((stg & 4) && (io->x_hat || dry)) g_s(yhat, io->x_hat);
         if (mode == MLIC_MODE_FORWARD && (stg & 4) && (io->rd_sums || dry)) {

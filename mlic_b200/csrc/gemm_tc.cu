@@ -975,7 +975,9 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
         if (warp == 0) { d[0] = (unsigned long long)(clock64() - t_start); d[1] = (unsigned long long)w0c; }
         if (warp == 1) { d[2] = (unsigned long long)w1c; d[3] = (unsigned long long)w2c; }
         if (PROD != PROD_TMA && warp == 4) { d[6] = (unsigned long long)w0c; d[7] = (unsigned long long)w1c; }
-        if (PROD != PROD_TMA && warp == EW0) { d[4] = (unsigned long long)w3c; d[5] = (unsigned long long)(clock64() - t_start); }
+        if (PROD != PROD_TMA && warp == EW0) { d[4] = (unsigned long long)w3c; d[5] = (unsigned long long)(clock64() - t_start);
+                         dbg[(size_t)gridDim.x * 8 + blockIdx.x] = (unsigned long long)w2c; dbg[(size_t)gridDim.x * 9 + blockIdx.x] = (unsigned long long)w0c;
+                         dbg[(size_t)gridDim.x * 10 + blockIdx.x] = (unsigned long long)w1c; }
         if (PROD == PROD_TMA && warp == EW0) { d[4] = (unsigned long long)w3c; d[5] = (unsigned long long)(clock64() - t_start);
                          d[6] = (unsigned long long)w0c; d[7] = (unsigned long long)w1c; dbg[(size_t)gridDim.x * 8 + blockIdx.x] = (unsigned long long)w2c; }
     }
@@ -1377,20 +1379,24 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     unsigned long long* dbg = nullptr;
     if (p.debug & 32) {             // development: per-role wait clocks of the first launches, printed to stderr
         static unsigned long long* dbuf = nullptr;
-        if (!dbuf) cudaMalloc((void**)&dbuf, 148 * 9 * sizeof(unsigned long long));
-        cudaMemsetAsync(dbuf, 0, 148 * 9 * sizeof(unsigned long long), s);
+        if (!dbuf) cudaMalloc((void**)&dbuf, 148 * 11 * sizeof(unsigned long long));
+        cudaMemsetAsync(dbuf, 0, 148 * 11 * sizeof(unsigned long long), s);
         dbg = dbuf;
     }
     fn<<<grid, c.prod == PROD_TMA ? TC_THREADS : TC_FUSED_THREADS, smem, s>>>(tm, p, e, dbg);
     if (dbg) {
         static int printed = 0;
-        unsigned long long h[148 * 9];
+        unsigned long long h[148 * 11];
         cudaStreamSynchronize(s);
         cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
         if (printed++ < 3 || (p.debug & 64)) {
             double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (unsigned i = 0; i < grid.x; ++i) { for (int j = 0; j < 8; ++j) a[j] += (double)h[i * 8 + j] / grid.x; a[8] += (double)h[grid.x * 8 + i] / grid.x; }
-            if (c.prod) fprintf(stderr, "[tc dbg] prod=%d compute warp 4: wait-raw %.0f wait-stage-free %.0f\n", c.prod, a[6], a[7]);
+            if (c.prod) {
+                double b9 = 0, b10 = 0;
+                for (unsigned i = 0; i < grid.x; ++i) { b9 += (double)h[grid.x * 9 + i] / grid.x; b10 += (double)h[grid.x * 10 + i] / grid.x; }
+                fprintf(stderr, "[tc dbg] prod=%d compute warp 4: wait-raw %.0f wait-stage-free %.0f | first epilogue warp: drain+operand wait %.0f math %.0f fence+barrier+store %.0f\n", c.prod, a[6], a[7], b9, b10, a[8]);
+            }
             else fprintf(stderr, "[tc dbg] epilogue warp 4: drain-wait %.0f math %.0f fence+barrier+store %.0f\n", a[6], a[7], a[8]);
             fprintf(stderr, "[tc dbg] BN=%d ksteps=%d stages=%d nstg=%d bres=%d tiles/cta=%.1f | clocks: total %.0f prod-wait-empty %.0f mma-wait-full %.0f mma-wait-accempty %.0f epi-wait-accfull %.0f epi-total %.0f\n",
                     p.BN, ksteps, p.stages, p.nstg, p.b_resident, (double)p.ntiles / grid.x, a[0], a[1], a[2], a[3], a[4], a[5]);

@@ -155,6 +155,25 @@ def test_full_size_properties(precision):
     assert c["symbols"].numel() == 2 * 10 * 32 * 68 * 60 and int((c["symbols"] != 0).sum()) > 1000
 
 
+def test_bench_batch_of_32_images_equals_single_image_runs():
+    """bench.py's step (32 images of 1920x1088 per launch: 6.4 GB activations, offsets beyond 2^32 bytes): the first, a middle
+    and the last image of the batch must come out exactly as when they are run alone."""
+    import mlic_b200
+    name, H, W, B = "MLICPP_L", 1088, 1920, 32
+    net = mlic_b200.get_model(name)
+    net.load_state_dict(weights.seeded_state_dict(net.state_dict(), 1234, y_gain=8.0, sigma_spread=3.0))
+    net.update(force=True)
+    net = net.cuda().set_precision("bf16")
+    x = weights.synthetic_image(B, H, W, seed=9, kind="rand").cuda()
+    big = net(x, taps=("y_hat",))
+    for b in (0, 13, 31):
+        one = net(x[b:b + 1], taps=("y_hat",))
+        assert torch.equal(one["y_hat"], big["y_hat"][b:b + 1]), b
+        assert torch.equal(one["x_hat"], big["x_hat"][b:b + 1]), b
+        assert torch.equal(one["likelihoods"]["y_likelihoods"], big["likelihoods"]["y_likelihoods"][b:b + 1]), b
+        assert torch.equal(one["likelihoods"]["z_likelihoods"], big["likelihoods"]["z_likelihoods"][b:b + 1]), b
+
+
 def test_host_buffer_call_matches_device_call():
     g, sd, x = load_case("MLICPP_S", 2, 64, 128)
     net = build_model("MLICPP_S", sd, "cuda").set_precision("fp32")
