@@ -25,7 +25,7 @@ typedef struct mlic_engine mlic_engine;
 
 enum { MLIC_KIND_BASE = 0, MLIC_KIND_SD = 1, MLIC_KIND_VBR = 2 };   /* MLICPlusPlus / ...SD / ...Vbr */
 enum { MLIC_PREC_FP32 = 0, MLIC_PREC_BF16 = 1 };                    /* validation mode / fast mode   */
-enum { MLIC_MODE_FORWARD = 0, MLIC_MODE_COMPRESS = 1, MLIC_MODE_DECODER = 2 };
+enum { MLIC_MODE_FORWARD = 0, MLIC_MODE_COMPRESS = 1, MLIC_MODE_DECODER = 2, MLIC_MODE_DECOMPRESS = 3 /* mlic_decompress only */ };
 
 /* Buffers of one call.  Unused outputs may be NULL.  B images of H x W (multiples of 64). */
 typedef struct {
@@ -79,6 +79,19 @@ int mlic_run(mlic_engine* e, int mode, int precision, int B, int H, int W, float
  * pointers are page-locked (async copies). */
 int mlic_run_host(mlic_engine* e, int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* host,
                   int pinned);
+
+/* decompress(strings, shape) (models/mlicpp.py:292-378; VBR models/mlicpp_vbr.py decompress with `gain`): the decoder-side
+ * walk with the range decoder in the slice loop.  `z_symbols` (device, [B,N,H/64,W/64]) are the values the caller decoded
+ * from z_strings (EntropyBottleneck.decompress before `+ medians`); `y_stream` (host) is the single y string of the batch.
+ * Per half-slice the engine writes the CDF index list (utils/ckbd.py:195-229 order), copies it to a pinned mailbox, runs
+ * mlic_rans_decode_stream on the calling thread against the tables of mlic_engine_set_cdf (gaussian_conditional's
+ * _quantized_cdf / _cdf_length / _offset), and copies the symbols back: 2 x slice_num stream synchronisations per call.
+ * x_hat: device [B,3,H,W]; y_hat: optional device tap.  workspace: mlic_workspace_bytes(mode = MLIC_MODE_DECOMPRESS). */
+int mlic_engine_set_cdf(mlic_engine* e, const int32_t* cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                        int n_tables);
+int mlic_decompress(mlic_engine* e, int precision, int B, int H, int W, float gain, const uint8_t* y_stream, size_t y_bytes,
+                    const int32_t* z_symbols, float* x_hat, float* y_hat, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream);
 
 /* Number of kernels the engine launched in the last mlic_run / mlic_run_host call. */
 int64_t mlic_last_launch_count(const mlic_engine* e);
@@ -154,6 +167,22 @@ int mlic_ga_head(const float* x, int B, int H, int W, const float* dw_weight, co
  * engine's own exp(linspace(log .11, log 256, 64)). */
 int mlic_gaussian_conditional(const float* y, const float* scales, const float* means, size_t n, const float* scale_table64,
                               float* y_hat, float* lik, int32_t* sym, int32_t* idx, void* cuda_stream);
+
+/* ---- host entropy coder (mlic_b200/csrc/rans.cpp): the range-ANS coder behind compress() / decompress().
+ * Replaces compressai.ans.BufferedRansEncoder.encode_with_indexes + flush, RansDecoder.set_stream + decode_stream and
+ * compressai._CXX.pmf_to_quantized_cdf as the reference calls them (MLIC++/models/mlicpp.py:212-216,279-280,303-304;
+ * MLIC++/utils/ckbd.py:195-229).  Tables: `cdfs` is [n_tables][cdf_stride] int32 (16-bit precision), `cdf_sizes[t]` the
+ * used length of row t, `offsets[t]` the symbol value of its first bin.  All return 0 on success. */
+typedef struct mlic_rans_decoder mlic_rans_decoder;
+int mlic_pmf_to_quantized_cdf(const float* pmf, int n, int32_t* cdf_out /* n + 1 */);
+size_t mlic_rans_encode_bound(size_t n_symbols);
+int mlic_rans_encode(const int32_t* symbols, const int32_t* indexes, size_t n, const int32_t* cdfs, int cdf_stride,
+                     const int32_t* cdf_sizes, const int32_t* offsets, int n_tables, uint8_t* out, size_t out_cap,
+                     size_t* out_bytes);
+mlic_rans_decoder* mlic_rans_decoder_create(const uint8_t* stream, size_t nbytes);
+void mlic_rans_decoder_destroy(mlic_rans_decoder* d);
+int mlic_rans_decode_stream(mlic_rans_decoder* d, const int32_t* indexes, size_t n, const int32_t* cdfs, int cdf_stride,
+                            const int32_t* cdf_sizes, const int32_t* offsets, int n_tables, int32_t* out);
 
 const char* mlic_last_error(void);
 const char* mlic_version(void);

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmlic_b200.so")
-SOURCES = ["kernels.cu", "gemm_tc.cu", "engine.cu"]
+SOURCES = ["kernels.cu", "gemm_tc.cu", "engine.cu", "rans.cpp"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "mlic_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false"]
@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

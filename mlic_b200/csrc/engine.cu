@@ -95,6 +95,12 @@ struct mlic_engine {
     std::map<std::string, HostT> params;
     bool finalized = false;
     int use_tc = 1;
+    // decompress (MLIC_MODE_DECOMPRESS): quantised CDF tables of gaussian_conditional and the pinned mailbox of the range decoder
+    std::vector<int32_t> cdf_tab, cdf_sizes, cdf_offsets;
+    int cdf_stride = 0;
+    mlic_rans_decoder* rans = nullptr;     // attached for the duration of one mlic_decompress call
+    int32_t* h_mail = nullptr;       // pinned: [indexes | symbols] of one half-slice
+    size_t h_mail_n = 0;
     int stages = 7;          // bit 0: g_a, bit 1: h_a + EntropyBottleneck + h_s + slice loop, bit 2: g_s (row-band sharding runs them apart)
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
 
@@ -184,6 +190,7 @@ struct mlic_engine {
         for (cudaEvent_t ev : ev_pool) cudaEventDestroy(ev);
         if (h_ws) cudaFree(h_ws);
         if (h_io) cudaFree(h_io);
+        if (h_mail) cudaFreeHost(h_mail);
         if (h_stream) cudaStreamDestroy(h_stream);
         if (h_in) cudaStreamDestroy(h_in);
         if (h_out) cudaStreamDestroy(h_out);
@@ -948,9 +955,11 @@ struct mlic_engine {
     int run(int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* io, void* ws, size_t ws_bytes,
             cudaStream_t stream, bool dry_run, const HostPipe* hp = nullptr) {
         if (!finalized) return fail("engine not finalized");
-        if (mode < 0 || mode > 2) return fail("bad mode %d", mode);
+        if (mode < 0 || mode > 3) return fail("bad mode %d", mode);
+        const bool decomp = mode == MLIC_MODE_DECOMPRESS;
+        if (decomp && (stages != 7 || hp)) return fail("decompress runs all stages on device buffers");
         // stage subsets (row bands): g_a alone ends at the `y` tap; without g_a `y` is an INPUT; g_s alone reads `y_hat`
-        const int stg = (mode == MLIC_MODE_DECODER && stages != 4) ? (stages | 1) : stages;   // the decoder walk has no g_a
+        const int stg = ((mode == MLIC_MODE_DECODER || decomp) && stages != 4) ? (stages | 1) : stages;   // the decoder walk has no g_a
         if (stg != 7 && stg != 1 && stg != 6 && stg != 2 && stg != 4 && stg != 3) return fail("bad stage mask %d", stages);
         if (stg != 7 && hp) return fail("stage subsets take device buffers (mlic_run)");
         const int hmul = (stg & 2) ? 64 : 16;         // a band of g_a / g_s rows only has to keep the 16x sampling phase
@@ -986,7 +995,10 @@ struct mlic_engine {
             g_s(yhat, io->x_hat);
             return rc;
         }
-        if (mode != MLIC_MODE_DECODER) {
+        if (decomp) {                                     // z_hat from the decoded z symbols (EntropyBottleneck.decompress)
+            if (!dry && !io->z_symbols) return fail("decompress needs z_symbols");
+            if (go()) { launch_zsym_to_zhat(bf, io->z_symbols, eb_medians, zh, st); after_launch("z_hat_in"); }
+        } else if (mode != MLIC_MODE_DECODER) {
             size_t mark = ws_off;
             if (!(stg & 1)) {                             // g_a ran elsewhere (its row bands were gathered): y is an input
                 if (!dry && !io->y) return fail("stages without g_a need y as input");
@@ -1040,6 +1052,33 @@ struct mlic_engine {
         if (go()) { launch_copy_channels(bf, view(EPW, 10 * C + Me, Me), view(LRPW, 0, Me), st); after_launch("copy_hyper_means"); }
 
         const size_t half = (size_t)B * C * h * (w / 2);
+        int32_t* d_mail = decomp ? (int32_t*)ws_alloc(2 * half * sizeof(int32_t)) : nullptr;      // device [indexes | symbols]
+        if (decomp && !dry) {
+            if (!rans) return fail("decompress: no range decoder attached");
+            if (cdf_tab.empty()) return fail("decompress: mlic_engine_set_cdf was not called");
+            if (h_mail_n < 2 * half) {
+                if (h_mail) cudaFreeHost(h_mail);
+                h_mail = nullptr; h_mail_n = 0;
+                if (cudaMallocHost((void**)&h_mail, 2 * half * sizeof(int32_t)) != cudaSuccess) return fail("cudaMallocHost failed");
+                h_mail_n = 2 * half;
+            }
+        }
+        // one half-slice of decompress_anchor / decompress_nonanchor (utils/ckbd.py:195-229): index list to the host, the range
+        // decoder reads `half` symbols, symbols back, y_hat = symbols (* 1/gain) + means on this parity
+        auto decode_half = [&](QuantArgs q, bool anchor) {
+            q.mode = 3; q.idx = d_mail; q.sym = d_mail + half;
+            if (go()) { if (anchor) launch_quant_anchor(bf, q, st); else launch_quant_nonanchor(bf, q, st); after_launch(anchor ? "index_anchor" : "index_nonanchor"); }
+            if (!dry && !rc) {
+                cudaMemcpyAsync(h_mail, d_mail, half * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+                if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail("decompress: %s", cudaGetErrorString(cudaGetLastError())); return; }
+                const int r = mlic_rans_decode_stream(rans, h_mail, half, cdf_tab.data(), cdf_stride, cdf_sizes.data(), cdf_offsets.data(),
+                                                      (int)cdf_sizes.size(), h_mail + half);
+                if (r) { rc = fail("range decoder failed (%d) in half-slice", r); return; }
+                cudaMemcpyAsync(d_mail + half, h_mail + half, half * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            }
+            q.mode = 4;
+            if (go()) { if (anchor) launch_quant_anchor(bf, q, st); else launch_quant_nonanchor(bf, q, st); after_launch(anchor ? "dequant_anchor" : "dequant_nonanchor"); }
+        };
         for (int i = 0; i < S && !rc; ++i) {
             const std::string is = std::to_string(i);
             Act slot = view(LRPW, Me + i * C, C);
@@ -1066,13 +1105,15 @@ struct mlic_engine {
                 q.sym = io->symbols ? io->symbols + (size_t)(2 * i) * half : nullptr;
                 q.idx = io->indexes ? io->indexes + (size_t)(2 * i) * half : nullptr;
             }
-            if (go()) { launch_quant_anchor(bf, q, st); after_launch("quant_anchor"); }
+            if (decomp) decode_half(q, true);
+            else if (go()) { launch_quant_anchor(bf, q, st); after_launch("quant_anchor"); }
             lrp(lrp_in, "lrp_anchor." + is, slot, PAR_ANCHOR);
             if (i) intra_ctx(view(LRPW, Me + (i - 1) * C, C), slot, "global_intra_context." + is, s_intra);
             local_ctx(slot, "local_context." + is, s_local);
             ep(ep_n, "entropy_parameters_nonanchor." + is, pn, esq ? PAR_NONANCHOR : 0);
             if (mode == MLIC_MODE_COMPRESS) { q.sym += half; q.idx += half; }
-            if (go()) { launch_quant_nonanchor(bf, q, st); after_launch("quant_nonanchor"); }
+            if (decomp) decode_half(q, false);
+            else if (go()) { launch_quant_nonanchor(bf, q, st); after_launch("quant_nonanchor"); }
             lrp(lrp_in, "lrp_nonanchor." + is, slot, PAR_NONANCHOR);
         }
         if (rc) return rc;
@@ -1180,6 +1221,35 @@ int mlic_run(mlic_engine* e, int mode, int precision, int B, int H, int W, float
     return e->run(mode, precision, B, H, W, gain, dev, workspace, workspace_bytes, (cudaStream_t)cuda_stream, false);
 }
 int64_t mlic_last_launch_count(const mlic_engine* e) { return e ? e->launches : 0; }
+
+int mlic_engine_set_cdf(mlic_engine* e, const int32_t* cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                        int n_tables) {
+    if (!e || !cdfs || !cdf_sizes || !offsets || cdf_stride <= 0 || n_tables <= 0) return fail("bad arguments");
+    for (int t = 0; t < n_tables; ++t)
+        if (cdf_sizes[t] < 2 || cdf_sizes[t] > cdf_stride) return fail("cdf table %d: size %d does not fit stride %d", t, cdf_sizes[t], cdf_stride);
+    e->cdf_tab.assign(cdfs, cdfs + (size_t)n_tables * cdf_stride);
+    e->cdf_sizes.assign(cdf_sizes, cdf_sizes + n_tables);
+    e->cdf_offsets.assign(offsets, offsets + n_tables);
+    e->cdf_stride = cdf_stride;
+    return 0;
+}
+
+int mlic_decompress(mlic_engine* e, int precision, int B, int H, int W, float gain, const uint8_t* y_stream, size_t y_bytes,
+                    const int32_t* z_symbols, float* x_hat, float* y_hat, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream) {
+    if (!e) return fail("engine is NULL");
+    if (!y_stream || !z_symbols || !x_hat) return fail("decompress needs y_stream, z_symbols and x_hat");
+    mlic_rans_decoder* d = mlic_rans_decoder_create(y_stream, y_bytes);
+    if (!d) return fail("y stream of %zu bytes is not a range-coder stream", y_bytes);
+    mlic_buffers io;
+    memset(&io, 0, sizeof io);
+    io.z_symbols = const_cast<int32_t*>(z_symbols); io.x_hat = x_hat; io.y_hat = y_hat;
+    e->rans = d;
+    const int r = e->run(MLIC_MODE_DECOMPRESS, precision, B, H, W, gain, &io, workspace, workspace_bytes, (cudaStream_t)cuda_stream, false);
+    e->rans = nullptr;
+    mlic_rans_decoder_destroy(d);
+    return r;
+}
 
 int mlic_profile_read(mlic_engine* e, double* out3, int reset) {
     if (!e || !out3) return fail("bad arguments");

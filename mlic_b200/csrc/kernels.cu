@@ -735,6 +735,27 @@ void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const flo
     else entropy_bottleneck_kernel<float><<<blocks, 128, 0, s>>>((const float*)z.p, z.ld, (float*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw);
 }
 
+// EntropyBottleneck.decompress after the range decoder (CompressAI: dequantize(values, medians)): z_hat = sym + median
+template <typename T>
+__global__ void zsym_to_zhat_kernel(const int32_t* __restrict__ sym_nchw, T* __restrict__ zh, int zhld, int C, int HW,
+                                    long long total, const float* __restrict__ med) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / C;
+        int c = (int)(i - p * C);
+        int b = (int)(p / HW);
+        int hw = (int)(p - (long long)b * HW);
+        zh[p * zhld + c] = from_f<T>((float)sym_nchw[((size_t)b * C + c) * HW + hw] + med[c]);
+    }
+}
+void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians, const Act& z_hat, cudaStream_t s) {
+    long long total = (long long)z_hat.B * z_hat.H * z_hat.W * z_hat.C;
+    if (!total) return;
+    int blocks = cdiv(total, 128);
+    if (bf) zsym_to_zhat_kernel<bf16><<<blocks, 128, 0, s>>>(z_sym_nchw, (bf16*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians);
+    else zsym_to_zhat_kernel<float><<<blocks, 128, 0, s>>>(z_sym_nchw, (float*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians);
+}
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the channel dim of an NHWC view (eps 1e-5, affine); one warp per pixel.
 // ------------------------------------------------------------------------------------------
@@ -1483,13 +1504,18 @@ __global__ void quant_anchor_kernel(QuantArgs a) {
         int h = (int)(q % a.H);
         int b = (int)(q / a.H);
         T* slot = reinterpret_cast<T*>(a.slot.p) + p * a.slot.ld + c;
-        if (((h + w) & 1) == 0) { *slot = from_f<T>(0.f); continue; }
+        if (((h + w) & 1) == 0) { if (a.mode != 3) *slot = from_f<T>(0.f); continue; }
         const long long pe = a.sq ? (q * (a.W >> 1) + (w >> 1)) : p;       // row of this pixel in the entropy-parameter buffer
         const float sigma = a.pa[pe * 2 * C + c];
         const float mu = a.pa[pe * 2 * C + C + c];
         float out;
         if (a.mode == 2) {
             out = mu;
+        } else if (a.mode >= 3) {       // decompress (utils/ckbd.py:195-211): 3 = index list for the range decoder, 4 = symbols back
+            size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
+            if (a.mode == 3) { a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels); continue; }
+            const float sq = (float)a.sym[o];
+            out = a.vbr ? sq * a.rgain + mu : sq + mu;
         } else {
             const float y = a.y[p * a.y_ld + c];
             if (a.mode == 0) {
@@ -1526,6 +1552,13 @@ __global__ void quant_nonanchor_kernel(QuantArgs a) {
         const float mu = pp[pe * 2 * C + C + c];
         if (a.mode == 2) {           // decoder walk: both halves take means_anchor (mlicpp.py:405,418)
             if (anchor) *slot = from_f<T>(to_f<T>(*slot) + mu);
+            continue;
+        }
+        if (a.mode >= 3) {           // decompress (utils/ckbd.py:213-229)
+            if (anchor) continue;
+            size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
+            if (a.mode == 3) a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels);
+            else { const float sq = (float)a.sym[o]; *slot = from_f<T>(a.vbr ? sq * a.rgain + mu : sq + mu); }
             continue;
         }
         const float y = a.y[p * a.y_ld + c];

@@ -32,6 +32,8 @@ void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
 void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const float* packed /*[N][58]*/,
                                const float* medians, float* z_lik_nchw, int32_t* z_sym_nchw, cudaStream_t s);
 
+void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians, const Act& z_hat, cudaStream_t s);
+
 // LocalContext windowed attention: F[pix][3C] fp32 (q|k|v) -> O[pix][25][C] (activation type); C = 32 or 64.
 // returns non-zero for an unsupported C.
 int launch_local_attn(int bf, const float* F, int B, int H, int W, int C, const float* rel_bias /*[2][25][25]*/,
@@ -57,7 +59,7 @@ struct QuantArgs {
     const float* pn;                // non-anchor entropy parameters [pix][2C] (may be null in the anchor pass)
     Act slot;                       // y_hat slice i inside the LRP/concat workspace (activation type)
     int B, H, W, C;
-    int mode;                       // 0 forward, 1 compress, 2 decoder walk
+    int mode;                       // 0 forward, 1 compress, 2 decoder walk, 3 decompress: index list only, 4 decompress: symbols -> y_hat
     int vbr; float gain, rgain;     // VBR: gain g and 1/g as computed on the host in fp32
     float* lik; int lik_ld;         // forward: likelihood slice inside the fp32 NHWC [pix][M] buffer
     int32_t* sym; int32_t* idx;     // compress: base of this half-slice (flattened over [B,C,H,W/2])

@@ -1,4 +1,4 @@
-"""Summarise an ncu launch-list CSV (gpu__time_duration.sum per launch): second half = the warmed forward."""
+"""Summarise an ncu launch-list CSV (gpu__time_duration.sum per launch): the last forward of the run (from its g_a head kernel)."""
 import csv, collections, re, sys
 path = sys.argv[1]
 with open(path) as f:
@@ -8,6 +8,9 @@ for row in csv.DictReader(lines):
     d = recs.setdefault(int(row['ID']), {'name': row['Kernel Name']})
     d[row['Metric Name']] = float(row['Metric Value'].replace(',', ''))
 L = list(recs.values()); half = len(L) // 2; S = L[half:]
+heads = [i for i, d in enumerate(L) if 'ga_head_kernel' in d['name']]
+if heads:                      # the last forward of the run: from its g_a head kernel on, this repo's kernels only
+    S = [d for d in L[heads[-1]:] if 'mlic::' in d['name']]
 tot = sum(d['gpu__time_duration.sum'] for d in S)
 print(f"launches in the measured forward: {len(S)}; summed kernel time {tot/1e3:.1f} us")
 agg = collections.defaultdict(lambda: [0, 0.0])
