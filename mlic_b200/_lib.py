@@ -8,13 +8,15 @@ LIB_PATH = os.path.join(_HERE, "libmlic_b200.so")
 
 KIND_BASE, KIND_SD, KIND_VBR = 0, 1, 2
 PREC_FP32, PREC_BF16 = 0, 1
-MODE_FORWARD, MODE_COMPRESS, MODE_DECODER = 0, 1, 2
+MODE_FORWARD, MODE_COMPRESS, MODE_DECODER, MODE_DECOMPRESS = 0, 1, 2, 3
 
 # every symbol include/mlic_b200.h declares (tests check the library exports exactly these)
 EXPORTS = (
     "mlic_engine_create", "mlic_engine_destroy", "mlic_engine_set_param", "mlic_engine_finalize",
     "mlic_engine_set_option", "mlic_workspace_bytes", "mlic_run", "mlic_run_host", "mlic_last_launch_count",
     "mlic_profile_read", "mlic_profile_read_top", "mlic_trace_dump", "mlic_conv2d_nhwc", "mlic_dwconv3x3_nhwc", "mlic_dsconv_nhwc", "mlic_final_subpel", "mlic_local_attn", "mlic_ga_head", "mlic_gaussian_conditional", "mlic_last_error", "mlic_version",
+    "mlic_engine_set_cdf", "mlic_decompress", "mlic_pmf_to_quantized_cdf", "mlic_rans_encode_bound", "mlic_rans_encode",
+    "mlic_rans_decoder_create", "mlic_rans_decoder_destroy", "mlic_rans_decode_stream",
 )
 
 
@@ -65,6 +67,17 @@ def lib():
     L.mlic_local_attn.argtypes = [i32, vp, i32, i32, i32, vp, vp, i32, C.POINTER(f32), vp]
     L.mlic_ga_head.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, C.POINTER(f32), vp]
     L.mlic_gaussian_conditional.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
+    L.mlic_engine_set_cdf.argtypes = [vp, vp, i32, vp, vp, i32]
+    L.mlic_decompress.argtypes = [vp, i32, i32, i32, i32, f32, vp, sz, vp, vp, vp, vp, sz, vp]
+    L.mlic_pmf_to_quantized_cdf.argtypes = [vp, i32, vp]
+    L.mlic_rans_encode_bound.argtypes = [sz]
+    L.mlic_rans_encode_bound.restype = sz
+    L.mlic_rans_encode.argtypes = [vp, vp, sz, vp, i32, vp, vp, i32, vp, sz, C.POINTER(sz)]
+    L.mlic_rans_decoder_create.argtypes = [vp, sz]
+    L.mlic_rans_decoder_create.restype = vp
+    L.mlic_rans_decoder_destroy.argtypes = [vp]
+    L.mlic_rans_decoder_destroy.restype = None
+    L.mlic_rans_decode_stream.argtypes = [vp, vp, sz, vp, i32, vp, vp, i32, vp]
     L.mlic_last_error.restype = C.c_char_p
     L.mlic_version.restype = C.c_char_p
     _lib = L

@@ -1491,6 +1491,10 @@ __device__ __forceinline__ float gauss_lik(float yq, float sigma, float mu) {
     return fmaxf(up - lo, 1e-9f);
 }
 
+// symbols / gain + means as the reference evaluates it (torch: a product, then a sum: two roundings, no FMA contraction), so
+// that the encoder-side and the decoder-side walks rebuild bit-identical y_hat whatever the compiler fuses elsewhere
+__device__ __forceinline__ float vbr_deq(float sq, float rgain, float mu) { return __fadd_rn(__fmul_rn(sq, rgain), mu); }
+
 template <typename T>
 __global__ void quant_anchor_kernel(QuantArgs a) {
     const int C = a.C;
@@ -1515,17 +1519,17 @@ __global__ void quant_anchor_kernel(QuantArgs a) {
             size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
             if (a.mode == 3) { a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels); continue; }
             const float sq = (float)a.sym[o];
-            out = a.vbr ? sq * a.rgain + mu : sq + mu;
+            out = a.vbr ? vbr_deq(sq, a.rgain, mu) : sq + mu;
         } else {
             const float y = a.y[p * a.y_ld + c];
             if (a.mode == 0) {
-                out = a.vbr ? rintf((y - mu) * a.gain) * a.rgain + mu : rintf(y - mu) + mu;
+                out = a.vbr ? vbr_deq(rintf((y - mu) * a.gain), a.rgain, mu) : rintf(y - mu) + mu;
             } else {
                 float sq = a.vbr ? rintf((y - mu) - mu) : rintf(y - mu);
                 size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
                 a.sym[o] = (int32_t)sq;
                 a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels);
-                out = a.vbr ? sq * a.rgain + mu : sq + mu;
+                out = a.vbr ? vbr_deq(sq, a.rgain, mu) : sq + mu;
             }
         }
         *slot = from_f<T>(out);
@@ -1558,7 +1562,7 @@ __global__ void quant_nonanchor_kernel(QuantArgs a) {
             if (anchor) continue;
             size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
             if (a.mode == 3) a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels);
-            else { const float sq = (float)a.sym[o]; *slot = from_f<T>(a.vbr ? sq * a.rgain + mu : sq + mu); }
+            else { const float sq = (float)a.sym[o]; *slot = from_f<T>(a.vbr ? vbr_deq(sq, a.rgain, mu) : sq + mu); }
             continue;
         }
         const float y = a.y[p * a.y_ld + c];
@@ -1571,13 +1575,13 @@ __global__ void quant_nonanchor_kernel(QuantArgs a) {
                 lik = gauss_lik(rintf(y - mu) + mu, sigma, mu);
             }
             a.lik[p * a.lik_ld + c] = lik;
-            if (!anchor) *slot = from_f<T>(a.vbr ? rintf((y - mu) * a.gain) * a.rgain + mu : rintf(y - mu) + mu);
+            if (!anchor) *slot = from_f<T>(a.vbr ? vbr_deq(rintf((y - mu) * a.gain), a.rgain, mu) : rintf(y - mu) + mu);
         } else if (!anchor) {
             float sq = rintf(y - mu);
             size_t o = (((size_t)b * C + c) * a.H + h) * (a.W / 2) + (w >> 1);
             a.sym[o] = (int32_t)sq;
             a.idx[o] = cdf_index(a.vbr ? sigma * a.gain : sigma, a.table, a.levels);
-            *slot = from_f<T>(a.vbr ? sq * a.rgain + mu : sq + mu);
+            *slot = from_f<T>(a.vbr ? vbr_deq(sq, a.rgain, mu) : sq + mu);
         }
     }
 }

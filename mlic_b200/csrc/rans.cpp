@@ -104,7 +104,7 @@ int mlic_rans_encode(const int32_t* symbols, const int32_t* indexes, size_t n, c
         syms.push_back({(uint16_t)cdf[value], (uint16_t)(cdf[value + 1] - cdf[value]), false});
         if (value == max_value) {
             int n_bypass = 0;
-            while ((raw >> (n_bypass * kBypassBits)) != 0) ++n_bypass;
+            while (n_bypass < 8 && (raw >> (n_bypass * kBypassBits)) != 0) ++n_bypass;      // (8 nibbles cover 32 bits: no shift by 32)
             int32_t val = n_bypass;
             while (val >= (int32_t)kMaxBypass) { syms.push_back({(uint16_t)kMaxBypass, 1, true}); val -= kMaxBypass; }
             syms.push_back({(uint16_t)val, 1, true});

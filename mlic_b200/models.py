@@ -14,6 +14,7 @@ import math
 import time
 import types
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -146,15 +147,23 @@ class MLICPlusPlus(nn.Module):
         return out
 
     def update(self, scale_table=None, force=False):
-        """models/mlicpp.py:470-475.  Populates gaussian_conditional.scale_table; the quantised CDF tables that
-        only the host rANS coder reads are not rebuilt here (coder is out of this path's scope)."""
+        """models/mlicpp.py:470-475: gaussian_conditional.update_scale_table(scale_table) and CompressionModel.update():
+        fills `scale_table` and the quantised CDF tables (`_quantized_cdf`, `_cdf_length`, `_offset`) of both entropy
+        models, which compress() / decompress() hand to the range coder (mlic_b200/coder.py)."""
+        from . import coder
         if scale_table is None:
             scale_table = get_scale_table()
-        gc = self.gaussian_conditional
-        if not force and gc.scale_table.numel() == len(scale_table):
+        gc, eb = self.gaussian_conditional, self.entropy_bottleneck
+        if not force and gc.scale_table.numel() == len(scale_table) and gc._offset.numel() > 0 and eb._offset.numel() > 0:
             return False
         gc.scale_table.resize_(len(scale_table))
         gc.scale_table.copy_(torch.as_tensor(scale_table, dtype=torch.float32))
+        for mod, tabs in ((gc, coder.gaussian_tables(gc.scale_table)), (eb, coder.bottleneck_tables(eb))):
+            for name, arr in zip(("_quantized_cdf", "_cdf_length", "_offset"), tabs):
+                buf = getattr(mod, name)
+                t = torch.from_numpy(arr)
+                buf.resize_(t.shape)
+                buf.copy_(t)
         self.invalidate_engine()
         return True
 
@@ -372,23 +381,87 @@ class MLICPlusPlus(nn.Module):
         res.update({k: o[k] for k in taps})
         return res
 
+    def _tables(self, mod):
+        if mod._offset.numel() == 0:
+            raise RuntimeError("call update(force=True) before compress() / decompress() (models/mlicpp.py:470-475)")
+        return (mod._quantized_cdf.detach().cpu().numpy(), mod._cdf_length.detach().cpu().numpy().reshape(-1),
+                mod._offset.detach().cpu().numpy().reshape(-1))
+
+    def _strings(self, o, B):
+        """The coder side of compress() (models/mlicpp.py:205-206,279-280): ONE y string for the whole batch (the symbol
+        lists are flattened over [B,C,H,W/2] per half-slice), one z string per image (EntropyBottleneck.compress)."""
+        from . import coder
+        y_string = coder.encode_with_indexes(o["symbols"].cpu().numpy(), o["indexes"].cpu().numpy(), *self._tables(self.gaussian_conditional))
+        zs = o["z_symbols"].cpu().numpy()
+        ztab = self._tables(self.entropy_bottleneck)
+        zidx = np.broadcast_to(np.arange(self.N, dtype=np.int32)[:, None, None], zs.shape[1:])
+        return [[y_string], [coder.encode_with_indexes(zs[b], zidx, *ztab) for b in range(B)]]
+
     @torch.no_grad()
     def compress(self, x, *, taps=()):
-        """models/mlicpp.py:199-290 up to the entropy coder: returns the coder's inputs (`symbols`, `indexes`: flat
-        int32 in the reference's list order A0,N0,A1,N1,...; `z_symbols`) instead of byte strings, plus `x_hat`."""
+        """models/mlicpp.py:199-290 -> {"strings": [[y_string], z_strings], "shape", "cost_time"} plus the coder's inputs
+        (`symbols`, `indexes`: flat int32 in the reference's list order A0,N0,A1,N1,...; `z_symbols`) and `x_hat`."""
         t0 = time.time()
         B, _, H, W = x.shape
         self.update_resolutions(H // 16, W // 16)
         o = self._run(_lib.MODE_COMPRESS, x, B, H, W, 0.0, taps)
         if x.is_cuda:
             torch.cuda.synchronize(x.device)
-        o.update(strings=None, shape=(H // 64, W // 64), cost_time=time.time() - t0)
+        strings = self._strings(o, B) if self.gaussian_conditional._offset.numel() else None
+        o.update(strings=strings, shape=(H // 64, W // 64), cost_time=time.time() - t0)
         return o
 
-    def decompress(self, strings, shape, **kwargs):
-        """models/mlicpp.py:292-378 needs the host rANS decoder inside the slice loop."""
-        raise NotImplementedError("decompress() needs the CompressAI rANS decoder in the loop; the network walk it "
-                                  "performs is available as net_decoder_forward()")
+    @torch.no_grad()
+    def decompress(self, strings, shape, *, taps=(), _gain=0.0):
+        """models/mlicpp.py:292-378 -> {"x_hat", "cost_time"}: z strings decoded on the host, then the decoder-side walk with
+        the range decoder inside the slice loop (C ABI mlic_decompress)."""
+        from . import coder
+        t0 = time.time()
+        if not torch.cuda.is_available():
+            raise _lib.MlicError("mlic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        y_string, z_strings = strings[0][0], strings[1]
+        B, (hz, wz) = len(z_strings), shape
+        H, W = 64 * int(hz), 64 * int(wz)
+        ztab = self._tables(self.entropy_bottleneck)
+        zidx = np.broadcast_to(np.arange(self.N, dtype=np.int32)[:, None, None], (self.N, hz, wz))
+        dec = coder.RansDecoder()
+        zs = np.stack([dec.decode_with_indexes(s, zidx, *ztab).reshape(self.N, hz, wz) for s in z_strings])
+        dec.close()
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.MlicError("move the model to a CUDA device before decompress()")
+        self.update_resolutions(H // 16, W // 16)
+        L = self._sync_engine(dev)
+        ytab = self._tables(self.gaussian_conditional)
+        cdf, ln, off = (np.ascontiguousarray(t, dtype=np.int32) for t in ytab)
+        _lib.check(L.mlic_engine_set_cdf(self._engine, cdf.ctypes.data_as(C.c_void_p), cdf.shape[1], ln.ctypes.data_as(C.c_void_p),
+                                         off.ctypes.data_as(C.c_void_p), cdf.shape[0]))
+        for name, val in ((b"tensor_cores", self.tensor_cores), (b"profile", False), (b"fuse", self.fuse), (b"trace", self._trace), (b"stages", 7)):
+            _lib.check(L.mlic_engine_set_option(self._engine, name, int(val)))
+        prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        out = {"x_hat": torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)}
+        if "y_hat" in taps:
+            out["y_hat"] = torch.empty((B, self.M, H // 16, W // 16), dtype=torch.float32, device=dev)
+        z_dev = torch.from_numpy(zs.astype(np.int32)).to(dev)
+        ybuf = np.frombuffer(bytes(y_string), dtype=np.uint8)
+        with torch.cuda.device(dev):
+            need = C.c_size_t()
+            _lib.check(L.mlic_workspace_bytes(self._engine, _lib.MODE_DECOMPRESS, prec, B, H, W, C.byref(need)))
+            key = str(dev)
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < need.value:
+                self._ws[key] = ws = None
+                ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+                self._ws[key] = ws
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(L.mlic_decompress(self._engine, prec, B, H, W, float(_gain), ybuf.ctypes.data_as(C.c_void_p), ybuf.size,
+                                         C.c_void_p(z_dev.data_ptr()), C.c_void_p(out["x_hat"].data_ptr()),
+                                         C.c_void_p(out["y_hat"].data_ptr()) if "y_hat" in out else None,
+                                         C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(stream)))
+            torch.cuda.synchronize(dev)
+        self.last_launch_count = int(L.mlic_last_launch_count(self._engine))
+        out["cost_time"] = time.time() - t0
+        return out
 
     @torch.no_grad()
     def net_decoder_forward(self, x):
@@ -445,8 +518,14 @@ class MLICPlusPlusVbr(MLICPlusPlus):
         o = self._run(_lib.MODE_COMPRESS, x, B, H, W, self._scale(s, inputscale, True), taps)
         if x.is_cuda:
             torch.cuda.synchronize(x.device)
-        o.update(strings=None, shape=(H // 64, W // 64), cost_time=time.time() - t0)
+        strings = self._strings(o, B) if self.gaussian_conditional._offset.numel() else None
+        o.update(strings=strings, shape=(H // 64, W // 64), cost_time=time.time() - t0)
         return o
+
+    @torch.no_grad()
+    def decompress(self, strings, shape, stage=2, s=1, inputscale=0, *, taps=()):
+        """models/mlicpp_vbr.py:889-1040 (stage 2 arithmetic: indexes from sigma * gain, y_hat = symbols / gain + means)."""
+        return super().decompress(strings, shape, taps=taps, _gain=self._scale(s, inputscale, True))
 
 
 _CLASSES = {"base": MLICPlusPlus, "sd": MLICPlusPlusSD, "vbr": MLICPlusPlusVbr}
