@@ -1035,6 +1035,17 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
     }
     const int pw = warp;
     int n = 0;
+    // the 9 taps + bias of an item's channel pair come from global memory (L2): those of the NEXT item are requested before the
+    // arithmetic of the current one, so their latency is not paid at the head of every item (the chunk changes item by item)
+    float2 w2[9], b2 = make_float2(0.f, 0.f);
+    auto load_w = [&](int item, float2* wv, float2& bv) {
+        const int cn = (item % chunks) * 64 + 2 * lane;
+        const bool ok = item < nitems && cn < C;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wv[t] = ok ? __ldg(reinterpret_cast<const float2*>(w9 + (size_t)t * C + cn)) : make_float2(0.f, 0.f);
+        bv = ok ? __ldg(reinterpret_cast<const float2*>(bias + cn)) : make_float2(0.f, 0.f);
+    };
+    load_w(blockIdx.x, w2, b2);
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
         const int slot = n % TT::SLOTS;
         const uint32_t ph = (uint32_t)(n / TT::SLOTS) & 1u;
@@ -1044,10 +1055,8 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
         const int oh0 = th * TT::TH, ow0 = tw * TT::TW;
         const int c = cc * 64 + 2 * lane;
         const bool cok = c < C;
-        float2 w2[9], b2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int t = 0; t < 9; ++t) w2[t] = cok ? make_float2(w9[t * C + c], w9[t * C + c + 1]) : make_float2(0.f, 0.f);
-        if (cok) b2 = make_float2(bias[c], bias[c + 1]);
+        float2 w2n[9], b2n;
+        load_w(it + (int)gridDim.x, w2n, b2n);
         mbar_wait(&full_bar[slot], ph);
         const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * TT::BYTES) + (size_t)(2 * pw * S) * 32 + lane;
         float2 acc[TT::TH][2];
@@ -1085,6 +1094,9 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[slot]);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w2[t] = w2n[t];
+        b2 = b2n;
     }
 }
 
