@@ -1009,6 +1009,7 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
     extern __shared__ uint8_t dw_smem_raw[];
     uint8_t* ring = (uint8_t*)(((uintptr_t)dw_smem_raw + 127) & ~(uintptr_t)127);
     __shared__ uint64_t full_bar[TT::SLOTS], empty_bar[TT::SLOTS];
+    __shared__ int4 item_desc[TT::SLOTS];          // (channel chunk, image, first output row, first output column) of the item in a slot
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < TT::SLOTS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
@@ -1027,6 +1028,7 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
                 const int cc = it % chunks, tile = it / chunks;
                 const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
                 const int th = tr / tilesW, tw = tr - th * tilesW;
+                item_desc[slot] = make_int4(cc, b, th * TT::TH, tw * TT::TW);      // published by the arrive below (release) / the wait (acquire)
                 mbar_expect_tx(&full_bar[slot], (uint32_t)TT::BYTES);
                 tma_load_4d(ring + (size_t)slot * TT::BYTES, &tmap, &full_bar[slot], cc * 64, tw * TT::TW * S - 1, th * TT::TH * S - 1, b);
             }
@@ -1034,30 +1036,42 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
         return;
     }
     const int pw = warp;
+    const size_t row_stride = (size_t)Wo * old;
     int n = 0;
     // the 9 taps + bias of an item's channel pair come from global memory (L2): those of the NEXT item are requested before the
     // arithmetic of the current one, so their latency is not paid at the head of every item (the chunk changes item by item)
     float2 w2[9], b2 = make_float2(0.f, 0.f);
-    auto load_w = [&](int item, float2* wv, float2& bv) {
-        const int cn = (item % chunks) * 64 + 2 * lane;
-        const bool ok = item < nitems && cn < C;
+    auto load_w = [&](int cq, bool live, float2* wv, float2& bv) {
+        const int cn = cq * 64 + 2 * lane;
+        const bool ok = live && cn < C;
 #pragma unroll
         for (int t = 0; t < 9; ++t) wv[t] = ok ? __ldg(reinterpret_cast<const float2*>(w9 + (size_t)t * C + cn)) : make_float2(0.f, 0.f);
         bv = ok ? __ldg(reinterpret_cast<const float2*>(bias + cn)) : make_float2(0.f, 0.f);
     };
-    load_w(blockIdx.x, w2, b2);
+    // the chunk index advances by gridDim.x (mod chunks) per item: no division in the item loop; the tile coordinates come from the
+    // descriptor the TMA thread left in the slot (the three integer divisions per item and warp were ~15 % of the instructions)
+    const int cstep = (int)(gridDim.x % (unsigned)chunks);
+    int ccur = (int)(blockIdx.x % (unsigned)chunks);
+    load_w(ccur, (int)blockIdx.x < nitems, w2, b2);
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
         const int slot = n % TT::SLOTS;
         const uint32_t ph = (uint32_t)(n / TT::SLOTS) & 1u;
-        const int cc = it % chunks, tile = it / chunks;
-        const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
-        const int th = tr / tilesW, tw = tr - th * tilesW;
-        const int oh0 = th * TT::TH, ow0 = tw * TT::TW;
+        int cnext = ccur + cstep;
+        if (cnext >= chunks) cnext -= chunks;
+        float2 w2n[9], b2n;
+        load_w(cnext, it + (int)gridDim.x < nitems, w2n, b2n);
+        mbar_wait(&full_bar[slot], ph);
+        const int4 ds = item_desc[slot];
+        const int cc = ds.x, b = ds.y, oh0 = ds.z, ow0 = ds.w;
+        ccur = cnext;
         const int c = cc * 64 + 2 * lane;
         const bool cok = c < C;
-        float2 w2n[9], b2n;
-        load_w(it + (int)gridDim.x, w2n, b2n);
-        mbar_wait(&full_bar[slot], ph);
+        // output addressing once per item (the per-store 64-bit index arithmetic and bounds tests were a third of this kernel's
+        // instructions: profiles/r01_ncu_dwtma.txt): row pointer of the warp's two columns, advanced by one output row per step
+        const int ow = ow0 + 2 * pw;
+        bf16* orow = out + (((size_t)b * Ho + oh0) * Wo + ow) * old + c;
+        const int nrows = cok ? Ho - oh0 : 0;                                   // rows of this tile inside the image (0: channel tail)
+        const bool okq[2] = {ow < Wo, ow + 1 < Wo};
         const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * TT::BYTES) + (size_t)(2 * pw * S) * 32 + lane;
         float2 acc[TT::TH][2];
 #pragma unroll
@@ -1079,17 +1093,16 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
             }
             if (iy >= 2 && ((iy - 2) % S) == 0) {
                 const int oy = (iy - 2) / S;
-                const int oh = oh0 + oy;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int ow = ow0 + 2 * pw + q;
                     float2 v = acc[oy][q];
                     if (act == ACT_GELU) v = gelu2(v);
-                    if (cok && oh < Ho && ow < Wo) {
+                    if (oy < nrows && okq[q]) {
                         __nv_bfloat162 hv = __floats2bfloat162_rn(v.x, v.y);
-                        *reinterpret_cast<uint32_t*>(out + (((size_t)b * Ho + oh) * Wo + ow) * old + c) = *reinterpret_cast<uint32_t*>(&hv);
+                        *reinterpret_cast<uint32_t*>(orow + (q ? old : 0)) = *reinterpret_cast<uint32_t*>(&hv);
                     }
                 }
+                orow += row_stride;
             }
         }
         __syncwarp();
