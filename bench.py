@@ -151,10 +151,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--size", default="1080p", choices=["1080p", "4k"],
+                    help="1080p: 1920x1088 (BASELINE configs[1], the headline); 4k: 3840x2160 padded to 3840x2176 as the reference pads "
+                         "(configs[4], per-image sharding; MP counted on the nominal 3840x2160)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global H, W, MP_PER_IMAGE, FLOP_PER_IMAGE
+    if args.size == "4k":
+        H, W, MP_PER_IMAGE, FLOP_PER_IMAGE = 2176, 3840, 3840 * 2160 / 1e6, 4 * 1.753e12
+        if args.batch == 32:
+            args.batch = 8
+        args.no_cpu_baseline = True
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -168,6 +177,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from oracle import weights
@@ -261,10 +272,10 @@ def main():
         # DRAM traffic of that launch shape: one `ncu --set full` capture (profiles/r01_ncu_subpel_full.txt), taken at one image
         # per launch (dram__bytes_read.sum + dram__bytes_write.sum = 196.7 MB; algorithmic 50.1 + 200.5 MB, the tail of the
         # output is still in L2 when the kernel ends); scaled here to this run's images per launch.
-        ncu_bytes_per_image = 196.7e6
+        ncu_bytes_per_image = 196.7e6 * (4 if args.size == "4k" else 1)
         roof = {"bound": "tensor",
                 "kernel": "conv_gemm_tc_kernel<GELU|none> as the 3x3 192->768 sub-pixel convolution at 272x480 (g_s.5 subpel_conv / upsample): "
-                          "the heaviest launch shape, 2 launches per step",
+                          "the heaviest launch shape, 2 launches per step" + (" (4k: the same layer at 544x960)" if args.size == "4k" else ""),
                 "achieved": top_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": top_tflops / pk["tf_sust"],
                 "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "flops_per_launch": top_flops, "launches": top_n, "avg_launch_ms": top_ms / max(top_n, 1),
@@ -282,10 +293,12 @@ def main():
             cpu = {"value": mps, "unit": "MP/s", "cores": threads, "kind": "port",
                    "sample": f"1 image 1920x1088 of the workload per run, best of {len(times)} runs ({sum(times):.1f} s of CPU work), "
                              f"fp32 torch CPU, {threads} threads"}
-        line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC if args.size == "1080p" else "megapixels/sec MLICPP_L forward @3840x2160", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": "MLICPP_L forward 1920x1088 (BASELINE configs[1])", "images_per_gpu_per_step": B,
+                "config": {"workload": "MLICPP_L forward 1920x1088 (BASELINE configs[1])" if args.size == "1080p" else
+                                       "MLICPP_L forward 3840x2160 padded to 3840x2176, sharded by image (BASELINE configs[4])",
+                           "images_per_gpu_per_step": B,
                            "global_batch": B * world, "parallelism": f"batch-shard x{world}", "weights": "random-init seed 1234",
                            "l2": "per-step inputs + activations (>1 GB/image) exceed the 126 MB L2; no explicit flush"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,

@@ -20,11 +20,13 @@ SHAPES = [  # name, B, H, W, Cin, N, ks
     ("q 32->32", 8, 68, 120, 32, 32, 1),
 ]
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
+BM = int(os.environ.get("EM_BATCH_MULT", "1"))        # 4: the bench batch (32 images per launch)
 iters = 2 if os.environ.get("MLIC_TC_DEBUG") else 20
 torch.manual_seed(0)
 for name, B, H, W, Cin, N, ks in SHAPES:
     if only and not any(o in name for o in only):
         continue
+    B = B * BM
     x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16)
     w = torch.randn(N, Cin, ks, ks) / (Cin * ks * ks) ** 0.5
     b = torch.randn(N) * 0.1
