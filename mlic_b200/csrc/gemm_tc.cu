@@ -660,10 +660,11 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     const uint32_t rp = smem_u32(rawbuf) + (uint32_t)(rslot * p.raw_bytes + ((2 * pw) * 32 + lane) * 4);
                     const uint32_t wk = smem_u32(sDw) + (uint32_t)((k * 64 + 2 * lane) * 4);         // tap t at wk + t * Cin * 4
                     const uint32_t sa_s = smem_u32(sa);
+                    const bool chok = k * 64 + 2 * lane < p.Cin;        // channel tail of the last chunk: taps and bias 0 (the patch is zero-filled there)
                     float2 w2[9];
 #pragma unroll
-                    for (int tp = 0; tp < 9; ++tp) w2[tp] = lds_f2(wk + (uint32_t)(tp * p.Cin * 4));
-                    const float2 b2 = lds_f2(wk + (uint32_t)(9 * p.Cin * 4));
+                    for (int tp = 0; tp < 9; ++tp) w2[tp] = chok ? lds_f2(wk + (uint32_t)(tp * p.Cin * 4)) : make_float2(0.f, 0.f);
+                    const float2 b2 = chok ? lds_f2(wk + (uint32_t)(9 * p.Cin * 4)) : make_float2(0.f, 0.f);
                     float2 acc[8][2];
 #pragma unroll
                     for (int oy = 0; oy < 8; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
@@ -1166,10 +1167,12 @@ bool tc_conv_supported(const TcConv& c, const Epi& e) {
     if (e.nchw && !(e.shuffle && e.N == 12 && e.out_f32)) return false;
     if (c.prod != PROD_TMA) {
         // fused producers: 1x1 GEMM over a dense-stride-1 view, whole weight matrix resident, <= 3 column groups
-        if (c.ks != 1 || c.pad != 0 || (c.Cin % 64) != 0 || e.N > 192 || (e.N % 8) != 0 || e.shuffle || e.out_f32 || e.out2) return false;
-        if ((c.Cin / 64) > 4 || (size_t)(c.Cin / 64) * ((e.N + 63) / 64 * 64) * 128 > 80 * 1024) return false;
+        // (depthwise producer: a channel tail is fine, the halo patch arrives zero-filled and the producer zeroes its taps: Cin % 8 for TMA)
+        if (c.ks != 1 || c.pad != 0 || (c.Cin % (c.prod == PROD_DW ? 8 : 64)) != 0 || e.N > 192 || (e.N % 8) != 0 || e.shuffle || e.out_f32 || e.out2) return false;
+        if ((c.Cpad / 64) > 4 || (size_t)(c.Cpad / 64) * ((e.N + 63) / 64 * 64) * 128 > 80 * 1024) return false;
         if (c.prod == PROD_DW && (!c.dw_w9 || !c.dw_bias)) return false;
-        if (c.prod == PROD_DW && (e.gdn || e.act == ACT_HALF_TANH)) return false;
+        if (c.prod == PROD_DW && e.gdn) return false;
+        if (c.prod == PROD_DW && e.act == ACT_HALF_TANH && !e.res) return false;      // (instantiated with the residual only: the LRP tail)
         if (c.prod == PROD_SQ && (!e.gdn || e.act != ACT_NONE)) return false;
         auto ok16 = [](const void* q, int ld) { return q == nullptr || ((((uintptr_t)q) % 16 == 0) && ((ld * 2) % 16 == 0)); };
         if (!e.out || !ok16(e.out, e.out_ld) || !ok16(e.res, e.res_ld) || !ok16(e.gdn_x, e.gdn_ld)) return false;
@@ -1375,8 +1378,9 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
          {conv_gemm_tc_kernel<1, 2, false, 0>, conv_gemm_tc_kernel<1, 2, true, 0>}},
         {{conv_gemm_tc_kernel<2, 0, false, 0>, conv_gemm_tc_kernel<2, 0, true, 0>}, {conv_gemm_tc_kernel<2, 1, false, 0>, conv_gemm_tc_kernel<2, 1, true, 0>},
          {conv_gemm_tc_kernel<2, 2, false, 0>, conv_gemm_tc_kernel<2, 2, true, 0>}}};
-    static const KernelFn table_dw[2][2] = {{conv_gemm_tc_kernel<0, 0, false, PROD_DW>, conv_gemm_tc_kernel<0, 0, true, PROD_DW>},
-                                            {conv_gemm_tc_kernel<1, 0, false, PROD_DW>, conv_gemm_tc_kernel<1, 0, true, PROD_DW>}};
+    static const KernelFn table_dw[3][2] = {{conv_gemm_tc_kernel<0, 0, false, PROD_DW>, conv_gemm_tc_kernel<0, 0, true, PROD_DW>},
+                                            {conv_gemm_tc_kernel<1, 0, false, PROD_DW>, conv_gemm_tc_kernel<1, 0, true, PROD_DW>},
+                                            {nullptr, conv_gemm_tc_kernel<2, 0, true, PROD_DW>}};
     static const KernelFn table_sq[2][2] = {{conv_gemm_tc_kernel<0, 1, false, PROD_SQ>, conv_gemm_tc_kernel<0, 1, true, PROD_SQ>},
                                             {conv_gemm_tc_kernel<0, 2, false, PROD_SQ>, conv_gemm_tc_kernel<0, 2, true, PROD_SQ>}};
     static bool attr_set[3][3][2][3] = {};
@@ -1384,6 +1388,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     const int ri = e.res ? 1 : 0;
     KernelFn fn = table[e.act][e.gdn][ri];
     if (c.prod == PROD_DW) fn = table_dw[e.act][ri];
+    if (!fn) { snprintf(g_tc_err, sizeof g_tc_err, "no kernel instantiation for act=%d res=%d prod=%d", e.act, ri, c.prod); return 9; }
     else if (c.prod == PROD_SQ) fn = table_sq[e.gdn - 1][ri];
     if (!attr_set[e.act][e.gdn][ri][c.prod]) {
         cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, budget0 + 1024);

@@ -149,6 +149,32 @@ def test_depthwise_kernels(B, H, W, C, stride, act, dtype):
         assert bool(((out.float() - ref).abs() <= tol).all()), (out.float() - ref).abs().max().item()
 
 
+@pytest.mark.parametrize("B,H,W,Cin,N,act,res", [(1, 24, 40, 192, 192, "gelu", True), (2, 17, 30, 224, 128, "gelu", False),
+                                                 (1, 20, 28, 160, 192, "gelu", False), (2, 17, 30, 128, 32, "half_tanh", True),
+                                                 (1, 13, 21, 104, 72, None, True)])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_depthwise_separable_conv_bf16(B, H, W, Cin, N, act, res, fuse):
+    """DepthWiseConv (conv.py:46-63) as one tcgen05 kernel with the depthwise producer (fuse) or as dw kernel + GEMM, incl. a
+    channel tail in the last 64-channel chunk and the LRP tail (0.5 tanh + residual, quantization.py:30-45)."""
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+    dw, db = torch.randn(Cin, 1, 3, 3, generator=g) / 3, torch.randn(Cin, generator=g) * 0.1
+    pw = (torch.randn(N, Cin, 1, 1, generator=g) / Cin ** 0.5).to(torch.bfloat16).float()
+    pb = torch.randn(N, generator=g) * 0.1
+    r = torch.randn(B, H, W, N, generator=g).cuda().to(torch.bfloat16) if res else None
+    out, _ = ops.dsconv_nhwc(x, dw, db, pw, pb, 1, act, r, fuse)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), dw.cuda(), db.cuda(), padding=1, groups=Cin)
+    y = F.conv2d(y, pw.cuda(), pb.cuda())
+    y = F.gelu(y) if act == "gelu" else (0.5 * torch.tanh(y) if act == "half_tanh" else y)
+    y = y.permute(0, 2, 3, 1)
+    if r is not None:
+        y = y + r.float()
+    # the depthwise result is rounded to bf16 before the GEMM (2^-9 relative on ~sqrt(Cin) terms of size ~1/sqrt(Cin))
+    tol = 2.0 ** -7 * y.abs() + 1.5e-2
+    assert bool(((out.float() - y).abs() <= tol).all()), (out.float() - y).abs().max().item()
+    assert float((out.float() - y).pow(2).mean().sqrt()) < 4e-3
+
+
 @pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("B,H,W,C", [(1, 16, 8, 64), (2, 30, 50, 192), (1, 67, 29, 192)])
 def test_final_subpel_conv(impl, B, H, W, C):
