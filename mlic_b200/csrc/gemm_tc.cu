@@ -208,6 +208,7 @@ struct TcParams {
     int epi_vec;            // STORE_DIRECT: 16-byte epilogue accesses are legal for every pointer involved
     int ld_vec;             // 16-byte loads of the residual / GDN operand are legal
     int store_mode;
+    int bsplit;             // 1: the weight tile of every K step is issued by a second thread (warp 3), the activation patch by warp 0
     int esplit;             // STORE_TMA: epilogue warp groups per 64-column block (narrow GEMMs: 4 or 2 groups share a block, 16 or 32 columns each)
     int nstg;               // STORE_TMA: 16 KB staging buffers behind the stage ring (ring slots x buffers per block)
     int b_resident;         // 1: the whole weight matrix (all K chunks x BN rows, tilesN == 1) is loaded into shared
@@ -483,6 +484,9 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tilesH * p.tilesW;
     const int ksteps = p.ks * p.ks * p.kchunks;
+    // tile walk of every role: t = t_first, t_first + t_step, ... < t_end; (nt, mt) = TILE_OF(t), N tile fastest
+    const int t_first = (int)blockIdx.x, t_step = (int)gridDim.x, t_end = p.ntiles;
+#define TILE_OF(t, nt, mt) const int nt = (t) % p.tilesN; const int mt = (t) / p.tilesN
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.a) : "memory");
@@ -528,8 +532,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     tma_load_2d(bres + (size_t)k * b_bytes, &tm.b, &bres_bar, tap * p.Cpad + cc * 64, 0);
                 }
             }
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-                const int nt = t % p.tilesN, mt = t / p.tilesN;
+            for (int t = t_first; t < t_end; t += t_step) {
+                TILE_OF(t, nt, mt);
                 const int img = mt / tiles_per_img;
                 const int trem = mt - img * tiles_per_img;
                 const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
@@ -581,9 +585,26 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                     mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                     if (p.ck) tma_load_5d(sa, &tm.a, &full_bar[stage], cc * 64, w0, 0, h0 >> 1, img);
                     else tma_load_4d(sa, &tm.a, &full_bar[stage], cc * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
-                    if (!p.b_resident) tma_load_2d(sa + p.a_bytes, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
+                    if (!p.b_resident && !p.bsplit) tma_load_2d(sa + p.a_bytes, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);      // (bsplit: warp 3)
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // second TMA issuer (TcParams::bsplit): the weight tile of every K step.  One thread issuing both boxes of a K step was the
+        // pace of the big 3x3 convs (busy, not waiting, ~900 clocks per K step against 512 clocks of MMA: tools/tc_bench.py role
+        // clocks); a third issuer (the weight tile in halves) adds nothing
+        if (lane == 0 && p.bsplit) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t_first; t < t_end; t += t_step) {
+                const int n0 = ((t) % p.tilesN) * p.BN;
+                for (int k = 0; k < ksteps; ++k) {
+                    mbar_wait<false>(&empty_bar[stage], phase ^ 1);
+                    const int tap = k / p.kchunks, cc = k - tap * p.kchunks;
+                    tma_load_2d(base + (size_t)stage * stage_bytes + p.a_bytes, &tm.b, &full_bar[stage], tap * p.Cpad + cc * 64, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -595,7 +616,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
             uint32_t phase = 0;
             int it = 0;
             if (p.b_resident) { mbar_wait(&bres_bar, 0); tcgen05_fence_after(); }
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+            for (int t = t_first; t < t_end; t += t_step, ++it) {
                 const int as = it & 1;
                 TIMED_SPIN(w2c, &acc_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
@@ -646,7 +667,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
         int stage = 0, rslot = 0;
         uint32_t phase = 0, rphase = 0;
         (void)rslot; (void)rphase;
-        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        for (int t = t_first; t < t_end; t += t_step) {
             for (int k = 0; k < ksteps; ++k) {
                 uint8_t* sa = base + (size_t)stage * stage_bytes;
                 if constexpr (PROD == PROD_DW) {
@@ -760,8 +781,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                                ((uint32_t)sx << 14) | (1u << 15) | ((uint32_t)pofs << 16);
             }
         }
-        for (int t = blockIdx.x; t < p.ntiles && !idle; t += gridDim.x, ++it) {
-            const int nt = t % p.tilesN, mt = t / p.tilesN;
+        for (int t = t_first; t < t_end && !idle; t += t_step, ++it) {
+            TILE_OF(t, nt, mt);
             const int img = mt / tiles_per_img;
             const int trem = mt - img * tiles_per_img;
             const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
@@ -984,6 +1005,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     }
 #undef TIMED_WAIT
 #undef TIMED_SPIN
+#undef TILE_OF
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -1286,6 +1308,10 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     while (p.acc_stride < p.BN * (p.acc_split ? p.ks * p.ks : 1)) p.acc_stride <<= 1;
     p.tilesN = (e.N + p.BN - 1) / p.BN;
     p.ntiles = c.B * p.tilesH * p.tilesW * p.tilesN;
+    {
+        static const int bs_mode = getenv("MLIC_BSPLIT") ? atoi(getenv("MLIC_BSPLIT")) : 1;      // development: 0 = one TMA issuer
+        p.bsplit = (bs_mode && c.prod == PROD_TMA && !p.b_resident && !p.halo && !c.ss && !c.ck && ksteps >= 4) ? 1 : 0;
+    }
     p.ld_vec = (ok16(e.res, e.res_ld, 2) && ok16(e.gdn_x, e.gdn_ld, 2) && (e.N % 8 == 0) && (!e.shuffle || (Cq % 32) == 0)) ? 1 : 0;
     {
         bool v = vec != 0 && (e.N % 8 == 0) && p.ld_vec;
@@ -1388,8 +1414,8 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     const int ri = e.res ? 1 : 0;
     KernelFn fn = table[e.act][e.gdn][ri];
     if (c.prod == PROD_DW) fn = table_dw[e.act][ri];
-    if (!fn) { snprintf(g_tc_err, sizeof g_tc_err, "no kernel instantiation for act=%d res=%d prod=%d", e.act, ri, c.prod); return 9; }
     else if (c.prod == PROD_SQ) fn = table_sq[e.gdn - 1][ri];
+    if (!fn) { snprintf(g_tc_err, sizeof g_tc_err, "no kernel instantiation for act=%d res=%d prod=%d", e.act, ri, c.prod); return 9; }
     if (!attr_set[e.act][e.gdn][ri][c.prod]) {
         cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, budget0 + 1024);
         if (er != cudaSuccess) {
