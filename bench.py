@@ -269,10 +269,10 @@ def main():
         pk = peaks()
         tc_tflops = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         top_tflops = top_flops * top_n / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
-        # DRAM traffic of that launch shape: one `ncu --set full` capture (profiles/r01_ncu_subpel_full.txt), taken at one image
-        # per launch (dram__bytes_read.sum + dram__bytes_write.sum = 196.7 MB; algorithmic 50.1 + 200.5 MB, the tail of the
+        # DRAM traffic of that launch shape: one `ncu --set full` capture (profiles/r01_ncu_subpel_full_late.txt), taken at one image
+        # per launch (dram__bytes_read.sum + dram__bytes_write.sum = 52.9 + 143.3 MB; algorithmic 50.1 + 200.5 MB, the tail of the
         # output is still in L2 when the kernel ends); scaled here to this run's images per launch.
-        ncu_bytes_per_image = 196.7e6 * (4 if args.size == "4k" else 1)
+        ncu_bytes_per_image = 196.2e6 * (4 if args.size == "4k" else 1)
         roof = {"bound": "tensor",
                 "kernel": "conv_gemm_tc_kernel<GELU|none> as the 3x3 192->768 sub-pixel convolution at 272x480 (g_s.5 subpel_conv / upsample): "
                           "the heaviest launch shape, 2 launches per step" + (" (4k: the same layer at 544x960)" if args.size == "4k" else ""),
