@@ -1300,7 +1300,13 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         }
     }
     if (!planned) { snprintf(g_tc_err, sizeof g_tc_err, "no shared-memory plan for BN=%d ksteps=%d", p.BN, ksteps); return 8; }
-    p.l2_prefetch = (p.ks == 1 && c.prod != PROD_SQ && !c.ck && !(p.debug & 16)) ? (c.prod == PROD_DW ? 2 : 3) : 0;
+    // L2 prefetch of the A patch a few tiles ahead (MLIC_L2PF_MB = input size in MB from which it is used; default: never).  It paid
+    // while the pointwise layers were DRAM-latency-bound; they are epilogue-bound now, and on the slice loop's GEMMs the extra TMA
+    // instructions only load the single issuing thread.  Same box, 32 / 8 images per step: always 526 / 501, >= 384 MB 531 / 501,
+    // never 533 / 504 MP/s.
+    static const double pf_mb = getenv("MLIC_L2PF_MB") ? atof(getenv("MLIC_L2PF_MB")) : 1e12;
+    const bool streams = (double)c.B * c.H * c.W * c.Cin * 2.0 >= pf_mb * 1e6;
+    p.l2_prefetch = (p.ks == 1 && c.prod != PROD_SQ && !c.ck && !(p.debug & 16) && streams) ? (c.prod == PROD_DW ? 2 : 3) : 0;
     if (c.prod != PROD_TMA && p.store_mode == STORE_DIRECT) p.epi_vec = p.epi_vec && p.ld_vec;
     // (development, MLIC_HALO bit3; measured slower than the single accumulator: 420 us vs 195 us on the final 192 -> 12 conv)
     p.acc_split = ((halo_mode & 8) && p.halo && p.store_mode == STORE_NCHW3 && p.BN == 16 && p.ks * p.ks * p.BN <= 256) ? 1 : 0;
