@@ -173,6 +173,9 @@ def main():
         return
 
     import torch.distributed as dist
+    if world > 1 and os.environ.get("MLIC_BIND_CPUS", "1") != "0":
+        from mlic_b200.dist import bind_to_gpu_cpus
+        bind_to_gpu_cpus(local)                # host staging memory next to this rank's GPU (matters for `e2e` on two-socket boxes)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

@@ -15,6 +15,30 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def bind_to_gpu_cpus(device_index):
+    """Pins the calling process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root), so
+    that the pinned host buffers of the host-buffer path are first-touched next to the GPU that reads them.  Multi-rank jobs on
+    a two-socket box otherwise put half of the ranks' staging memory across the socket link.  Returns the core list or None."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def rd_sums(out, x):
     """Per-rank sums of loss/rd_loss.py:37-48: [sum log2(likelihoods), sum squared error, pixels (unpadded N*H*W)]."""
     n, _, h, w = x.shape
