@@ -23,7 +23,7 @@ extern "C" {
 
 typedef struct mlic_engine mlic_engine;
 
-enum { MLIC_KIND_BASE = 0, MLIC_KIND_SD = 1, MLIC_KIND_VBR = 2 };   /* MLICPlusPlus / ...SD / ...Vbr */
+enum { MLIC_KIND_BASE = 0, MLIC_KIND_SD = 1, MLIC_KIND_VBR = 2, MLIC_KIND_SD_VBR = 3 };   /* MLICPlusPlus / ...SD / ...Vbr / ...SDVbr (bit 0: small decoder, bit 1: gains) */
 enum { MLIC_PREC_FP32 = 0, MLIC_PREC_BF16 = 1 };                    /* validation mode / fast mode   */
 enum { MLIC_MODE_FORWARD = 0, MLIC_MODE_COMPRESS = 1, MLIC_MODE_DECODER = 2, MLIC_MODE_DECOMPRESS = 3 /* mlic_decompress only */ };
 

@@ -1167,12 +1167,12 @@ const char* mlic_version(void) { return "mlic_b200 0.1 (sm_100a)"; }
 int mlic_engine_create(int N, int M, int slice_num, int kind, mlic_engine** out) {
     if (!out) return fail("out is NULL");
     if (N <= 0 || M <= 0 || slice_num <= 0 || M % slice_num) return fail("M must be divisible by slice_num");     // mlicpp.py:21
-    if (kind < 0 || kind > 2) return fail("bad kind %d", kind);
+    if (kind < 0 || kind > 3) return fail("bad kind %d", kind);
     int C = M / slice_num;
     if (C != 32 && C != 64) return fail("slice width %d unsupported (32 or 64)", C);
     mlic_engine* e = new mlic_engine();
     e->N = N; e->M = M; e->S = slice_num; e->C = C; e->kind = kind;
-    e->sd = kind == MLIC_KIND_SD; e->vbr = kind == MLIC_KIND_VBR;
+    e->sd = (kind & MLIC_KIND_SD) != 0; e->vbr = (kind & MLIC_KIND_VBR) != 0;
     e->Me = e->sd ? M / 4 : M;
     *out = e;
     return 0;

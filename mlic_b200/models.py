@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .params import KIND_CODE, MODEL_TABLE, VBR_GAINS, VBR_LAMBDAS, build_entries
+from .params import KIND_CODE, MODEL_TABLE, SDVBR_GAINS, SDVBR_LAMBDAS, VBR_GAINS, VBR_LAMBDAS, build_entries
 
 
 def model_config(name):
@@ -69,7 +69,7 @@ def _init_tensor(entry):
     if kind == "relpos_index":
         return _relpos_index(5)
     if kind == "vbr_gain":
-        return torch.tensor(VBR_GAINS, dtype=torch.float32)
+        return torch.tensor(SDVBR_GAINS if shape[0] == len(SDVBR_GAINS) else VBR_GAINS, dtype=torch.float32)
     if kind == "empty":
         return torch.zeros(shape, dtype=dt)
     raise ValueError(kind)
@@ -483,10 +483,11 @@ class MLICPlusPlusSD(MLICPlusPlus):
 class MLICPlusPlusVbr(MLICPlusPlus):
     """models/mlicpp_vbr.py:14-117: 6 gain levels, stage-2 gain-scaled quantisation (no_quantoffset=True)."""
     KIND = "vbr"
+    LAMBDAS = VBR_LAMBDAS
 
     def __init__(self, config, name=None, **kwargs):
         super().__init__(config, name=name, **kwargs)
-        self.lmbda = list(VBR_LAMBDAS)
+        self.lmbda = list(self.LAMBDAS)
         self.levels = len(self.lmbda)
         self.no_quantoffset = True
         self.vr_entbttlnck = None
@@ -528,7 +529,14 @@ class MLICPlusPlusVbr(MLICPlusPlus):
         return super().decompress(strings, shape, taps=taps, _gain=self._scale(s, inputscale, True))
 
 
-_CLASSES = {"base": MLICPlusPlus, "sd": MLICPlusPlusSD, "vbr": MLICPlusPlusVbr}
+class MLICPlusPlusSDVbr(MLICPlusPlusVbr):
+    """models/mlicpp_sd_vbr.py:19-127: the small-decoder network (dense encoder, quarter-width h_s / g_s / contexts,
+    LRP-Old) under the Vbr methods, 5 gain levels. forward / compress / decompress bodies are those of mlicpp_vbr.py."""
+    KIND = "sdvbr"
+    LAMBDAS = SDVBR_LAMBDAS
+
+
+_CLASSES = {"base": MLICPlusPlus, "sd": MLICPlusPlusSD, "vbr": MLICPlusPlusVbr, "sdvbr": MLICPlusPlusSDVbr}
 
 
 def get_model(name):

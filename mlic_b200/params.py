@@ -18,10 +18,13 @@ MODEL_TABLE = {
     "MLICPP_M_SMALL_DEC": dict(N=192, M=320, slice_num=10, kind="sd"),
     "MLICPP_S_VBR": dict(N=96, M=160, slice_num=5, kind="vbr"),
     "MLICPP_L_VBR": dict(N=192, M=320, slice_num=10, kind="vbr"),
+    "MLICPP_M_SMALL_DEC_VBR": dict(N=192, M=320, slice_num=10, kind="sdvbr"),   # mlicpp_sd_vbr.py:19-127
 }
-KIND_CODE = {"base": 0, "sd": 1, "vbr": 2}
+KIND_CODE = {"base": 0, "sd": 1, "vbr": 2, "sdvbr": 3}
 VBR_GAINS = (0.06556, 0.13944, 0.19293, 0.37268, 0.51801, 1.00000)   # mlicpp_vbr.py:86-91
 VBR_LAMBDAS = (0.0005, 0.0035, 0.0067, 0.025, 0.0483, 0.18)          # mlicpp_vbr.py:83
+SDVBR_GAINS = (0.002424, 0.06556, 0.13944, 0.51801, 1.00000)          # mlicpp_sd_vbr.py:95-100 (5 levels)
+SDVBR_LAMBDAS = (0.0002, 0.0005, 0.0035, 0.0483, 0.18)                # mlicpp_sd_vbr.py:92
 
 
 class Entry:
@@ -102,7 +105,7 @@ def build_entries(name):
     N, M, S, kind = cfg["N"], cfg["M"], cfg["slice_num"], cfg["kind"]
     C = M // S
     assert C * S == M, "M must be divisible by slice_num"      # mlicpp.py:21
-    sd = kind == "sd"
+    sd = kind in ("sd", "sdvbr")
     b = _Builder()
     e = b.e
 
@@ -217,8 +220,8 @@ def build_entries(name):
             for j, ci, co in zip(idx, widths[:-1], widths[1:]):
                 b.dsconv(p + str(j), ci, co)
     # VBR extras (mlicpp_vbr.py:83-101)
-    if kind == "vbr":
-        e["Gain"] = Entry((len(VBR_GAINS),), init=("vbr_gain", None))
+    if kind in ("vbr", "sdvbr"):                       # mlicpp_sd_vbr.py:92-110 for the SD variant
+        e["Gain"] = Entry((len(SDVBR_GAINS if sd else VBR_GAINS),), init=("vbr_gain", None))
         for j, (ci, co) in zip((0, 2, 4), ((2, 12), (12, 12), (12, 1))):
             b.linear(f"QuantABCD.{j}", ci, co)
     return e

@@ -22,6 +22,7 @@ CASES = [
     ("MLICPP_M_SMALL_DEC", 1, 64, 128, 1234, 16.0, 6.0, None, None),
     ("MLICPP_S_VBR", 1, 64, 128, 1234, 16.0, 6.0, range(6), 2),
     ("MLICPP_L_VBR", 1, 64, 64, 1234, 16.0, 6.0, range(6), 1),
+    ("MLICPP_M_SMALL_DEC_VBR", 1, 64, 128, 1234, 16.0, 6.0, range(5), 3),      # mlicpp_sd_vbr.py: 5 gain levels
 ]
 
 
@@ -29,10 +30,13 @@ def case_file(name, B, H, W):
     return os.path.join(OUT, f"{name}_b{B}_{H}x{W}.npz")
 
 
-def main():
+def main(only=None):
+    """only: optional list of model names -- regenerate just those fixtures."""
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     for name, B, H, W, seed, yg, ss, levels, fwd_level in CASES:
+        if only and name not in only:
+            continue
         net = ref_loader.get_reference_model(name)
         sd = weights.seeded_state_dict(net.state_dict(), seed, y_gain=yg, sigma_spread=ss)
         net.load_state_dict(sd)
@@ -67,4 +71,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(sys.argv[1:] or None)

@@ -29,6 +29,7 @@ MODEL_TABLE = {
     "MLICPP_M_SMALL_DEC": dict(N=192, M=320, slices=10, kind="sd"),
     "MLICPP_S_VBR": dict(N=96, M=160, slices=5, kind="vbr"),
     "MLICPP_L_VBR": dict(N=192, M=320, slices=10, kind="vbr"),
+    "MLICPP_M_SMALL_DEC_VBR": dict(N=192, M=320, slices=10, kind="sdvbr"),   # mlicpp_sd_vbr.py:19-127
 }
 
 SCALE_MIN, SCALE_MAX, SCALE_LEVELS = 0.11, 256.0, 64
@@ -100,6 +101,7 @@ class Oracle:
     def __init__(self, name, state_dict, dtype=torch.float32):
         cfg = MODEL_TABLE[name]
         self.name, self.kind = name, cfg["kind"]
+        self.sd, self.vbr = self.kind in ("sd", "sdvbr"), self.kind in ("vbr", "sdvbr")
         self.N, self.M, self.S = cfg["N"], cfg["M"], cfg["slices"]
         self.C = self.M // self.S
         self.dtype = dtype
@@ -157,7 +159,7 @@ class Oracle:
     # ---------------------------------------------------------------- transforms
     def g_a(self, x):
         """transform/analysis.py:9-17 (analysis_old.py:10-16 = dense, SD)."""
-        d = self.kind == "sd"
+        d = self.sd
         p = "g_a.analysis_transform."
         for i in (0, 2, 4):
             x = self._rbws(x, p + str(i), d)
@@ -166,7 +168,7 @@ class Oracle:
 
     def h_a(self, y):
         """transform/analysis.py:33-43"""
-        d = self.kind == "sd"
+        d = self.sd
         p = "h_a.reduction."
         x = y
         for i, s in zip((0, 2, 4, 6, 8), (1, 1, 2, 1, 2)):
@@ -221,7 +223,7 @@ class Oracle:
 
     def _lrp(self, x, p):
         """transform/quantization.py:33-44 (:12-28 for the SD 'Old' pyramid) -- 0.5*tanh(stack)."""
-        idxs = (0, 2, 4, 6) if self.kind == "sd" else (0, 2, 4)
+        idxs = (0, 2, 4, 6) if self.sd else (0, 2, 4)
         for n, i in enumerate(idxs):
             x = self._ds(x, f"{p}.lrp_transform.{i}")
             if n != len(idxs) - 1:
@@ -230,7 +232,7 @@ class Oracle:
 
     def _channel_ctx(self, x, p):
         """transform/context.py:118-138 (context_old.py:120-126 = dense, SD)."""
-        d = self.kind == "sd"
+        d = self.sd
         x = F.gelu(self._c3(x, p + ".fushion.0", dense=d))
         x = F.gelu(self._c3(x, p + ".fushion.2", dense=d))
         return self._c3(x, p + ".fushion.4", dense=d)
@@ -320,7 +322,7 @@ class Oracle:
     # ---------------------------------------------------------------- the slice loop
     def _gain(self, s, inputscale=0):
         """mlicpp_vbr.py:122-135 (forward, eval) / :537-544 (compress: abs)."""
-        if self.kind != "vbr":
+        if not self.vbr:
             return None
         if inputscale != 0:
             return torch.tensor(float(inputscale), dtype=self.dtype)

@@ -12,7 +12,12 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 # name, B, H, W  (fixtures produced by oracle/make_golden.py from the unmodified reference)
 CASES = [("MLICPP_S", 2, 64, 128), ("MLICPP_L", 1, 64, 128), ("MLICPP_M_SMALL_DEC", 1, 64, 128),
-         ("MLICPP_S_VBR", 1, 64, 128), ("MLICPP_L_VBR", 1, 64, 64)]
+         ("MLICPP_S_VBR", 1, 64, 128), ("MLICPP_L_VBR", 1, 64, 64), ("MLICPP_M_SMALL_DEC_VBR", 1, 64, 128)]
+
+
+def vbr_levels(g):
+    """Gain levels a VBR fixture holds symbols for (6 for mlicpp_vbr.py:86-91, 5 for mlicpp_sd_vbr.py:95-100)."""
+    return [lv for lv in range(8) if f"symbols_s{lv}" in g]
 
 
 def pytest_configure(config):

@@ -12,13 +12,15 @@ def test_registry_matches_reference_configs():
     # config/config.py:19-62
     assert {k: (v["N"], v["M"], v["slice_num"]) for k, v in mlic_b200.MODEL_TABLE.items()} == {
         "MLICPP_L": (192, 320, 10), "MLICPP_M": (160, 256, 8), "MLICPP_S": (96, 160, 5), "MLICPP_S2": (128, 128, 2),
-        "MLICPP_M_SMALL_DEC": (192, 320, 10), "MLICPP_S_VBR": (96, 160, 5), "MLICPP_L_VBR": (192, 320, 10)}
+        "MLICPP_M_SMALL_DEC": (192, 320, 10), "MLICPP_S_VBR": (96, 160, 5), "MLICPP_L_VBR": (192, 320, 10),
+        "MLICPP_M_SMALL_DEC_VBR": (192, 320, 10)}
     with pytest.raises(KeyError):
         mlic_b200.get_model("MLICPP_XL")
 
 
 @pytest.mark.parametrize("name,nparams,nkeys", [("MLICPP_L", 41.72e6, 1261), ("MLICPP_S", 11.79e6, 711),
-                                                 ("MLICPP_M_SMALL_DEC", 25.07e6, 1251), ("MLICPP_L_VBR", None, 1268)])
+                                                 ("MLICPP_M_SMALL_DEC", 25.07e6, 1251), ("MLICPP_L_VBR", None, 1268),
+                                                 ("MLICPP_M_SMALL_DEC_VBR", 25072266, 1258)])
 def test_state_dict_layout(name, nparams, nkeys):
     net = mlic_b200.get_model(name)
     sd = net.state_dict()
@@ -32,7 +34,7 @@ def test_state_dict_layout(name, nparams, nkeys):
     assert net.slice_ch * net.slice_num == net.M
     assert len(net.local_context) == net.slice_num
     conv1 = net.g_a.analysis_transform[0].conv1
-    if name == "MLICPP_M_SMALL_DEC":                  # dense encoder (analysis_old.py:10-16)
+    if name.startswith("MLICPP_M_SMALL_DEC"):         # dense encoder (analysis_old.py:10-16)
         assert conv1.weight.shape == (net.N, 3, 3, 3)
     else:                                             # depthwise-separable (conv.py:46-63)
         assert conv1.depth_conv.weight.shape == (3, 1, 3, 3) and conv1.point_conv.weight.shape == (net.N, 3, 1, 1)
@@ -53,6 +55,19 @@ def test_load_state_dict_and_update():
     bad.pop("g_a.analysis_transform.6.point_conv.bias")
     with pytest.raises(RuntimeError):
         other.load_state_dict(bad)
+
+
+def test_sd_vbr_surface():
+    """models/mlicpp_sd_vbr.py:92-110: 5 levels, own gain / lambda tables, the Vbr call signatures."""
+    net = mlic_b200.get_model("MLICPP_M_SMALL_DEC_VBR")
+    assert isinstance(net, mlic_b200.MLICPlusPlusSDVbr) and isinstance(net, mlic_b200.MLICPlusPlusVbr)
+    assert net.levels == 5 and net.lmbda == [0.0002, 0.0005, 0.0035, 0.0483, 0.18]
+    np.testing.assert_allclose(net.Gain.detach().numpy(), [0.002424, 0.06556, 0.13944, 0.51801, 1.0], rtol=1e-6)
+    assert net.lrp_anchor[0].lrp_transform[6].point_conv.weight.shape[0] == net.slice_ch      # LRP-Old pyramid, 4 convs
+    with pytest.raises(AssertionError):
+        net._scale(5, 0, True)                                       # mlicpp_sd_vbr.py compress: s in range(levels)
+    with pytest.raises(ValueError):
+        net.forward(torch.zeros(1, 3, 64, 64), stage=0)
 
 
 def test_vbr_surface():
