@@ -41,11 +41,12 @@ def test_compress_decompress_round_trip(name, precision, B, H, W):
     assert d["cost_time"] > 0 and net.last_launch_count > 100
 
 
-def test_vbr_levels_round_trip():
-    net = _net("MLICPP_L_VBR", "fp32", 16.0)
+@pytest.mark.parametrize("name,levels", [("MLICPP_L_VBR", (0, 3, 5)), ("MLICPP_M_SMALL_DEC_VBR", (0, 2, 4))])
+def test_vbr_levels_round_trip(name, levels):
+    net = _net(name, "fp32", 16.0)
     x = weights.synthetic_image(1, 64, 128, seed=22).cuda()
     sizes = []
-    for s in (0, 3, 5):
+    for s in levels:
         c = net.compress(x, stage=2, s=s, taps=("y_hat",))
         d = net.decompress(c["strings"], c["shape"], stage=2, s=s, taps=("y_hat",))
         assert torch.equal(d["y_hat"], c["y_hat"]) and torch.equal(d["x_hat"], c["x_hat"]), s
