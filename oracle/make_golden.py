@@ -23,6 +23,8 @@ CASES = [
     ("MLICPP_S_VBR", 1, 64, 128, 1234, 16.0, 6.0, range(6), 2),
     ("MLICPP_L_VBR", 1, 64, 64, 1234, 16.0, 6.0, range(6), 1),
     ("MLICPP_M_SMALL_DEC_VBR", 1, 64, 128, 1234, 16.0, 6.0, range(5), 3),      # mlicpp_sd_vbr.py: 5 gain levels
+    ("MLICPP_M", 1, 64, 128, 1234, 16.0, 6.0, None, None),                     # 8 slices of 32
+    ("MLICPP_S2", 1, 128, 128, 1234, 16.0, 6.0, None, None),                   # 2 slices of 64 (head_dim 32 everywhere)
 ]
 
 

@@ -12,7 +12,8 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 # name, B, H, W  (fixtures produced by oracle/make_golden.py from the unmodified reference)
 CASES = [("MLICPP_S", 2, 64, 128), ("MLICPP_L", 1, 64, 128), ("MLICPP_M_SMALL_DEC", 1, 64, 128),
-         ("MLICPP_S_VBR", 1, 64, 128), ("MLICPP_L_VBR", 1, 64, 64), ("MLICPP_M_SMALL_DEC_VBR", 1, 64, 128)]
+         ("MLICPP_S_VBR", 1, 64, 128), ("MLICPP_L_VBR", 1, 64, 64), ("MLICPP_M_SMALL_DEC_VBR", 1, 64, 128),
+         ("MLICPP_M", 1, 64, 128), ("MLICPP_S2", 1, 128, 128)]
 
 
 def vbr_levels(g):
