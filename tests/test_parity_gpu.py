@@ -49,7 +49,7 @@ def test_fp32_mode_bit_exact_symbols_and_tight_outputs(name, B, H, W):
 
 
 @pytest.mark.parametrize("tensor_cores", [False, True])
-@pytest.mark.parametrize("name,B,H,W", CASES[:3])
+@pytest.mark.parametrize("name,B,H,W", CASES[:3] + CASES[6:])
 def test_bf16_mode_on_stress_fixture(name, B, H, W, tensor_cores):
     """y_gain = 16 fixtures: |y| is tens of quantisation steps, so bf16 activation noise (2^-9 relative) moves ~0.5 % of
     the symbols across a rounding boundary; the bar here is >= 99 % symbol agreement, x_hat within 35 dB of the
