@@ -194,3 +194,48 @@ def test_host_buffer_call_bf16_pipelined_matches_device_call():
     assert torch.equal(host["x_hat"], dev["x_hat"].cpu())
     assert torch.equal(host["likelihoods"]["y_likelihoods"], dev["likelihoods"]["y_likelihoods"].cpu())
     assert torch.equal(host["likelihoods"]["z_likelihoods"], dev["likelihoods"]["z_likelihoods"].cpu())
+
+
+def _stress_net(name, precision):
+    import mlic_b200
+    net = mlic_b200.get_model(name)
+    net.load_state_dict(weights.seeded_state_dict(net.state_dict(), 1234, y_gain=16.0, sigma_spread=6.0))
+    net.update(force=True)
+    return net.cuda().set_precision(precision)
+
+
+def test_graphed_call_replays_the_same_forward():
+    """CUDA-graph replay of a fixed-shape call (mlic_b200.models.GraphedCall): bit-identical outputs for new inputs, also for
+    the decoder-side walk; shape and stale-weight misuse raise."""
+    B, H, W = 2, 128, 192
+    net = _stress_net("MLICPP_L", "bf16")
+    g = net.graphed(B, H, W)
+    assert g.launches > 100
+    for seed in (5, 6):
+        x = weights.synthetic_image(B, H, W, seed=seed).cuda()
+        plain = net(x)
+        out = g(x)
+        assert torch.equal(out["x_hat"], plain["x_hat"])
+        assert torch.equal(out["likelihoods"]["y_likelihoods"], plain["likelihoods"]["y_likelihoods"])
+        assert torch.equal(out["likelihoods"]["z_likelihoods"], plain["likelihoods"]["z_likelihoods"])
+    gd = net.graphed(B, H, W, fn=net.net_decoder_forward)
+    assert torch.equal(gd(x), net.net_decoder_forward(x))
+    with pytest.raises(ValueError):
+        g(x[:1])
+    with torch.no_grad():
+        net.g_a.analysis_transform[6].point_conv.bias.add_(0.25)
+    with pytest.raises(RuntimeError):
+        g(x)
+
+
+def test_graphed_vbr_forward():
+    """A VBR call is captured with its gain resolved beforehand (`inputscale`): reading `Gain[s]` is a device -> host copy,
+    which a capturing stream does not allow."""
+    vbr = _stress_net("MLICPP_S_VBR", "fp32")
+    gain = vbr._scale(3, 0, False)
+    gv = vbr.graphed(1, 64, 128, fn=lambda t: vbr(t, stage=2, inputscale=gain))
+    xv = weights.synthetic_image(1, 64, 128, seed=7).cuda()
+    ref = vbr(xv, stage=2, s=3)
+    out = gv(xv)
+    assert torch.equal(out["x_hat"], ref["x_hat"])
+    assert torch.equal(out["likelihoods"]["y_likelihoods"], ref["likelihoods"]["y_likelihoods"])

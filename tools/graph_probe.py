@@ -1,39 +1,42 @@
-"""Development probe (GPU): one forward replayed from a captured CUDA graph vs launched from the host."""
-import sys, os
+"""Development probe (GPU): fixed-shape calls replayed from a captured CUDA graph (mlic_b200.models.GraphedCall) vs launched
+from the host -- MLICPP_L forward and the MLICPP_M_SMALL_DEC decoder-side walk at 1920x1088."""
+import json, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from oracle import weights
 
-net = bench.seeded_model("MLICPP_L", "cuda:0").set_precision("bf16")
-for B in [int(a) for a in sys.argv[1:]] or [1, 8]:
-    x = weights.synthetic_image(B, 1088, 1920, seed=2024, kind="rand").cuda()
-    s = torch.cuda.Stream()
-    with torch.cuda.stream(s):
-        for _ in range(3):
-            out = net(x)
-        s.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(s)
-        for _ in range(5):
-            out = net(x)
-        e1.record(s)
-        s.synchronize()
-        plain = e0.elapsed_time(e1) / 5
-        ref = {k: v.clone() for k, v in (("x_hat", out["x_hat"]), ("lik", out["likelihoods"]["y_likelihoods"]))}
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s):
-            out = net(x)
-        for _ in range(2):
-            g.replay()
-        s.synchronize()
-        e0.record(s)
-        for _ in range(5):
-            g.replay()
-        e1.record(s)
-        s.synchronize()
-        graph = e0.elapsed_time(e1) / 5
-    same = torch.equal(out["x_hat"], ref["x_hat"]) and torch.equal(out["likelihoods"]["y_likelihoods"], ref["lik"])
-    mp = B * 1920 * 1088 / 1e6
-    print(f"B={B}: host-launched {plain:.2f} ms ({mp/plain*1e3:.0f} MP/s)  graph replay {graph:.2f} ms ({mp/graph*1e3:.0f} MP/s)  identical={same}", flush=True)
-    del g
+
+def timed(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+H, W = 1088, 1920
+res = {}
+for name, what in (("MLICPP_L", "forward"), ("MLICPP_M_SMALL_DEC", "net_decoder_forward")):
+    net = bench.seeded_model(name, "cuda:0").set_precision("bf16")
+    fn = net if what == "forward" else net.net_decoder_forward
+    for B in [int(a) for a in sys.argv[1:]] or [1, 4]:
+        x = weights.synthetic_image(B, H, W, seed=2024, kind="rand").cuda()
+        plain = timed(lambda: fn(x))
+        ref = fn(x)
+        ref = (ref["x_hat"] if isinstance(ref, dict) else ref).clone()
+        g = net.graphed(B, H, W, fn=fn)
+        graph = timed(lambda: g(x))
+        out = g(x)
+        out = out["x_hat"] if isinstance(out, dict) else out
+        mp = B * H * W / 1e6
+        res[f"{name}.{what}.b{B}"] = {"host_launched_ms": plain, "graph_replay_ms": graph, "mp_per_s_host": mp / plain * 1e3,
+                                      "mp_per_s_graph": mp / graph * 1e3, "identical": bool(torch.equal(out, ref)), "launches": g.launches}
+        del g
+    del net
+print(json.dumps(res))
