@@ -2,6 +2,7 @@
 (tests/golden/stream_container.*, from oracle/make_stream_golden.py), and the file-level codec calls on the GPU."""
 import io
 import json
+import math
 import os
 
 import pytest
@@ -66,3 +67,52 @@ def test_file_round_trip_on_the_engine(name, tmp_path):
     assert x_hat.shape == (1, 3, 100, 150) and torch.equal(x_hat, ref[:, :, :100, :150])
     assert bpp == os.path.getsize(tmp_path / "a.bin") * 8 / (100 * 150) and bpp > 0
     assert stream.psnr(img, img) == float("inf") and 0 < stream.psnr(x_hat, img) < 60
+
+
+def test_eval_helpers_on_cpu():
+    """testing.py:264-295 Gaussian (sigma 0.5, normalised, zero padding) and the 8-bit PSNR of metrics.py:26-33."""
+    one = torch.ones(1, 3, 8, 8)
+    b = stream.gaussian_blur3(one)
+    e, c = math.exp(-2.0), math.exp(-4.0)
+    tot = 1 + 4 * e + 4 * c
+    assert b.shape == one.shape and float((b[:, :, 1:-1, 1:-1] - 1).abs().max()) < 1e-6
+    assert float(b[0, 0, 0, 0]) == pytest.approx((1 + 2 * e + c) / tot, rel=1e-6)       # corner: zero padding
+    delta = torch.zeros(1, 3, 5, 5)
+    delta[:, :, 2, 2] = 1
+    k = stream.gaussian_blur3(delta)[0, 1, 1:4, 1:4]
+    assert float(k[1, 1]) == pytest.approx(1 / tot, rel=1e-6) and float(k[0, 1]) == pytest.approx(e / tot, rel=1e-6)
+    a = torch.full((1, 3, 4, 4), 0.5)
+    assert stream.to_uint8(a).unique().tolist() == [127]                                # truncation, not rounding
+    assert stream.psnr_8bit(a, a) == float("inf")
+    assert stream.psnr_8bit(a, a + 2.0 / 255) == pytest.approx(20 * math.log10(255) - 10 * math.log10(4.0), abs=1e-9)
+    assert stream.psnr_8bit(torch.full((1, 3, 2, 2), 1.7), torch.ones(1, 3, 2, 2)) == float("inf")   # clamp first
+
+
+@pytest.mark.gpu
+def test_eval_loops_on_the_engine(tmp_path):
+    """stream.test_model / test_model_vbr (testing.py:338-520 without the perceptual metrics)."""
+    import mlic_b200
+    from oracle import weights
+
+    def build(name):
+        net = mlic_b200.get_model(name)
+        net.load_state_dict(weights.seeded_state_dict(net.state_dict(), 1234, y_gain=16.0, sigma_spread=6.0))
+        net.update(force=True)
+        return net.to("cuda").set_precision("fp32")
+
+    imgs = [weights.synthetic_image(1, 128, 192, seed=51)[:, :, :100, :150], weights.synthetic_image(1, 64, 128, seed=52)]
+    net = build("MLICPP_S")
+    lines = []
+    r = stream.test_model(imgs, net, str(tmp_path / "a"), cons=1e9, log=lines.append)
+    assert len(r["images"]) == 2 and len(lines) == 2 and all(rec["blurs"] == 0 for rec in r["images"])
+    assert r["images"][0]["bpp"] == os.path.getsize(tmp_path / "a" / "0") * 8 / (100 * 150)
+    assert r["avg"]["bpp"] == pytest.approx(sum(rec["bpp"] for rec in r["images"]) / 2)
+    assert all(5 < rec["psnr"] < 60 and rec["enc_time"] > 0 and rec["dec_time"] > 0 for rec in r["images"])
+    r2 = stream.test_model(imgs[:1], net, str(tmp_path / "b"), cons=1e-6, max_blur=2)            # the blur-until-it-fits loop
+    assert r2["images"][0]["blurs"] == 2 and r2["images"][0]["bpp"] > 0
+    vbr = build("MLICPP_S_VBR")
+    rv = stream.test_model_vbr(imgs[1:], vbr, str(tmp_path / "v"))
+    assert sorted(rv) == list(range(6)) and all(len(v["images"]) == 1 and v["avg"]["bpp"] > 0 for v in rv.values())
+    assert os.path.exists(tmp_path / "v" / "000_lv05")
+    rg = stream.test_model_vbr(imgs[1:], vbr, str(tmp_path / "g"), custom_scales=[0.25])          # forced gain
+    assert list(rg) == [0.25] and rg[0.25]["avg"]["psnr"] > 5
