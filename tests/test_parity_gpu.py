@@ -239,3 +239,25 @@ def test_graphed_vbr_forward():
     out = gv(xv)
     assert torch.equal(out["x_hat"], ref["x_hat"])
     assert torch.equal(out["likelihoods"]["y_likelihoods"], ref["likelihoods"]["y_likelihoods"])
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_rd_sums_of_the_engine(host):
+    """mlic_buffers.rd_sums (loss/rd_loss.py:37-48: sum log2 of both likelihood tensors, sum of squared error), reduced on the
+    device in the same call, against the same sums taken from the returned tensors; device-buffer and host-buffer calls."""
+    from mlic_b200 import _lib
+    from mlic_b200.dist import aggregate_rd, rd_sums
+    B, H, W = 2, 128, 192
+    net = _stress_net("MLICPP_S", "bf16")
+    x = weights.synthetic_image(B, H, W, seed=9)
+    xin = x.pin_memory() if host else x.cuda()
+    o = net._run(_lib.MODE_FORWARD, xin, B, H, W, 0.0, ("rd_sums",))
+    if not host:
+        torch.cuda.synchronize()
+    out = {"x_hat": o["x_hat"], "likelihoods": {"y": o["y_likelihoods"], "z": o["z_likelihoods"]}}
+    ref = rd_sums(out, xin)
+    got = o["rd_sums"].cpu()
+    assert float(got[0]) == pytest.approx(float(ref[0]), rel=1e-6) and float(got[0]) < 0       # log2f per element, double sums
+    assert float(got[1]) == pytest.approx(float(ref[1]), rel=1e-6)
+    bpp, mse, psnr = aggregate_rd(torch.stack([got[0], got[1], torch.tensor(float(B * H * W), dtype=torch.float64)]))
+    assert bpp == pytest.approx(-float(ref[0]) / (B * H * W)) and mse > 0 and psnr > 0
