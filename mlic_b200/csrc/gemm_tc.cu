@@ -517,6 +517,12 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // Programmatic dependent launch (launch attribute set by launch_conv_tc when enabled; both instructions are no-ops
+    // otherwise): everything above -- barrier init, TMEM allocation, bias / depthwise weights (parameters, never written by
+    // a kernel of the walk) -- may run while the previous kernel of the stream drains; no activation is touched before the
+    // wait.  The trigger lets the NEXT kernel's CTAs do the same as soon as this grid's CTAs leave their SMs.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1445,7 +1451,26 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
         cudaMemsetAsync(dbuf, 0, 148 * 11 * sizeof(unsigned long long), s);
         dbg = dbuf;
     }
-    fn<<<grid, c.prod == PROD_TMA ? TC_THREADS : TC_FUSED_THREADS, smem, s>>>(tm, p, e, dbg);
+    // MLIC_PDL: 1 (default) programmatic stream serialization -- the kernel's prologue overlaps the tail of its predecessor:
+    // one 1920x1088 forward 8.61 -> 7.67 ms, 32 images 130.2 -> 129.8 ms (profiles/r01_pdl_probe.txt); 0 plain launch;
+    // 2 as 1 with the dynamic shared memory padded above half an SM, so that early CTAs of a small-footprint launch cannot
+    // double up on the SMs that free first (measured: no better than 1)
+    static const int pdl = getenv("MLIC_PDL") ? atoi(getenv("MLIC_PDL")) : 1;
+    const unsigned nthreads = c.prod == PROD_TMA ? TC_THREADS : TC_FUSED_THREADS;
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(nthreads);
+        cfg.dynamicSmemBytes = pdl == 2 ? std::max<size_t>(smem, (size_t)117 * 1024) : smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, fn, tm, p, e, dbg);
+    } else
+    fn<<<grid, nthreads, smem, s>>>(tm, p, e, dbg);
     if (dbg) {
         static int printed = 0;
         unsigned long long h[148 * 11];
