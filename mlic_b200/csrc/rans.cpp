@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "../../include/mlic_b200.h"
@@ -26,16 +27,38 @@ constexpr int kBypassBits = 4;
 constexpr uint32_t kMaxBypass = (1u << kBypassBits) - 1;
 constexpr uint64_t kRansL = 1ull << 31;
 
-struct Sym {
-    uint16_t start;
-    uint16_t range;       // 0 = 2^16 never occurs: a symbol always leaves room for the others
-    bool bypass;
-};
 
-inline void enc_put(uint64_t& x, uint32_t*& p, uint32_t start, uint32_t freq, int bits) {
+// x / freq without a divide (the 64-bit division is most of an encoder step): Alverson reciprocals as in ryg_rans'
+// rans64.h -- rcp = ceil(2^(shift+63) / freq), shift = ceil(log2 freq); q = mulhi(x, rcp) >> (shift - 1) is exact for
+// every state x < 2^63.  One entry per frequency 1..2^16, built once (tests/test_coder.py checks it against `/`).
+struct Rcp {
+    uint64_t rcp;
+    uint32_t shift;
+};
+const Rcp* rcp_table() {
+    static const std::vector<Rcp> table = [] {
+        std::vector<Rcp> t((size_t)(1u << kPrecision) + 1);
+        t[0] = {0, 0};
+        t[1] = {~0ull, 0};                               // q = x - 1, folded into the bias below
+        for (uint32_t f = 2; f <= (1u << kPrecision); ++f) {
+            uint32_t sh = 0;
+            while (f > (1u << sh)) ++sh;
+            const unsigned __int128 num = ((unsigned __int128)1 << (sh + 63)) + f - 1;
+            t[f] = {(uint64_t)(num / f), sh - 1};
+        }
+        return t;
+    }();
+    return table.data();
+}
+inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+
+inline void enc_put(uint64_t& x, uint32_t*& p, uint32_t start, uint32_t freq, int bits, const Rcp* rt) {
     const uint64_t x_max = ((kRansL >> bits) << 32) * freq;
     if (x >= x_max) { *--p = (uint32_t)x; x >>= 32; }
-    x = ((x / freq) << bits) + (x % freq) + start;
+    // ((x / freq) << bits) + (x % freq) + start  ==  x + start + q * (2^bits - freq),  q = x / freq
+    const Rcp r = rt[freq];
+    if (freq == 1) x = x + start + ((1u << bits) - 1) + (x - 1) * (uint64_t)((1u << bits) - 1);
+    else x = x + start + (mulhi64(x, r.rcp) >> r.shift) * (uint64_t)((1u << bits) - freq);
 }
 inline void enc_put_bits(uint64_t& x, uint32_t*& p, uint32_t val, int nbits) {
     const uint64_t freq = 1ull << (kPrecision - nbits);
@@ -50,6 +73,10 @@ struct mlic_rans_decoder {
     std::vector<uint32_t> words;
     size_t pos = 0;
     uint64_t x = 0;
+    // per decode_stream call and table, built on first use: first[b] = the symbol whose interval holds the cumulative
+    // value b << 8, b = 0..256 -- a 16-bit value is then searched among the few symbols of its 1/256 bucket only
+    std::vector<uint16_t> first;
+    std::vector<uint8_t> ready;
     uint32_t next() { return pos < words.size() ? words[pos++] : 0u; }      // a truncated stream decodes zeros, never reads past it
 };
 
@@ -89,39 +116,43 @@ int mlic_rans_encode(const int32_t* symbols, const int32_t* indexes, size_t n, c
                      size_t* out_bytes) {
     if ((!symbols || !indexes) && n) return 1;
     if (!cdfs || !cdf_sizes || !offsets || !out || !out_bytes || cdf_stride <= 0) return 1;
-    std::vector<Sym> syms;
-    syms.reserve(n + n / 8 + 8);
-    for (size_t i = 0; i < n; ++i) {
+    // rANS is last-in first-out: walk the symbols backwards and write the words backwards, so that the decoder reads
+    // both forwards.  No intermediate symbol list: per symbol one table lookup, one reciprocal multiply; an escape is
+    // its bypass nibbles (in reverse), then the escape symbol itself.
+    // worst case: every symbol an 8-nibble escape.  The words are written backwards from the end of the caller's buffer when
+    // it holds the worst case (mlic_rans_encode_bound does) and moved to its front afterwards; only touched pages are paid for.
+    const size_t worst = 2 * n + 16;
+    std::unique_ptr<uint32_t[]> tmp;
+    uint32_t* end;
+    if (((uintptr_t)out & 3u) == 0 && out_cap / 4 >= worst) end = (uint32_t*)out + out_cap / 4;
+    else { tmp.reset(new uint32_t[worst]); end = tmp.get() + worst; }
+    uint32_t* p = end;
+    uint64_t x = kRansL;
+    const Rcp* const rt = rcp_table();
+    for (size_t i = n; i-- > 0;) {
         const int t = indexes[i];
         if (t < 0 || t >= n_tables) return 2;
         const int32_t* cdf = cdfs + (size_t)t * cdf_stride;
         const int32_t max_value = cdf_sizes[t] - 2;
         if (max_value < 0 || cdf_sizes[t] > cdf_stride) return 3;
         int32_t value = symbols[i] - offsets[t];
-        uint32_t raw = 0;
-        if (value < 0) { raw = (uint32_t)(-2 * (int64_t)value - 1); value = max_value; }
-        else if (value >= max_value) { raw = (uint32_t)(2 * ((int64_t)value - max_value)); value = max_value; }
-        syms.push_back({(uint16_t)cdf[value], (uint16_t)(cdf[value + 1] - cdf[value]), false});
-        if (value == max_value) {
+        if (value < 0 || value >= max_value) {
+            const uint32_t raw = value < 0 ? (uint32_t)(-2 * (int64_t)value - 1) : (uint32_t)(2 * ((int64_t)value - max_value));
+            value = max_value;
             int n_bypass = 0;
             while (n_bypass < 8 && (raw >> (n_bypass * kBypassBits)) != 0) ++n_bypass;      // (8 nibbles cover 32 bits: no shift by 32)
+            // forward order: [escape symbol] [nibble count, in units of at most 15] [nibbles, least significant first]
+            for (int j = n_bypass; j-- > 0;) enc_put_bits(x, p, (raw >> (j * kBypassBits)) & kMaxBypass, kBypassBits);
+            uint32_t cnt[2];
+            int nc = 0;
             int32_t val = n_bypass;
-            while (val >= (int32_t)kMaxBypass) { syms.push_back({(uint16_t)kMaxBypass, 1, true}); val -= kMaxBypass; }
-            syms.push_back({(uint16_t)val, 1, true});
-            for (int j = 0; j < n_bypass; ++j) syms.push_back({(uint16_t)((raw >> (j * kBypassBits)) & kMaxBypass), 1, true});
+            while (val >= (int32_t)kMaxBypass) { cnt[nc++] = kMaxBypass; val -= kMaxBypass; }
+            cnt[nc++] = (uint32_t)val;
+            while (nc-- > 0) enc_put_bits(x, p, cnt[nc], kBypassBits);
         }
-    }
-    std::vector<uint32_t> buf(syms.size() + 4);
-    uint32_t* const end = buf.data() + buf.size();
-    uint32_t* p = end;
-    uint64_t x = kRansL;
-    for (size_t i = syms.size(); i-- > 0;) {
-        const Sym& s = syms[i];
-        if (s.bypass) enc_put_bits(x, p, s.start, kBypassBits);
-        else {
-            if (s.range == 0) return 4;                  // zero-frequency symbol: the table was not built by pmf_to_quantized_cdf
-            enc_put(x, p, s.start, s.range, kPrecision);
-        }
+        const uint32_t start = (uint32_t)cdf[value], range = (uint32_t)(cdf[value + 1] - cdf[value]);
+        if (range == 0 || range >= (1u << kPrecision)) return 4;      // zero-frequency symbol: the table was not built by pmf_to_quantized_cdf
+        enc_put(x, p, start, range, kPrecision, rt);
     }
     p -= 2;
     p[0] = (uint32_t)x;
@@ -129,7 +160,7 @@ int mlic_rans_encode(const int32_t* symbols, const int32_t* indexes, size_t n, c
     const size_t nbytes = (size_t)(end - p) * 4;
     *out_bytes = nbytes;
     if (nbytes > out_cap) return 5;
-    memcpy(out, p, nbytes);
+    memmove(out, p, nbytes);
     return 0;
 }
 
@@ -156,6 +187,10 @@ int mlic_rans_decode_stream(mlic_rans_decoder* d, const int32_t* indexes, size_t
         d->x = x;
         return val;
     };
+    constexpr int kBuckets = 256, kBucketShift = kPrecision - 8;
+    if (n_tables <= 0) return n ? 2 : 0;
+    d->first.resize((size_t)n_tables * (kBuckets + 1));
+    d->ready.assign((size_t)n_tables, 0);                 // the caller may pass other tables on every call
     for (size_t i = 0; i < n; ++i) {
         const int t = indexes[i];
         if (t < 0 || t >= n_tables) return 2;
@@ -163,12 +198,26 @@ int mlic_rans_decode_stream(mlic_rans_decoder* d, const int32_t* indexes, size_t
         const int size = cdf_sizes[t];
         const int32_t max_value = size - 2;
         if (max_value < 0 || size > cdf_stride) return 3;
+        uint16_t* const first = d->first.data() + (size_t)t * (kBuckets + 1);
+        if (!d->ready[t]) {
+            // a table is 0 = cdf[0] <= cdf[1] <= ... <= cdf[size - 1] = 2^16 (pmf_to_quantized_cdf); anything else cannot decode
+            if (cdf[0] != 0 || cdf[size - 1] != (1 << kPrecision) || size - 1 > 0xffff) return 4;
+            for (int j = 1; j < size; ++j) if (cdf[j] < cdf[j - 1]) return 4;
+            int sidx = 0;
+            for (int b = 0; b <= kBuckets; ++b) {
+                const int32_t v = b << kBucketShift;
+                while (sidx + 1 <= max_value && cdf[sidx + 1] <= v) ++sidx;        // largest s <= max_value with cdf[s] <= v
+                first[b] = (uint16_t)sidx;
+            }
+            d->ready[t] = 1;
+        }
         const uint32_t cum = (uint32_t)(d->x & mask);
-        // first entry above cum (the tables are short and increasing; the last entry is 2^16 > cum)
-        int lo = 0, hi = size - 1;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)cdf[mid] > cum) hi = mid; else lo = mid + 1; }
-        const int s = lo - 1;
-        if (s < 0) return 4;
+        // the symbol s with cdf[s] <= cum < cdf[s + 1] (the last one of a run of equal entries, as a search for the first
+        // entry above cum finds it)
+        // (one path for every table size: a size test per symbol mispredicts on mixed streams and costs more than it saves)
+        int lo = first[cum >> kBucketShift], hi = first[(cum >> kBucketShift) + 1];
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((uint32_t)cdf[mid] <= cum) lo = mid; else hi = mid - 1; }
+        const int s = lo;
         const uint32_t start = (uint32_t)cdf[s], freq = (uint32_t)(cdf[s + 1] - cdf[s]);
         uint64_t x = d->x;
         x = (uint64_t)freq * (x >> kPrecision) + (x & mask) - start;

@@ -116,3 +116,70 @@ def test_update_fills_the_reference_buffers():
     other = mlic_b200.get_model("MLICPP_S")
     other.load_state_dict(net.state_dict())
     assert torch.equal(other.gaussian_conditional._quantized_cdf, gc._quantized_cdf)
+
+
+def _reference_encode(symbols, indexes, cdf, ln, off):
+    """The published algorithm of compressai.ans with Python integers (exact division, no reciprocal, no tables): 64-bit
+    rANS, 16-bit precision, 32-bit words emitted backwards, 4-bit bypass escapes -- an independent statement of what
+    mlic_rans_encode must write, byte for byte."""
+    L, P = 1 << 31, 16
+    ops = []                                              # (start, range, bits) in coding order
+    for sv, t in zip(symbols, indexes):
+        mx = int(ln[t]) - 2
+        v = int(sv) - int(off[t])
+        raw = None
+        if v < 0:
+            raw, v = -2 * v - 1, mx
+        elif v >= mx:
+            raw, v = 2 * (v - mx), mx
+        ops.append((int(cdf[t][v]), int(cdf[t][v + 1] - cdf[t][v]), P))
+        if raw is not None:
+            nb = 0
+            while nb < 8 and (raw >> (4 * nb)) != 0:
+                nb += 1
+            val = nb
+            while val >= 15:
+                ops.append((15, 1, 4))
+                val -= 15
+            ops.append((val, 1, 4))
+            ops.extend(((raw >> (4 * j)) & 15, 1, 4) for j in range(nb))
+    x, words = L, []
+    for start, rng, bits in reversed(ops):
+        if x >= ((L >> bits) << 32) * rng:
+            words.append(x & 0xFFFFFFFF)
+            x >>= 32
+        x = ((x // rng) << bits) + (x % rng) + start
+    words += [x >> 32, x & 0xFFFFFFFF]
+    return np.array(words[::-1], dtype="<u4").tobytes()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_encoder_bytes_equal_an_exact_integer_reference(seed):
+    """The encoder divides by reciprocal multiplication and writes in place; the bytes must equal the plain-integer
+    statement of the algorithm, on every frequency class: wide and narrow tables, frequency-1 tails, escapes of 1..8 nibbles."""
+    st = mlic_b200.get_scale_table()
+    cdf, ln, off = coder.gaussian_tables(st)
+    rng = np.random.default_rng(seed)
+    n = 6000
+    idx = rng.integers(0, 64, n).astype(np.int32)
+    sym = np.round(rng.standard_normal(n) * st.numpy()[idx] * 1.5).astype(np.int32)
+    sym[::53] = rng.integers(-70000, 70000, sym[::53].size)
+    sym[3], sym[4], sym[5], sym[6] = 2 ** 30, -(2 ** 30), 2 ** 31 - 1 - int(ln[idx[5]]), 0
+    got = coder.encode_with_indexes(sym, idx, cdf, ln, off)
+    assert got == _reference_encode(sym.tolist(), idx.tolist(), np.asarray(cdf), np.asarray(ln), np.asarray(off))
+    assert np.array_equal(coder.RansDecoder().decode_with_indexes(got, idx, cdf, ln, off), sym)
+
+
+def test_decoder_rejects_a_table_that_is_not_a_cdf():
+    st = mlic_b200.get_scale_table()
+    cdf, ln, off = coder.gaussian_tables(st)
+    s = coder.encode_with_indexes([0, 1, -1], [5, 5, 5], cdf, ln, off)
+    bad = np.array(cdf, dtype=np.int32, copy=True)
+    bad[5, 2] = bad[5, 1] - 1                              # not monotone
+    with pytest.raises(ValueError):
+        coder.RansDecoder().decode_with_indexes(s, [5, 5, 5], bad, ln, off)
+    bad = np.array(cdf, dtype=np.int32, copy=True)
+    bad[5, int(ln[5]) - 1] = 65535                         # does not end at 2^16
+    with pytest.raises(ValueError):
+        coder.RansDecoder().decode_with_indexes(s, [5, 5, 5], bad, ln, off)
+    assert coder.RansDecoder().decode_with_indexes(s, [5, 5, 5], cdf, ln, off).tolist() == [0, 1, -1]
