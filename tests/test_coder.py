@@ -183,3 +183,34 @@ def test_decoder_rejects_a_table_that_is_not_a_cdf():
     with pytest.raises(ValueError):
         coder.RansDecoder().decode_with_indexes(s, [5, 5, 5], bad, ln, off)
     assert coder.RansDecoder().decode_with_indexes(s, [5, 5, 5], cdf, ln, off).tolist() == [0, 1, -1]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_tables_against_the_integer_reference(seed):
+    """Tables of arbitrary shape (2..300 bins, Dirichlet masses incl. near-one and frequency-1 bins) through
+    pmf_to_quantized_cdf: encoder bytes == integer reference, decoder inverts them, also in split calls."""
+    rng = np.random.default_rng(100 + seed)
+    n_tables, stride = 12, 304
+    cdf = np.zeros((n_tables, stride), dtype=np.int32)
+    ln = np.zeros(n_tables, dtype=np.int32)
+    off = rng.integers(-150, 5, n_tables).astype(np.int32)
+    for t in range(n_tables):
+        bins = int(rng.integers(2, 301))
+        pmf = rng.dirichlet(np.full(bins, rng.choice([0.05, 0.5, 5.0]))).astype(np.float32) + 1e-12
+        if t == 0:
+            pmf = np.array([1e-9, 1.0, 1e-9], dtype=np.float32)      # one bin takes 65534 of the 65536
+            bins = 3
+        tail = np.float32(1e-9)
+        c = coder.pmf_to_quantized_cdf(np.concatenate([pmf, [tail]]))
+        cdf[t, :len(c)] = c
+        ln[t] = len(c)
+        assert c[0] == 0 and c[-1] == 65536 and (np.diff(c) >= 1).all()
+    n = 5000
+    idx = rng.integers(0, n_tables, n).astype(np.int32)
+    sym = (off[idx] + rng.integers(-3, ln[idx] + 2)).astype(np.int32)          # inside and just outside every table
+    got = coder.encode_with_indexes(sym, idx, cdf, ln, off)
+    assert got == _reference_encode(sym.tolist(), idx.tolist(), cdf, ln, off)
+    d = coder.RansDecoder()
+    d.set_stream(got)
+    out = np.concatenate([d.decode_stream(idx[:777], cdf, ln, off), d.decode_stream(idx[777:], cdf, ln, off)])
+    assert np.array_equal(out, sym)
