@@ -391,12 +391,33 @@ class MLICPlusPlus(nn.Module):
         return (mod._quantized_cdf.detach().cpu().numpy(), mod._cdf_length.detach().cpu().numpy().reshape(-1),
                 mod._offset.detach().cpu().numpy().reshape(-1))
 
+    def _to_host(self, *tensors):
+        """Device int32 tensors -> numpy views of cached PINNED host buffers (one async copy each, one sync): the 2 x 10 MB
+        symbol / index lists of a 1080p image cost ~3.5 ms through pageable memory, under 1 ms this way.  The views are
+        valid until the next call."""
+        if not hasattr(self, "_pin"):
+            self._pin = {}
+        out = []
+        for i, t in enumerate(tensors):
+            if not t.is_cuda:
+                out.append(t.numpy())
+                continue
+            buf = self._pin.get(i)
+            if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+                buf = self._pin[i] = torch.empty(max(t.numel(), 1), dtype=t.dtype, pin_memory=True)
+            view = buf[:t.numel()].view(t.shape)
+            view.copy_(t, non_blocking=True)
+            out.append(view.numpy())
+        if any(t.is_cuda for t in tensors):
+            torch.cuda.current_stream(next(t for t in tensors if t.is_cuda).device).synchronize()
+        return out
+
     def _strings(self, o, B):
         """The coder side of compress() (models/mlicpp.py:205-206,279-280): ONE y string for the whole batch (the symbol
         lists are flattened over [B,C,H,W/2] per half-slice), one z string per image (EntropyBottleneck.compress)."""
         from . import coder
-        y_string = coder.encode_with_indexes(o["symbols"].cpu().numpy(), o["indexes"].cpu().numpy(), *self._tables(self.gaussian_conditional))
-        zs = o["z_symbols"].cpu().numpy()
+        sym, idx, zs = self._to_host(o["symbols"], o["indexes"], o["z_symbols"])
+        y_string = coder.encode_with_indexes(sym, idx, *self._tables(self.gaussian_conditional))
         ztab = self._tables(self.entropy_bottleneck)
         zidx = np.broadcast_to(np.arange(self.N, dtype=np.int32)[:, None, None], zs.shape[1:])
         return [[y_string], [coder.encode_with_indexes(zs[b], zidx, *ztab) for b in range(B)]]
