@@ -96,7 +96,10 @@ def bottleneck_tables(eb):
         return logits
 
     lower, upper = cum(samples - 0.5), cum(samples + 0.5)
-    pmf = (torch.sigmoid(upper) - torch.sigmoid(lower))[:, 0, :]
+    # CompressAI EntropyBottleneck.update(): the difference is taken on the side of the sigmoid where it does not cancel
+    # (sign = -sign(lower + upper)); equal to sigmoid(upper) - sigmoid(lower) in exact arithmetic, not in fp32 in the upper tail
+    sign = -torch.sign(lower + upper)
+    pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
     tail = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
     cdf = _pmf_to_cdf(pmf.numpy(), tail.numpy(), pmf_length.tolist(), max_length)
     return cdf, (pmf_length + 2).numpy().astype(np.int32), (-minima).numpy().astype(np.int32)

@@ -112,6 +112,7 @@ struct mlic_engine {
     float* eb_packed = nullptr;
     float* eb_medians = nullptr;
     float* scale_table = nullptr;
+    int scale_levels = 64;
 
     // per-call state
     int bf = 0;
@@ -439,10 +440,15 @@ struct mlic_engine {
             eb_medians = upload(med);
         }
         {   // utils/func.py:16-19 -- exp(linspace(log .11, log 256, 64)) in fp32 (torch.linspace is symmetric around the middle)
+            // (a table of any length set through update(scale_table=...) is used as it is: build_indexes only counts the
+            // entries below sigma; the 0.11 lower bound of the kernels is GaussianConditional's scale_bound, not table[0])
             std::vector<float> tab(64);
             auto it = params.find("gaussian_conditional.scale_table");
-            if (it != params.end() && it->second.v.size() == 64) tab = it->second.v;
-            else {
+            if (it != params.end() && !it->second.v.empty()) {
+                tab = it->second.v;
+                for (size_t k = 1; k < tab.size(); ++k)
+                    if (!(tab[k] > tab[k - 1])) return fail("gaussian_conditional.scale_table must be strictly increasing (entry %zu)", k);
+            } else {
                 const float lo = logf(0.11f), hi = logf(256.0f);
                 const float step = (hi - lo) / 63.0f;
                 for (int k = 0; k < 64; ++k) {
@@ -451,6 +457,7 @@ struct mlic_engine {
                 }
             }
             scale_table = upload(tab);
+            scale_levels = (int)tab.size();
         }
         if (rc) return rc;
         cudaError_t e = cudaDeviceSynchronize();
@@ -1099,7 +1106,7 @@ struct mlic_engine {
             q.y = y32 + (size_t)i * C; q.y_ld = M; q.pa = pa; q.pn = pn; q.slot = slot;
             q.B = B; q.H = h; q.W = w; q.C = C; q.mode = mode; q.vbr = use_gain; q.gain = gain; q.rgain = rgain;
             q.lik = lik ? lik + (size_t)i * C : nullptr; q.lik_ld = M;
-            q.table = scale_table; q.levels = 64; q.sq = esq ? 1 : 0;
+            q.table = scale_table; q.levels = scale_levels; q.sq = esq ? 1 : 0;
             if (mode == MLIC_MODE_COMPRESS) {
                 if (!dry && (!io->symbols || !io->indexes)) return fail("compress needs symbols and indexes buffers");
                 q.sym = io->symbols ? io->symbols + (size_t)(2 * i) * half : nullptr;

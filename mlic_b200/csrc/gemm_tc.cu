@@ -27,7 +27,7 @@
 
 namespace mlic {
 
-static char g_tc_err[512] = "";
+static thread_local char g_tc_err[512] = "";
 const char* tc_last_error() { return g_tc_err; }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -46,6 +46,16 @@ int tc_init() {
     }
     g_encode = (PFN_encodeTiled)fn;
     return 0;
+}
+
+// Per-device launch state: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to the CURRENT device,
+// not to the process (a model moved to a second GPU of the same process launches there with the first one's attributes otherwise).
+constexpr int TC_MAX_DEV = 64;
+static int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < TC_MAX_DEV) ? d : 0; }
+static int dev_sms(int dev) {
+    static int sms[TC_MAX_DEV] = {};
+    if (!sms[dev]) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); sms[dev] = n > 0 ? n : 148; }
+    return sms[dev];
 }
 
 // ------------------------------------------------------------------------------------------ device PTX helpers
@@ -1157,10 +1167,10 @@ static int launch_dw_tma(const Act& in, const Act& out, const float* w9, const f
     const long long nitems = (long long)out.B * tilesW * tilesH * chunks;
     if (nitems <= 0 || nitems > 0x7fffffffLL) return 3;
     const int smem = TT::SLOTS * TT::BYTES + 128;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(dwconv3x3_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+    const int dev = cur_dev();
+    static bool attr[TC_MAX_DEV] = {};
+    if (!attr[dev]) { cudaFuncSetAttribute(dwconv3x3_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[dev] = true; }
+    const int num_sms = dev_sms(dev);
     const int grid = (int)std::min<long long>(nitems, 2LL * num_sms);
     dwconv3x3_tma_kernel<S><<<grid, 288, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
     return cudaGetLastError() == cudaSuccess ? 0 : 4;
@@ -1421,28 +1431,23 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
                                             {nullptr, conv_gemm_tc_kernel<2, 0, true, PROD_DW>}};
     static const KernelFn table_sq[2][2] = {{conv_gemm_tc_kernel<0, 1, false, PROD_SQ>, conv_gemm_tc_kernel<0, 1, true, PROD_SQ>},
                                             {conv_gemm_tc_kernel<0, 2, false, PROD_SQ>, conv_gemm_tc_kernel<0, 2, true, PROD_SQ>}};
-    static bool attr_set[3][3][2][3] = {};
+    static bool attr_set[TC_MAX_DEV][3][3][2][3] = {};
+    const int dev = cur_dev();
     if (e.act < 0 || e.act > 2 || e.gdn < 0 || e.gdn > 2) { snprintf(g_tc_err, sizeof g_tc_err, "bad epilogue mode"); return 9; }
     const int ri = e.res ? 1 : 0;
     KernelFn fn = table[e.act][e.gdn][ri];
     if (c.prod == PROD_DW) fn = table_dw[e.act][ri];
     else if (c.prod == PROD_SQ) fn = table_sq[e.gdn - 1][ri];
     if (!fn) { snprintf(g_tc_err, sizeof g_tc_err, "no kernel instantiation for act=%d res=%d prod=%d", e.act, ri, c.prod); return 9; }
-    if (!attr_set[e.act][e.gdn][ri][c.prod]) {
+    if (!attr_set[dev][e.act][e.gdn][ri][c.prod]) {
         cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, budget0 + 1024);
         if (er != cudaSuccess) {
             snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(er));
             return 4;
         }
-        attr_set[e.act][e.gdn][ri][c.prod] = true;
+        attr_set[dev][e.act][e.gdn][ri][c.prod] = true;
     }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = dev_sms(dev);
     dim3 grid((unsigned)(p.ntiles < num_sms ? p.ntiles : num_sms));
     unsigned long long* dbg = nullptr;
     if (p.debug & 32) {             // development: per-role wait clocks of the first launches, printed to stderr

@@ -1100,8 +1100,11 @@ __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __re
 int launch_local_attn_mma(const Act& F, const float* rel_bias, void* O, cudaStream_t s) {
     if (F.C != 96 || (F.W & 1) || (F.ld % 8) != 0 || ((uintptr_t)F.p % 16) != 0 || ((uintptr_t)O % 16) != 0) return 1;
     if (F.B * F.H * F.W == 0) return 0;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(local_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM); attr = true; }
+    static bool attr[64] = {};           // the attribute belongs to the current device, not to the process
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr[dev]) { cudaFuncSetAttribute(local_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM); attr[dev] = true; }
     dim3 grid(cdiv(F.W, LM_TW), cdiv(F.H, LM_TH), F.B);
     local_attn_mma_kernel<<<grid, 256, LM_SMEM, s>>>((const bf16*)F.p, F.ld, F.H, F.W, rel_bias, (bf16*)O);
     return 0;

@@ -77,7 +77,8 @@ struct mlic_rans_decoder {
     // value b << 8, b = 0..256 -- a 16-bit value is then searched among the few symbols of its 1/256 bucket only
     std::vector<uint16_t> first;
     std::vector<uint8_t> ready;
-    uint32_t next() { return pos < words.size() ? words[pos++] : 0u; }      // a truncated stream decodes zeros, never reads past it
+    bool overrun = false;      // a word was requested past the end of the stream: truncated or mismatched (tables / gain) stream
+    uint32_t next() { if (pos < words.size()) return words[pos++]; overrun = true; return 0u; }      // never reads past the stream
 };
 
 extern "C" {
@@ -237,7 +238,7 @@ int mlic_rans_decode_stream(mlic_rans_decoder* d, const int32_t* indexes, size_t
         }
         out[i] = value + offsets[t];
     }
-    return 0;
+    return d->overrun ? 6 : 0;       // symbols decoded from words the stream does not hold are not data
 }
 
 }  // extern "C"

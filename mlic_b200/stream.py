@@ -86,7 +86,11 @@ def decompress_one_image(model, stream_path, img_name):
 
 
 def compress_one_image_vbr(model, x, stream_path, H, W, img_name, level=0, force=False):
-    """testing.py:232-247"""
+    """testing.py:232-247.  The reference writes `level` itself with struct.pack(">3I"): a non-integer level raises there, so
+    a fractional custom gain cannot reach a file whose header would carry only its integer part."""
+    if float(level) != int(level) or int(level) < 0:
+        raise ValueError(f"level {level!r} cannot be stored in the stream header (unsigned integer): the decoder would "
+                         "dequantise with a different gain than the encoder used")
     out = model.compress(x, stage=2, s=int(level), inputscale=0 if not force else level)
     output = os.path.join(stream_path, img_name)
     with Path(output).open("wb") as f:

@@ -105,6 +105,23 @@ def test_empty_and_errors():
         coder.RansDecoder().set_stream(b"abc")
 
 
+def test_truncated_or_mismatched_stream_is_an_error_not_zeros():
+    """A stream that ends before its symbols do (truncated file, wrong tables or gain on the decoder side) must fail: the decoder
+    used to zero-fill past the end and return plausible symbols with rc 0."""
+    st = mlic_b200.get_scale_table()
+    cdf, ln, off = coder.gaussian_tables(st)
+    rng = np.random.default_rng(3)
+    n = 20000
+    idx = rng.integers(0, 64, n).astype(np.int32)
+    sym = np.round(rng.standard_normal(n) * st.numpy()[idx]).astype(np.int32)
+    s = coder.encode_with_indexes(sym, idx, cdf, ln, off)
+    assert np.array_equal(coder.RansDecoder().decode_with_indexes(s, idx, cdf, ln, off), sym)      # the whole stream is fine
+    with pytest.raises(ValueError):
+        coder.RansDecoder().decode_with_indexes(s[:len(s) // 2], idx, cdf, ln, off)                # truncated
+    with pytest.raises(ValueError):                                                                # wider tables than it was coded with
+        coder.RansDecoder().decode_with_indexes(s, np.full(n, 63, np.int32), cdf, ln, off)
+
+
 def test_update_fills_the_reference_buffers():
     net = mlic_b200.get_model("MLICPP_S")
     assert net.gaussian_conditional._quantized_cdf.numel() == 0
