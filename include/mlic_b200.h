@@ -126,10 +126,21 @@ int mlic_dwconv3x3_nhwc(int precision, const void* in, int B, int H, int W, int 
 /* Stand-alone DepthWiseConv (modules/layers/conv.py:46-63): depthwise 3x3 (pad 1, `stride`, bias) followed by a 1x1
  * convolution (bias), then act / + residual, on an NHWC activation tensor.  dw_weight: HOST fp32 [Cin][1][3][3],
  * pw_weight: HOST fp32 [N][Cin][1][1].  fuse = 1 lets the bf16 path produce the depthwise result inside the tcgen05
- * GEMM kernel (A-operand producer) where the layer shape allows; 0 runs the two kernels back to back.  Timing as
- * mlic_conv2d_nhwc.  Kernel-level test / micro-benchmark hook. */
+ * GEMM kernel (A-operand producer) where the layer shape allows; 2 additionally allows the two-SM (cta_group::2) kernel
+ * for Cin = N = 192 | 128; 0 runs the two kernels back to back.  Timing as mlic_conv2d_nhwc.  Kernel-level test /
+ * micro-benchmark hook. */
 int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int W, int Cin, const float* dw_weight,
                      const float* dw_bias, const float* pw_weight, const float* pw_bias, int N, int stride, int act,
+                     const void* residual, void* out, int iters, float* avg_ms, void* cuda_stream);
+
+/* Stand-alone tail of ResidualBlockWithStride / ResidualBlockUpsample (modules/layers/res_blk.py:88-93,116-121), bf16:
+ * v = DepthWiseConv(in) (C -> C); out = v * rsqrt(gamma v^2 + beta) (GDN; `inverse`: v * sqrt(.), IGDN) + residual.
+ * in / residual / out: DEVICE bf16 NHWC [B,H,W,C]; dw_weight HOST [C][1][3][3]; pw_weight HOST [C][C]; gamma HOST [C][C] and
+ * beta HOST [C] are the EFFECTIVE (re-parametrised, CompressAI NonNegativeParametrizer) values.  fuse = 2: one two-SM kernel,
+ * v and v^2 stay on chip (fails if that kernel does not take the shape); 1: DepthWiseConv kernel + GDN GEMM that squares its
+ * operand on chip; 0: unfused.  Timing as mlic_conv2d_nhwc.  Kernel-level test / micro-benchmark hook. */
+int mlic_ds_gdn_nhwc(int fuse, const void* in, int B, int H, int W, int C, const float* dw_weight, const float* dw_bias,
+                     const float* pw_weight, const float* pw_bias, const float* gamma, const float* beta, int inverse,
                      const void* residual, void* out, int iters, float* avg_ms, void* cuda_stream);
 
 /* Stand-alone final synthesis layer (subpel_conv3x3(C, 3, 2) of g_s, modules/transform/synthesis.py:67 with CompressAI's

@@ -103,6 +103,7 @@ struct mlic_engine {
     size_t h_mail_n = 0;
     int stages = 7;          // bit 0: g_a, bit 1: h_a + EntropyBottleneck + h_s + slice loop, bit 2: g_s (row-band sharding runs them apart)
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
+    int pair = 1;            // fuse: DepthWiseConv / (I)GDN-tail blocks with C = N = 192 | 128 on the two-SM kernel (ds_pair.cu)
 
     std::vector<void*> dev_allocs;
     std::unordered_map<std::string, ConvW> convs;
@@ -622,8 +623,49 @@ struct mlic_engine {
         launch_dwconv3x3(bf, in, out, d->w9, d->bias, stride, actv, st);
         after_launch(key.c_str());
     }
+    // Two-SM kernel (ds_pair.cu): DepthWiseConv `p` (+ GELU, + residual), or with `gdn` the whole tail
+    // v = DepthWiseConv(in); out = v * (r)sqrt(gamma v^2 + beta) + res.  false: not taken, nothing launched.
+    bool ds_pair(const Act& in, const std::string& p, const Act* out, const EpiOpt& o, const std::string* gdn) {
+        if (!(bf && use_tc && fuse && pair) || !out || o.out2 || o.out_f32 || o.nchw || o.ck || o.premask || o.postmask) return false;
+        const DwW* d = dw(p + ".depth_conv");
+        const ConvW* w = cw(p + ".point_conv");
+        const ConvW* g = gdn ? cw(*gdn) : nullptr;
+        if (!d || !w || (gdn && !g)) return false;
+        if (d->C != in.C || w->Cin != in.C || w->N != in.C || w->Cpad != in.C || w->ks != 1 || w->shuffle || out->C != in.C) return false;
+        if (g && (g->Cin != in.C || g->N != in.C || g->Cpad != in.C || g->ks != 1)) return false;
+        if (!gdn && o.gdn) return false;
+        if (gdn && (!o.gdn || o.act != ACT_NONE)) return false;
+        DsPairArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = in.p; a.B = in.B; a.H = in.H; a.W = in.W; a.ld = in.ld; a.C = in.C;
+        a.dw_w9 = d->w9; a.dw_bias = d->bias; a.w1 = w->wbf; a.b1 = w->bias; a.act = o.act;
+        a.gdn = gdn ? o.gdn : GDN_NONE;
+        if (g) { a.w2 = g->wbf; a.b2 = g->bias; }
+        if (o.res) { a.res = o.res->p; a.res_ld = o.res->ld; }
+        a.out = out->p; a.out_ld = out->ld;
+        if (!dry && !ds_pair_supported(a)) return false;
+        if (dry) return (in.C == 192 || in.C == 128) && (in.ld % 8) == 0 && (out->ld % 8) == 0 && (!o.res || (o.res->ld % 8) == 0);
+        if (rc) return true;
+        cudaEvent_t ev1 = nullptr;
+        if (profile) {
+            cudaEventRecord(next_event(), st);
+            ev1 = next_event();
+            ev_flops.push_back((gdn ? 4.0 : 2.0) * (double)in.B * in.H * in.W * (double)in.C * (double)in.C);
+        }
+        const int r = launch_ds_pair(a, st);
+        if (ev1) cudaEventRecord(ev1, st);
+        if (r) { if (!rc) rc = fail("two-SM block '%s': %s", p.c_str(), ds_pair_last_error()); return true; }
+        ++launches;
+        if (trace) {
+            char lab[256];
+            snprintf(lab, sizeof lab, "%s [pair %s M=%d C=%d]", p.c_str(), gdn ? "dw+pw+gdn" : "dw+pw", in.B * in.H * in.W, in.C);
+            tr(lab);
+        }
+        return true;
+    }
     // DepthWiseConv (modules/layers/conv.py:46-63): dw3x3(stride) -> pw1x1 with epilogue
     void dsconv(const Act& in, const std::string& p, int stride, const Act* out, const EpiOpt& o) {
+        if (stride == 1 && !o.gdn && ds_pair(in, p, out, o, nullptr)) return;
         if (bf && use_tc && fuse && stride == 1 && !o.out2) {
             const DwW* d = dw(p + ".depth_conv");
             if (d && d->C == in.C && gemm(in, p + ".point_conv", 1, 0, out, o, 1, d)) return;
@@ -655,6 +697,7 @@ struct mlic_engine {
     // operand on chip (PROD_SQ); otherwise conv's epilogue writes v^2 as a side tensor for a plain GEMM.
     void gdn_block(const Act& t, const std::string& conv, bool dense, const Act& v, const std::string& gdn, const Act& out,
                    const EpiOpt& og) {
+        if (!dense && ds_pair(t, conv, &out, og, &gdn)) return;      // conv -> (I)GDN -> + res in one two-SM kernel, v stays on chip
         if (bf && use_tc && fuse) {
             size_t mark = ws_off;
             c3(t, conv, 1, dense, &v, EpiOpt());
@@ -1206,6 +1249,7 @@ int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
     if (!strcmp(name, "tensor_cores")) { e->use_tc = value; return 0; }
     if (!strcmp(name, "profile")) { e->profile = value; return 0; }
     if (!strcmp(name, "fuse")) { e->fuse = value; return 0; }
+    if (!strcmp(name, "pair")) { e->pair = value; return 0; }
     if (!strcmp(name, "trace")) { e->trace = value; return 0; }
     if (!strcmp(name, "stages")) { e->stages = value & 7; return 0; }
     return fail("unknown option '%s'", name);
@@ -1213,7 +1257,7 @@ int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {
     if (!e || !bytes) return fail("bad arguments");
     // the dry walk costs ~1 ms of host time: remember its result per call geometry (finalize() clears the cache)
-    const std::array<int, 8> key = {mode, precision, B, H, W, e->use_tc, e->fuse, e->stages};
+    const std::array<int, 8> key = {mode, precision, B, H, W, e->use_tc, e->fuse + 2 * e->pair, e->stages};
     auto it = e->ws_cache.find(key);
     if (it != e->ws_cache.end()) { *bytes = it->second; return 0; }
     int r = e->run(mode, precision, B, H, W, 1.0f, nullptr, nullptr, 0, nullptr, true);
@@ -1436,7 +1480,7 @@ int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int 
     e.pack_dw_list("d.depth_conv", {"d.depth_conv"});
     e.pack_conv_raw("d.point_conv", pw_weight, pw_bias, N, Cin, 1, 0);
     if (e.rc) return e.rc;
-    e.bf = precision == MLIC_PREC_BF16; e.use_tc = 1; e.fuse = fuse; e.dry = false; e.st = (cudaStream_t)cuda_stream;
+    e.bf = precision == MLIC_PREC_BF16; e.use_tc = 1; e.fuse = fuse ? 1 : 0; e.pair = fuse == 2; e.dry = false; e.st = (cudaStream_t)cuda_stream;
     if (e.bf && tc_init()) return fail("%s", tc_last_error());
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     void* ws = nullptr;
@@ -1453,6 +1497,50 @@ int mlic_dsconv_nhwc(int precision, int fuse, const void* in, int B, int H, int 
     e.dsconv(a, "d", stride, &o, eo);
     CUDA_OK(cudaEventRecord(e0, e.st));
     for (int i = 1; i < iters; ++i) e.dsconv(a, "d", stride, &o, eo);
+    CUDA_OK(cudaEventRecord(e1, e.st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e.rc) return e.rc;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mlic_ds_gdn_nhwc(int fuse, const void* in, int B, int H, int W, int Cc, const float* dw_weight, const float* dw_bias,
+                     const float* pw_weight, const float* pw_bias, const float* gamma, const float* beta, int inverse,
+                     const void* residual, void* out, int iters, float* avg_ms, void* cuda_stream) {
+    if (!in || !dw_weight || !dw_bias || !pw_weight || !pw_bias || !gamma || !beta || !out || iters < 1) return fail("bad arguments");
+    mlic_engine e;
+    e.N = e.M = e.S = e.C = 0; e.kind = 0; e.sd = e.vbr = false; e.Me = 0; e.rc = 0;
+    HostT w, b;
+    w.shape = {Cc, 1, 3, 3}; w.v.assign(dw_weight, dw_weight + (size_t)Cc * 9);
+    b.shape = {Cc}; b.v.assign(dw_bias, dw_bias + Cc);
+    e.params["d.depth_conv.weight"] = w; e.params["d.depth_conv.bias"] = b;
+    e.pack_dw_list("d.depth_conv", {"d.depth_conv"});
+    e.pack_conv_raw("d.point_conv", pw_weight, pw_bias, Cc, Cc, 1, 0);
+    e.pack_conv_raw("g", gamma, beta, Cc, Cc, 1, 0);         // effective (re-parametrised) gamma [C][C] and beta [C]
+    if (e.rc) return e.rc;
+    e.bf = 1; e.use_tc = 1; e.fuse = fuse ? 1 : 0; e.pair = fuse == 2; e.dry = false; e.st = (cudaStream_t)cuda_stream;
+    if (tc_init()) return fail("%s", tc_last_error());
+    void* ws = nullptr;
+    const size_t ws_bytes = (size_t)B * H * W * ((Cc + 7) / 8 * 8) * 2 * 3 + 4096;
+    CUDA_OK(cudaMalloc(&ws, ws_bytes));
+    e.dev_allocs.push_back(ws);
+    e.ws_base = (uint8_t*)ws; e.ws_size = ws_bytes; e.ws_off = 0;
+    Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cc; a.ld = Cc;
+    Act o = a; o.p = out;
+    Act r = a; r.p = const_cast<void*>(residual);
+    Act v = e.act(B, H, W, Cc);
+    EpiOpt og; og.gdn = inverse ? GDN_INV : GDN_FWD; og.gdn_x = &v; if (residual) og.res = &r;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    const int64_t l0 = e.launches;
+    e.gdn_block(a, "d", false, v, "g", o, og);
+    if (fuse == 2 && e.launches - l0 != 1 && !e.rc) return fail("two-SM kernel did not take the layer");
+    CUDA_OK(cudaEventRecord(e0, e.st));
+    for (int i = 1; i < iters; ++i) e.gdn_block(a, "d", false, v, "g", o, og);
     CUDA_OK(cudaEventRecord(e1, e.st));
     CUDA_OK(cudaEventSynchronize(e1));
     float ms = 0;

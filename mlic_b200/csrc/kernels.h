@@ -100,6 +100,23 @@ bool tc_conv_supported(const TcConv& c, const Epi& e);
 // returns cudaError_t-like int (0 ok)
 int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s);
 int tc_init();                   // resolves cuTensorMapEncodeTiled; 0 on success
+void* tc_encode_fn();            // the resolved cuTensorMapEncodeTiled entry point (after tc_init)
 const char* tc_last_error();
+
+// ---- two-SM (cta_group::2) fused DepthWiseConv / (I)GDN-tail blocks (ds_pair.cu), bf16 NHWC, C channels in and out
+struct DsPairArgs {
+    const void* in; int B, H, W, ld;        // input view (stride-1 conv: output grid = input grid)
+    int C;                                  // 192 | 128
+    const float* dw_w9; const float* dw_bias;       // depthwise 3x3 weights [9][C] fp32, bias [C]
+    const void* w1; const float* b1;        // pointwise weights bf16 [C][C] (K-major), bias [C]
+    int act;                                // gdn == GDN_NONE: ACT_NONE | ACT_GELU
+    int gdn;                                // GDN_NONE: out = act(pw(dw(x))) + res; GDN_FWD | GDN_INV: out = v * (r)sqrt(w2 v^2 + b2) + res, v = pw(dw(x))
+    const void* w2; const float* b2;        // (I)GDN gamma bf16 [C][C], beta [C]
+    const void* res; int res_ld;            // residual, addressed like the output (may be null)
+    void* out; int out_ld;
+};
+bool ds_pair_supported(const DsPairArgs& a);
+int launch_ds_pair(const DsPairArgs& a, cudaStream_t s);      // 0 ok
+const char* ds_pair_last_error();
 
 }  // namespace mlic

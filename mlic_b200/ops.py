@@ -66,10 +66,29 @@ def dsconv_nhwc(x, dw_weight, dw_bias, pw_weight, pw_bias, stride=1, act=None, r
     prec = _lib.PREC_BF16 if x.dtype == torch.bfloat16 else _lib.PREC_FP32
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(_lib.lib().mlic_dsconv_nhwc(prec, 1 if fuse else 0, C.c_void_p(x.data_ptr()), B, H, W, Cin,
+        _lib.check(_lib.lib().mlic_dsconv_nhwc(prec, int(fuse), C.c_void_p(x.data_ptr()), B, H, W, Cin,
                                                C.c_void_p(dw.data_ptr()), C.c_void_p(db.data_ptr()), C.c_void_p(pw.data_ptr()),
                                                C.c_void_p(pb.data_ptr()), N, stride, ACT[act],
                                                C.c_void_p(residual.data_ptr()) if residual is not None else None,
+                                               C.c_void_p(out.data_ptr()), iters, C.byref(ms), C.c_void_p(st)))
+    return out, float(ms.value)
+
+
+def ds_gdn_nhwc(x, dw_weight, dw_bias, pw_weight, pw_bias, gamma, beta, inverse=False, residual=None, fuse=2, iters=1):
+    """Tail of ResidualBlockWithStride / ResidualBlockUpsample on a CUDA bf16 NHWC tensor: v = DepthWiseConv(x),
+    out = v * rsqrt(gamma v^2 + beta) (IGDN: * sqrt) + residual, with EFFECTIVE gamma [C,C] / beta [C] -> (out, avg ms).
+    fuse 2: the two-SM kernel; 1: two fused kernels; 0: unfused."""
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.bfloat16
+    B, H, W, Cc = x.shape
+    hs = [t.detach().to("cpu", torch.float32).contiguous() for t in (dw_weight, dw_bias, pw_weight, pw_bias, gamma, beta)]
+    out = torch.empty_like(x)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == x.dtype and residual.is_contiguous()
+    ms = C.c_float(0)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_ds_gdn_nhwc(int(fuse), C.c_void_p(x.data_ptr()), B, H, W, Cc, *[C.c_void_p(h.data_ptr()) for h in hs],
+                                               1 if inverse else 0, C.c_void_p(residual.data_ptr()) if residual is not None else None,
                                                C.c_void_p(out.data_ptr()), iters, C.byref(ms), C.c_void_p(st)))
     return out, float(ms.value)
 

@@ -85,16 +85,32 @@ def decompress_one_image(model, stream_path, img_name):
     return out["x_hat"][:, :, 0:original_size[0], 0:original_size[1]], out["cost_time"]
 
 
+_GAIN_BITS = 0x00800000        # third header word >= this: not a level but the float32 bit pattern of a forced gain
+
+
+def _level_word(level, force):
+    """Third header word of a VBR stream.  The reference writes `level` itself (testing.py:244, struct ">3I"): an integer.
+    A fractional forced gain cannot be written by the reference at all (struct.pack raises on a float); here it travels as
+    its float32 bit pattern (every positive normal float32 is >= 0x00800000 as an integer, far above any level), so that
+    the decoder dequantises with exactly the gain the encoder used.  -> (word, the value handed to compress / decompress)"""
+    if float(level) == int(level) and 0 <= int(level) < _GAIN_BITS:
+        return int(level), int(level)
+    if not force:
+        raise ValueError(f"level {level!r} is not an index into the gain table")
+    g32 = struct.unpack("<f", struct.pack("<f", float(level)))[0]
+    word = struct.unpack("<I", struct.pack("<f", g32))[0]
+    if not (g32 > 0 and word >= _GAIN_BITS):
+        raise ValueError(f"forced gain {level!r} is not a positive normal float32")
+    return word, g32
+
+
 def compress_one_image_vbr(model, x, stream_path, H, W, img_name, level=0, force=False):
-    """testing.py:232-247.  The reference writes `level` itself with struct.pack(">3I"): a non-integer level raises there, so
-    a fractional custom gain cannot reach a file whose header would carry only its integer part."""
-    if float(level) != int(level) or int(level) < 0:
-        raise ValueError(f"level {level!r} cannot be stored in the stream header (unsigned integer): the decoder would "
-                         "dequantise with a different gain than the encoder used")
-    out = model.compress(x, stage=2, s=int(level), inputscale=0 if not force else level)
+    """testing.py:232-247"""
+    word, lv = _level_word(level, force)
+    out = model.compress(x, stage=2, s=int(lv), inputscale=0 if not force else lv)
     output = os.path.join(stream_path, img_name)
     with Path(output).open("wb") as f:
-        write_uints(f, (H, W, int(level)))
+        write_uints(f, (H, W, word))
         write_body(f, out["shape"], out["strings"])
     return float(os.path.getsize(output)) * 8 / (H * W), out["cost_time"]
 
@@ -102,8 +118,9 @@ def compress_one_image_vbr(model, x, stream_path, H, W, img_name, level=0, force
 def decompress_one_image_vbr(model, stream_path, img_name, force=False):
     """testing.py:250-262"""
     with Path(os.path.join(stream_path, img_name)).open("rb") as f:
-        H, W, level = read_uints(f, 3)
+        H, W, word = read_uints(f, 3)
         strings, shape = read_body(f)
+    level = struct.unpack("<f", struct.pack("<I", word))[0] if word >= _GAIN_BITS else word
     out = model.decompress(strings, shape, s=int(level), stage=2, inputscale=0 if not force else level)
     return out["x_hat"][:, :, 0:H, 0:W], out["cost_time"]
 

@@ -116,3 +116,23 @@ def test_eval_loops_on_the_engine(tmp_path):
     assert os.path.exists(tmp_path / "v" / "000_lv05")
     rg = stream.test_model_vbr(imgs[1:], vbr, str(tmp_path / "g"), custom_scales=[0.25])          # forced gain
     assert list(rg) == [0.25] and rg[0.25]["avg"]["psnr"] > 5
+    # the forced fractional gain reaches the decoder exactly (float32 bits in the third header word), so the decoded image is the
+    # encoder's own reconstruction at that gain, not one dequantised with int(0.25) = 0
+    with open(tmp_path / "g" / "000_g0.25", "rb") as f:
+        assert stream.read_uints(f, 3)[2] == 0x3E800000
+    padded, H, W = stream.pad_to_64(imgs[1])
+    enc = vbr.compress(padded.cuda(), stage=2, s=0, inputscale=0.25)
+    dec = vbr.decompress(enc["strings"], enc["shape"], stage=2, s=0, inputscale=0.25)
+    x_file, _ = stream.decompress_one_image_vbr(vbr, str(tmp_path / "g"), "000_g0.25", force=True)
+    assert torch.equal(x_file.cpu(), dec["x_hat"][:, :, :H, :W].cpu())
+
+
+def test_vbr_header_word_carries_integer_levels_and_fractional_gains():
+    import struct
+    assert stream._level_word(3, False) == (3, 3) and stream._level_word(2.0, True) == (2, 2)
+    word, g = stream._level_word(0.3, True)
+    assert word >= stream._GAIN_BITS and struct.unpack("<f", struct.pack("<I", word))[0] == g == torch.tensor(0.3).item()
+    with pytest.raises(ValueError):
+        stream._level_word(0.3, False)           # not an index into the gain table
+    with pytest.raises(ValueError):
+        stream._level_word(-1.5, True)

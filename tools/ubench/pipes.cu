@@ -30,6 +30,12 @@ __global__ void k(float* out, float a, float b, long long* clk) {
                        unsigned u4 = __float_as_uint(x4), u5 = __float_as_uint(x5), u6 = __float_as_uint(x6), u7 = __float_as_uint(x7);
                        u4 = (u4 << 16) ^ i; u5 = (u5 & 0xffff0000u) ^ i; u6 = (u6 << 16) ^ i; u7 = (u7 & 0xffff0000u) ^ i;
                        x0 = __uint_as_float(u0); x1 = __uint_as_float(u1); x2 = __uint_as_float(u2); x3 = __uint_as_float(u3); x4 = __uint_as_float(u4); x5 = __uint_as_float(u5); x6 = __uint_as_float(u6); x7 = __uint_as_float(u7); }
+        if (OP == 9) {     // FFMA2 with three distinct 64-bit register operands per instruction (no operand shared by neighbours)
+            p0 = __ffma2_rn(p1, p2, p0); p3 = __ffma2_rn(p4, p5, p3); p6 = __ffma2_rn(p7, aa, p6); p1 = __ffma2_rn(p2, p0, p1);
+            p4 = __ffma2_rn(p5, p3, p4); p7 = __ffma2_rn(bb, p6, p7); p2 = __ffma2_rn(p0, p1, p2); p5 = __ffma2_rn(p3, p4, p5); }
+        if (OP == 10) {    // plain FFMA with three distinct register operands
+            x0 = fmaf(x1, x2, x0); x3 = fmaf(x4, x5, x3); x6 = fmaf(x7, a, x6); x1 = fmaf(x2, x0, x1);
+            x4 = fmaf(x5, x3, x4); x7 = fmaf(b, x6, x7); x2 = fmaf(x0, x1, x2); x5 = fmaf(x3, x4, x5); }
     }
     long long t1 = clock64();
     if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
@@ -48,6 +54,6 @@ template <int OP> void run(const char* name, int per_iter_ops) {
     cudaFree(out); cudaFree(clk);
 }
 int main() {
-    run<0>("FFMA reg", 8); run<2>("FFMA imm", 8); run<1>("FFMA2", 16); run<6>("FMUL reg", 8); run<3>("MUFU.EX2", 8); run<4>("MUFU.RCP", 8); run<7>("MUFU.TANH", 8); run<5>("LDS.32", 8); run<8>("ALU shl/and+xor", 16);
+    run<0>("FFMA reg", 8); run<2>("FFMA imm", 8); run<1>("FFMA2", 16); run<6>("FMUL reg", 8); run<3>("MUFU.EX2", 8); run<4>("MUFU.RCP", 8); run<7>("MUFU.TANH", 8); run<5>("LDS.32", 8); run<8>("ALU shl/and+xor", 16); run<9>("FFMA2 3reg", 16); run<10>("FFMA 3reg", 8);
     return 0;
 }
