@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmlic_b200.so")
+LIB_PATH = os.environ.get("MLIC_LIB") or os.path.join(_HERE, "libmlic_b200.so")      # MLIC_LIB: development builds (tools/build_variant.sh)
 
 KIND_BASE, KIND_SD, KIND_VBR = 0, 1, 2
 PREC_FP32, PREC_BF16 = 0, 1

@@ -9,7 +9,9 @@ floating-point *parameter* is overwritten by a value that depends only on
 init) with extra jitter so that no term is trivially zero (GDN off-diagonals,
 EB factors/medians, relative-position table).
 """
+import json
 import math
+import os
 import zlib
 
 import torch
@@ -112,6 +114,25 @@ def seeded_state_dict(state_dict, seed=1234, y_gain=1.0, sigma_spread=0.0):
                     t[:C] += _u((C,), 0.0, float(sigma_spread), _gen(seed, k + "#spread"))
                 out[k] = t
     return out
+
+
+def template_state_dict(name):
+    """state_dict template of reference model `name` (keys, shapes and the small buffers weights.py leaves alone), read from
+    oracle/shapes/<name>.npz -- dumped from the unmodified reference by oracle/make_shapes.py.  Float parameters are zeros."""
+    import numpy as np
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shapes", f"{name}.npz")
+    z = np.load(path)
+    meta = json.loads(bytes(z["__meta__"]).decode())
+    out = {}
+    for k, m in meta.items():
+        dt = getattr(torch, m["dtype"])
+        out[k] = torch.from_numpy(z[k]).to(dt).reshape(m["shape"]) if m.get("stored") else torch.zeros(m["shape"], dtype=dt)
+    return out
+
+
+def reference_state_dict(name, seed=1234, y_gain=1.0, sigma_spread=0.0):
+    """The seeded weights of `name` built from the committed template alone (no model object, no product package)."""
+    return seeded_state_dict(template_state_dict(name), seed, y_gain=y_gain, sigma_spread=sigma_spread)
 
 
 def synthetic_image(B, H, W, seed=2024, kind="smooth"):
