@@ -213,6 +213,11 @@ def main():
         run_reference(args, cfg_name, cfg, rank)
         return
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: NCCL (version banner) and other native libraries write to file descriptor 1 directly,
+    # so everything but that line is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     H, W, MP_IMG = cfg["H"], cfg["W"], cfg["mp"]
     B = args.batch or cfg["batch"]
 
@@ -421,7 +426,7 @@ def main():
                            "parallelism": f"row bands x{world}" if bands else f"batch-shard x{world}", "weights": "random-init seed 1234",
                            "l2": "per-step inputs + activations (>1 GB/image) exceed the 126 MB L2; no explicit flush"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "quality": quality}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
