@@ -112,7 +112,26 @@ constexpr int DP_RAW_BYTES = (DP_TH + 2) * (DP_TW + 2) * 128;       // one halo 
 constexpr int DP_RAW_SLOTS_MAX = 4;
 constexpr int DP_A_BYTES = 128 * 128;
 constexpr int DP_STG_BYTES = 128 * 128;
-constexpr int DP_PROD_WARPS = 8;
+#ifndef MLIC_DP_PROD_WARPS
+#define MLIC_DP_PROD_WARPS 8
+#endif
+// 8: one warp = 2 columns x 8 rows of the tile; 16: 2 columns x 4 rows (1024 threads, registers traded between the roles with
+// setmaxnreg).  Measured at 4 x 544 x 960 x 192 (profiles/r02_pair_variants.txt): 16 warps make the producers fast enough that the
+// MMA never waits for A, but they take their issue slots from the epilogue warps, which then pace the tile: 460 -> 491 us without
+// and 514 -> 527 us with a residual.  The kernel is issue-bound (19 instructions per output value, ~50 % of the issue slots), not
+// short of one role's warps.
+constexpr int DP_PROD_WARPS = MLIC_DP_PROD_WARPS;
+constexpr int DP_PROD_ROWS = DP_TH * 8 / DP_PROD_WARPS;            // output rows per producer warp
+// register budgets per role (setmaxnreg, warpgroup-granular): 1024 threads leave 64 registers per thread on average
+#ifndef MLIC_DP_REGS_MISC
+#define MLIC_DP_REGS_MISC 40
+#endif
+#ifndef MLIC_DP_REGS_EPI
+#define MLIC_DP_REGS_EPI 80
+#endif
+#ifndef MLIC_DP_REGS_PROD
+#define MLIC_DP_REGS_PROD 56
+#endif
 
 struct DpParams {
     int tilesH, tilesW, ntiles, npairs;
@@ -128,19 +147,16 @@ struct DpMaps {
     CUtensorMap out, res;   // box {64, 16, 8, 1}, 128B swizzle
 };
 
-template <int NCH, int MODE> struct DpCfg {
+template <int NCH, int MODE, bool RES = false> struct DpCfg {
     static constexpr int C = 64 * NCH;
     static constexpr int WCH_BYTES = (C / 2) * 128;                 // one K chunk of this CTA's half of a weight matrix
     static constexpr int W_BYTES = NCH * WCH_BYTES;
     static constexpr int NA = MODE == DP_TAIL ? NCH : (NCH < 2 ? NCH : 2);     // A stages
-#ifndef MLIC_DP_NRING
-#define MLIC_DP_NRING 1
-#endif
-#ifndef MLIC_DP_RAW
-#define MLIC_DP_RAW 4
-#endif
-    static constexpr int NRING = MODE == DP_TAIL ? 1 : MLIC_DP_NRING;          // staging slots per epilogue group
-    static constexpr int RAW_SLOTS = MODE == DP_TAIL ? 2 : MLIC_DP_RAW;        // halo patches in flight (TAIL: shared memory is full)
+    // staging slots per epilogue group / halo patches in flight.  DS with a residual: two slots, so that the residual block of the
+    // next tile lands while this one is computed (the wait for it and for the drain of the previous store were 3.1 k of the
+    // 9.2 k clocks of a tile), paid for with two of the four halo slots; TAIL: shared memory is full
+    static constexpr int NRING = (MODE == DP_DS && RES) ? 2 : 1;
+    static constexpr int RAW_SLOTS = (MODE == DP_TAIL || RES) ? 2 : 4;
     static constexpr int OFF_W1 = 0;
     static constexpr int OFF_W2 = W_BYTES;
     static constexpr int OFF_A = (MODE == DP_TAIL ? 2 : 1) * W_BYTES;
@@ -153,6 +169,9 @@ template <int NCH, int MODE> struct DpCfg {
     static_assert(SMEM <= 232448, "shared-memory plan exceeds 227 KB");
     static constexpr int EPI_WARPS = 4 * NCH;
     static constexpr int THREADS = 128 + (DP_PROD_WARPS + EPI_WARPS) * 32;
+    // 1024 threads: 64 registers per thread at launch; the roles trade them (misc 40 / epilogue 80 / producers 56 per thread)
+    static constexpr bool SETREG = THREADS > 896;
+    static_assert(!SETREG || 4 * MLIC_DP_REGS_MISC + EPI_WARPS * MLIC_DP_REGS_EPI + DP_PROD_WARPS * MLIC_DP_REGS_PROD <= 2048, "register plan");
     static constexpr int EW0 = 4;                                   // epilogue warps 4 .. 4 + EPI_WARPS - 1 (multiple of 4: TMEM lane quarter = warp % 4)
     static constexpr int PW0 = 4 + EPI_WARPS;                       // producers get the highest warp ids: the issue arbiter prefers them, and they pace the tile
     // TMEM columns (512 allocated): DS: two accumulator stages at 0 and 256; TAIL: v at [0, C), the bf16 v^2 A operand at
@@ -163,9 +182,9 @@ template <int NCH, int MODE> struct DpCfg {
 };
 
 template <int NCH, int MODE, int ACT, bool RES, int GDN>
-__global__ void __launch_bounds__(DpCfg<NCH, MODE>::THREADS, 1)
+__global__ void __launch_bounds__(DpCfg<NCH, MODE, RES>::THREADS, 1)
 ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned long long* __restrict__ dbg) {
-    using Cfg = DpCfg<NCH, MODE>;
+    using Cfg = DpCfg<NCH, MODE, RES>;
     constexpr int C = Cfg::C;
     extern __shared__ uint8_t dp_smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)dp_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -217,8 +236,7 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // development (MLIC_TC_DEBUG & 32): per-role wait / work clocks of CTA 0's producer warp 4, first epilogue warp and MMA thread
-    long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;
-    const long long t_start = clock64();
+    const long long t_start = dbg ? clock64() : 0;
 #define DP_TIMED(acc, stmt) do { if (dbg) { const long long _t = clock64(); stmt; acc += clock64() - _t; } else { stmt; } } while (0)
     const int tiles_per_img = p.tilesH * p.tilesW;
     const int pair_first = (int)(blockIdx.x >> 1), pair_step = (int)(gridDim.x >> 1);
@@ -233,7 +251,11 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
     const int h0 = th * DP_TH, w0 = tw * DP_TW;                                               \
     (void)tvalid; (void)h0; (void)w0; (void)img
 
-    if (warp == 0) {
+    // the role split is ONE if / else chain and every setmaxnreg sits at the top of its arm: ptxas takes the smallest budget that can
+    // reach a point, so an arm that joined a `dec` path would be compiled for that path's registers
+    if (warp < 4) {
+      if constexpr (Cfg::SETREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MLIC_DP_REGS_MISC));
+      if (warp == 0) {
         if (lane == 0) {
             // this CTA's half of the N rows of each weight matrix, all K chunks, once
             mbar_expect_tx(&w_full, (uint32_t)((MODE == DP_TAIL ? 2 : 1) * Cfg::W_BYTES));
@@ -253,8 +275,9 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         if (lane == 0) {
+            long long tw0 = 0, tw1 = 0, tw2 = 0;
             // both CTAs report their weights to the leader
             mbar_wait(&w_full, 0);
             mbar_arrive_cluster(mapa_u32(smem_u32(&w_ready), 0));
@@ -311,25 +334,31 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                     }
                 }
             }
+            if (dbg && blockIdx.x == 0) { dbg[0] = (unsigned long long)(clock64() - t_start); dbg[1] = (unsigned long long)tw0; dbg[2] = (unsigned long long)tw1; dbg[3] = (unsigned long long)tw2; }
         }
+      }
     } else if (warp >= Cfg::PW0) {
-        // ---- depthwise 3x3 producers: halo patch -> A stage (bf16, K-major, 128B swizzle)
+        // ---- depthwise 3x3 producers: halo patch -> A stage (bf16, K-major, 128B swizzle).  Warp pw: columns 2 cp, 2 cp + 1 and
+        // output rows [row0, row0 + DP_PROD_ROWS) of the 8 x 16 tile; lane = channel pair
+        if constexpr (Cfg::SETREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MLIC_DP_REGS_PROD));
+        long long tw0 = 0, tw1 = 0;
         const int pw = warp - Cfg::PW0;
+        const int cp = pw & 7, row0 = (pw >> 3) * DP_PROD_ROWS;
         const uint32_t a_full_leader0 = mapa_u32(smem_u32(&a_full[0]), 0);
         int stage = 0, rslot = 0;
         uint32_t sphase = 0, rphase = 0;
-        // STS offsets of this lane inside an A stage: row r = oy * 16 + 2 pw + c, (r & 7) = (2 pw + c) & 7 whatever oy
+        // STS offsets of this lane inside an A stage: row r = oy * 16 + 2 cp + c, (r & 7) = (2 cp + c) & 7 whatever oy
         uint32_t st_off[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int r0 = 2 * pw + c;
-            st_off[c] = (uint32_t)(r0 * 128 + (((lane >> 2) ^ (r0 & 7)) << 4) + ((lane & 3) << 2));
+            const int r0 = 2 * cp + c;
+            st_off[c] = (uint32_t)(row0 * 16 * 128 + r0 * 128 + (((lane >> 2) ^ (r0 & 7)) << 4) + ((lane & 3) << 2));
         }
         for (int pp = pair_first; pp < p.npairs; pp += pair_step) {
             for (int k = 0; k < NCH; ++k) {
                 DP_TIMED(tw0, mbar_wait(&raw_full[rslot], rphase));
                 DP_TIMED(tw1, mbar_wait(&a_empty[stage], sphase ^ 1));
-                uint32_t rp = smem_u32(base + Cfg::OFF_RAW) + (uint32_t)(rslot * DP_RAW_BYTES + ((2 * pw) * 32 + lane) * 4);
+                uint32_t rp = smem_u32(base + Cfg::OFF_RAW) + (uint32_t)(rslot * DP_RAW_BYTES + (row0 * (DP_TW + 2) + 2 * cp) * 128 + lane * 4);
                 uint32_t wk = smem_u32(sDw) + (uint32_t)((k * 640 + 2 * lane) * 4);
                 asm volatile("" : "+r"(rp), "+r"(wk) :: "memory");        // the loads below depend on rp / wk: they stay behind the waits
                 const uint32_t sa = smem_u32(base + Cfg::OFF_A) + (uint32_t)(stage * DP_A_BYTES);
@@ -337,18 +366,18 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
 #pragma unroll
                 for (int tp = 0; tp < 9; ++tp) w2[tp] = lds_f2_nv(wk + (uint32_t)(tp * 256));
                 const float2 b2 = lds_f2_nv(wk + 9u * 256u);
-                float2 acc[DP_TH][2];
+                float2 acc[DP_PROD_ROWS][2];
 #pragma unroll
-                for (int oy = 0; oy < DP_TH; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
+                for (int oy = 0; oy < DP_PROD_ROWS; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
 #pragma unroll
-                for (int iy = 0; iy < DP_TH + 2; ++iy) {
+                for (int iy = 0; iy < DP_PROD_ROWS + 2; ++iy) {
                     float2 x[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) x[j] = bf2_unpack_alu(lds32_nv(rp + (uint32_t)((iy * (DP_TW + 2) + j) * 128)));
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
                         const int oy = iy - ky;
-                        if (oy >= 0 && oy < DP_TH) {
+                        if (oy >= 0 && oy < DP_PROD_ROWS) {
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -371,8 +400,11 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                 if (++stage == Cfg::NA) { stage = 0; sphase ^= 1; }
             }
         }
-    } else if (warp >= Cfg::EW0 && warp < Cfg::PW0) {
+        if (dbg && blockIdx.x == 0 && pw == 0 && lane == 0) { dbg[4] = (unsigned long long)(clock64() - t_start); dbg[5] = (unsigned long long)tw0; dbg[6] = (unsigned long long)tw1; }
+    } else {
         // ---- epilogue: group eb = 64 output columns, q = TMEM lane quarter of this warp, one pixel per thread
+        if constexpr (Cfg::SETREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MLIC_DP_REGS_EPI));
+        long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;
         const int q = warp & 3, eb = (warp - Cfg::EW0) >> 2;
         const int r = q * 32 + lane;
         const bool gissuer = (q == 0 && lane == 0);
@@ -389,12 +421,23 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
             const uint32_t sb_s = smem_u32(sb);
             uint64_t* sbar = &stg_bar[eb][slot];
             const uint32_t sbar_ph = Cfg::NRING == 1 ? ((uint32_t)it & 1u) : ((uint32_t)(it >> 1) & 1u);
-            // the slot's previous TMA store (NRING tiles ago) must have finished reading it
-            DP_TIMED(tw3, { if (gissuer) tma_store_wait_read(Cfg::NRING - 1); asm volatile("bar.sync %0, 128;" ::"r"(eb + 1) : "memory"); });
-            if constexpr (RES) {
-                if (gissuer) {
+            // RES with two slots: the residual block of tile it + 1 is fetched into the other slot while this tile is computed (issued
+            // below, after the first accumulator read), so neither the drain of the previous store nor the latency of the load is
+            // on the epilogue's path; the first tile's block is fetched here
+            constexpr bool RESPF = RES && Cfg::NRING == 2;
+            if constexpr (RESPF) {
+                if (it == 0 && gissuer) {
                     mbar_expect_tx(sbar, (uint32_t)DP_STG_BYTES);
                     tma_load_4d(sb, &tm.res, sbar, eb * 64, w0, h0, img);
+                }
+            } else {
+                // the slot's previous TMA store (NRING tiles ago) must have finished reading it
+                DP_TIMED(tw3, { if (gissuer) tma_store_wait_read(Cfg::NRING - 1); asm volatile("bar.sync %0, 128;" ::"r"(eb + 1) : "memory"); });
+                if constexpr (RES) {
+                    if (gissuer) {
+                        mbar_expect_tx(sbar, (uint32_t)DP_STG_BYTES);
+                        tma_load_4d(sb, &tm.res, sbar, eb * 64, w0, h0, img);
+                    }
                 }
             }
             if constexpr (MODE == DP_DS) {
@@ -408,6 +451,18 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                     uint32_t raw[16];
                     tmem_ld16(trow + (uint32_t)(pr * 16), raw);
                     tmem_ld_wait();
+                    if constexpr (RESPF) {
+                        if (pr == 0 && gissuer && pp + pair_step < p.npairs) {
+                            int tn = 2 * (pp + pair_step) + (int)rank;
+                            if (tn >= p.ntiles) tn = p.ntiles - 1;
+                            const int imgn = tn / tiles_per_img, tremn = tn - imgn * tiles_per_img;
+                            const int thn = tremn / p.tilesW, twn = tremn - thn * p.tilesW;
+                            tma_store_wait_read(0);             // the other slot's store (previous tile) has read its block
+                            mbar_expect_tx(&stg_bar[eb][slot ^ 1], (uint32_t)DP_STG_BYTES);
+                            tma_load_4d(base + Cfg::OFF_STG + (size_t)(eb * Cfg::NRING + (slot ^ 1)) * DP_STG_BYTES, &tm.res, &stg_bar[eb][slot ^ 1], eb * 64,
+                                        twn * DP_TW, thn * DP_TH, imgn);
+                        }
+                    }
                     if (pr == 3) {                  // accumulator fully read by this warp
                         tcgen05_fence_before();
                         __syncwarp();
@@ -522,15 +577,12 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
             }
         }
         if (gissuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (dbg && blockIdx.x == 0 && warp == Cfg::EW0 && lane == 0) {
+            dbg[8] = (unsigned long long)(clock64() - t_start); dbg[9] = (unsigned long long)tw0; dbg[10] = (unsigned long long)tw1; dbg[11] = (unsigned long long)tw2; dbg[12] = (unsigned long long)tw3;
+        }
     }
 #undef DP_TILE
 #undef DP_TIMED
-    if (dbg && blockIdx.x == 0 && lane == 0) {
-        const unsigned long long tot = (unsigned long long)(clock64() - t_start);
-        if (warp == 1) { dbg[0] = tot; dbg[1] = (unsigned long long)tw0; dbg[2] = (unsigned long long)tw1; dbg[3] = (unsigned long long)tw2; }
-        if (warp == Cfg::PW0) { dbg[4] = tot; dbg[5] = (unsigned long long)tw0; dbg[6] = (unsigned long long)tw1; }
-        if (warp == Cfg::EW0) { dbg[8] = tot; dbg[9] = (unsigned long long)tw0; dbg[10] = (unsigned long long)tw1; dbg[11] = (unsigned long long)tw2; dbg[12] = (unsigned long long)tw3; }
-    }
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();                 // the peer may still be reading this CTA's weights / TMEM through the pair MMA
@@ -562,7 +614,7 @@ bool ds_pair_supported(const DsPairArgs& a) {
 
 template <int NCH, int MODE, int ACT, bool RES, int GDN>
 static int dp_launch(const DpMaps& tm, const DpParams& p, int nclusters, cudaStream_t s) {
-    using Cfg = DpCfg<NCH, MODE>;
+    using Cfg = DpCfg<NCH, MODE, RES>;
     auto fn = ds_pair_kernel<NCH, MODE, ACT, RES, GDN>;
     static bool attr[64] = {};
     int dev = 0;
