@@ -210,10 +210,57 @@ class MLICPlusPlus(nn.Module):
         _lib.check(_lib.lib().mlic_trace_dump(self._engine, str(path).encode()))
 
     def set_precision(self, precision):
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        """"bf16" (fast mode), "fp32" (validation mode), or one precision per stage as a tuple (g_a, entropy model, g_s) --
+        "mixed" is ("fp32", "fp32", "bf16"): everything that decides a symbol (g_a -> y, h_a / h_s, the slice loop -> mu, sigma)
+        runs in the bit-exact fp32 mode, the synthesis transform (64 % of the FLOPs) on the tensor cores.  The stages are then
+        separate engine calls joined by the fp32 `y` / `y_hat` tensors (device inputs only; host tensors are uploaded first)."""
+        if precision == "mixed":
+            precision = ("fp32", "fp32", "bf16")
+        if isinstance(precision, (tuple, list)):
+            precision = tuple(precision)
+            if len(precision) != 3 or any(q not in ("bf16", "fp32") for q in precision):
+                raise ValueError("per-stage precision is a 3-tuple of 'bf16' / 'fp32' (g_a, entropy model, g_s)")
+            if len(set(precision)) == 1:
+                precision = precision[0]
+        elif precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16', 'fp32', 'mixed' or a 3-tuple of 'bf16' / 'fp32'")
         self.precision = precision
         return self
+
+    def _run_staged(self, mode, x, B, H, W, gain, want):
+        """A full call with per-stage precisions: consecutive stages of equal precision share one engine call."""
+        pa, pe, ps = self.precision
+        dev = x.device if (x is not None and x.is_cuda) else torch.device("cuda", torch.cuda.current_device())
+        host = x is not None and not x.is_cuda
+        if host:
+            x = x.to(dev, non_blocking=True)
+        keep = self.precision
+        out = {}
+        try:
+            y = None
+            if mode != _lib.MODE_DECODER and pa != pe:
+                self.precision = pa
+                o = self._run(mode, x, B, H, W, 0.0, ("y",), stages=1)
+                y = o["y"]
+                if "y" in want:
+                    out["y"] = y
+            self.precision = pe
+            first = 2 if (y is not None or mode == _lib.MODE_DECODER) else 3
+            if pe == ps:
+                o = self._run(mode, None if y is not None else x, B, H, W, gain, tuple(want), stages=first | 4, y=y)
+                out.update(o)
+            else:
+                w2 = tuple(set(want) | {"y_hat"})
+                o = self._run(mode, None if first == 2 else x, B, H, W, gain, w2, stages=first, y=y)
+                y_hat = o["y_hat"]
+                out.update({k: v for k, v in o.items() if k != "y_hat" or "y_hat" in want})
+                self.precision = ps
+                out.update(self._run(_lib.MODE_FORWARD, None, B, H, W, 0.0, (), stages=4, y_hat=y_hat))
+        finally:
+            self.precision = keep
+        if host:
+            out = {k: v.cpu() for k, v in out.items()}
+        return out
 
     # ------------------------------------------------------------------ engine plumbing
     def _signature(self):
@@ -268,6 +315,10 @@ class MLICPlusPlus(nn.Module):
         """One engine call.  x: CUDA tensor (device path) or CPU tensor (host path through mlic_run_host).
         stages: bit mask of include/mlic_b200.h option "stages" (1 g_a | 2 entropy model | 4 g_s); `y` / `y_hat` are the
         device INPUTS of the calls that start after g_a / at g_s (row-band sharding, mlic_b200/dist.py)."""
+        if isinstance(self.precision, tuple):
+            if stages != 7:
+                raise _lib.MlicError("stage-subset calls take one precision (set_precision('bf16' | 'fp32'))")
+            return self._run_staged(mode, x, B, H, W, gain, want)
         hmul = 64 if stages & 2 else 16
         if H % hmul or W % 64:
             raise ValueError("H and W must be multiples of 64 (the reference pads, utils/testing.py:130-137)")
@@ -463,7 +514,9 @@ class MLICPlusPlus(nn.Module):
                                          off.ctypes.data_as(C.c_void_p), cdf.shape[0]))
         for name, val in ((b"tensor_cores", self.tensor_cores), (b"profile", False), (b"fuse", self.fuse), (b"trace", self._trace), (b"stages", 7)):
             _lib.check(L.mlic_engine_set_option(self._engine, name, int(val)))
-        prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        # per-stage precisions: the decoder must reproduce the encoder's mu / sigma, so the whole walk runs in the entropy stage's
+        one = self.precision[1] if isinstance(self.precision, tuple) else self.precision
+        prec = _lib.PREC_BF16 if one == "bf16" else _lib.PREC_FP32
         out = {"x_hat": torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)}
         if "y_hat" in taps:
             out["y_hat"] = torch.empty((B, self.M, H // 16, W // 16), dtype=torch.float32, device=dev)
