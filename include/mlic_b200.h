@@ -110,7 +110,7 @@ int mlic_trace_dump(mlic_engine* e, const char* path);
 /* Stand-alone convolution on an NHWC activation tensor (fp32 or bf16 per `precision`; weights / bias are HOST
  * fp32 in the reference's nn.Conv2d layout [N][Cin][ks][ks]): out = act(conv(in) + bias) (+ residual), optionally
  * pixel-shuffled by 2 (CompressAI subpel_conv3x3).  tensor_cores = 1 selects the tcgen05 implicit-GEMM kernel where
- * it applies, 0 the CUDA-core kernel.  Runs `iters` launches and reports the average duration of launches 2..iters
+ * it applies, 2 additionally the two-SM (cta_group::2) kernel for wide 3x3 convs, 0 the CUDA-core kernel.  Runs `iters` launches and reports the average duration of launches 2..iters
  * (CUDA events); synchronises.  Kernel-level test / micro-benchmark hook for nn.Conv2d call sites such as
  * modules/layers/conv.py:55-60 and res_blk.py:107-111. */
 int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int H, int W, int Cin, const float* weight,

@@ -554,6 +554,32 @@ struct mlic_engine {
             if (prod && !sup) return false;
             if (o.ck && !sup) { if (!rc) rc = fail("gemm '%s': checkerboard rows not supported for this layer", key.c_str()); return true; }
             if (!go()) return true;
+            // wide dense 3x3 convs (the sub-pixel convs of g_s): two-SM kernel, each CTA stages half of the weight tile (conv3_pair.cu)
+            if (sup && pair && !prod && !o.ck && w->ks == 3 && stride == 1 && pad == 1 && !e.res && !e.gdn && !e.out2 && !e.out_f32 && !e.nchw &&
+                !e.premask && !e.postmask && w->Cpad == w->Cin) {
+                Conv3PairArgs a;
+                memset(&a, 0, sizeof a);
+                a.in = in.p; a.B = in.B; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ld = in.ld;
+                a.w = w->wbf; a.bias = w->bias; a.N = w->N; a.act = e.act; a.shuffle = w->shuffle; a.out = e.out; a.out_ld = e.out_ld;
+                if (conv3_pair_supported(a)) {
+                    cudaEvent_t ev1 = nullptr;
+                    if (profile) {
+                        cudaEventRecord(next_event(), st);
+                        ev1 = next_event();
+                        ev_flops.push_back(2.0 * (double)in.B * e.Hout * e.Wout * (double)w->N * (double)(9 * w->Cin));
+                    }
+                    int r = launch_conv3_pair(a, st);
+                    if (ev1) cudaEventRecord(ev1, st);
+                    if (r) { if (!rc) rc = fail("two-SM conv '%s': %s", key.c_str(), conv3_pair_last_error()); return true; }
+                    ++launches;
+                    if (trace) {
+                        char lab[256];
+                        snprintf(lab, sizeof lab, "%s [pair conv3 M=%d N=%d K=9x%d]", key.c_str(), in.B * e.Hout * e.Wout, w->N, w->Cin);
+                        tr(lab);
+                    }
+                    return true;
+                }
+            }
             if (sup) {
                 cudaEvent_t ev1 = nullptr;
                 if (profile) {
@@ -1412,7 +1438,7 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
     e.rc = 0;
     e.pack_conv_raw("w", weight, bias, N, Cin, ks, shuffle);
     if (e.rc) return e.rc;
-    e.bf = precision == MLIC_PREC_BF16; e.use_tc = tensor_cores; e.dry = false; e.st = (cudaStream_t)cuda_stream;
+    e.bf = precision == MLIC_PREC_BF16; e.use_tc = tensor_cores != 0; e.pair = tensor_cores == 2; e.dry = false; e.st = (cudaStream_t)cuda_stream;      // 2: the two-SM kernels where they apply
     if (e.bf && e.use_tc && tc_init()) return fail("%s", tc_last_error());
     Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin;
     const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;

@@ -244,75 +244,114 @@ void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const floa
 // tensor (the NHWC copy of x, the depthwise output) touches HBM.
 // ------------------------------------------------------------------------------------------
 constexpr int GH_PIX = 64;
-constexpr int GH_THREADS = 192;             // warps 0-2: conv1 path (GELU), warps 3-5: skip path
-__global__ void __launch_bounds__(GH_THREADS, 6) ga_head_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ dw9,
-                                                      const float* __restrict__ dwb, const float* __restrict__ w1,
-                                                      const float* __restrict__ b1, const float* __restrict__ wsk,
-                                                      const float* __restrict__ bsk, int N, bf16* __restrict__ t, int t_ld,
-                                                      bf16* __restrict__ sk, int sk_ld) {
-    __shared__ float sx[3][3][2 * GH_PIX + 2];
-    __shared__ float4 st[2][GH_PIX];         // [0]: depthwise result, [1]: the stride-2 sample of x
-    const int Ho = H >> 1, Wo = W >> 1;
-    const int tiles_w = (Wo + GH_PIX - 1) / GH_PIX;
-    int bid = blockIdx.x;
-    const int tw = bid % tiles_w; bid /= tiles_w;
-    const int oh = bid % Ho;
-    const int b = bid / Ho;
-    const int ow0 = tw * GH_PIX;
-    for (int rc = threadIdx.x / 32; rc < 9; rc += GH_THREADS / 32) {          // one warp per (channel, row): contiguous reads
-        const int r = rc % 3, c = rc / 3;
-        const int ih = 2 * oh - 1 + r;
-        const float* row = x + (((size_t)b * 3 + c) * H + ih) * W;
-        for (int j = threadIdx.x & 31; j < 2 * GH_PIX + 1; j += 32) {
-            const int iw = 2 * ow0 - 1 + j;
-            sx[c][r][j] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? row[iw] : 0.f;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < GH_PIX * 3) {
-        const int p = threadIdx.x / 3, c = threadIdx.x % 3;
-        float acc = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) acc = fmaf(sx[c][ky][2 * p + kx], dw9[(ky * 3 + kx) * 3 + c], acc);
-        reinterpret_cast<float*>(&st[0][p])[c] = acc + dwb[c];
-        reinterpret_cast<float*>(&st[1][p])[c] = sx[c][1][2 * p + 1];
-    }
-    __syncthreads();
-    const int role = threadIdx.x / 96, tr = threadIdx.x % 96;                 // warp-uniform role
-    const int ng = N >> 3;
-    const int g = tr % ng, pl = tr / ng, npl = 96 / ng;
-    if (pl >= npl) return;
+constexpr int GH_THREADS = 288;             // warps 0-5: conv1 path (GELU), warps 6-8: skip path (a third of the arithmetic per value)
+// One role's share of the block: thread (pixel lane pl, 8-column group g) keeps its 8 x 3 weights and 8 biases in registers and
+// walks the pixels pl, pl + npl, ... with one pointer increment per pixel.  (The first version re-read its parameters from the
+// constant bank, re-derived the role and the 64-bit address in every iteration and branched around the GELU per channel pair:
+// 106 / 71 instructions per 16-byte store against 66 / 26 here; profiles/r02_ncu_head.txt.)
+struct GhW { float2 wa[4][3], ba[4]; };
+__device__ __forceinline__ void gh_load(GhW& w, int g, const float* __restrict__ wsrc, const float* __restrict__ bsrc) {
     const int n = g * 8;
-    const float* wsrc = role ? wsk : w1;
-    const float* bsrc = role ? bsk : b1;
-    float2 wa[4][3], ba[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) wa[j][c] = make_float2(wsrc[(size_t)(n + 2 * j) * 3 + c], wsrc[(size_t)(n + 2 * j + 1) * 3 + c]);
-        ba[j] = make_float2(bsrc[n + 2 * j], bsrc[n + 2 * j + 1]);
+        for (int c = 0; c < 3; ++c) w.wa[j][c] = make_float2(wsrc[(size_t)(n + 2 * j) * 3 + c], wsrc[(size_t)(n + 2 * j + 1) * 3 + c]);
+        w.ba[j] = make_float2(bsrc[n + 2 * j], bsrc[n + 2 * j + 1]);
     }
-    bf16* dst = role ? sk : t;
-    const int dld = role ? sk_ld : t_ld;
-    for (int p = pl; p < GH_PIX; p += npl) {
-        const int ow = ow0 + p;
-        if (ow >= Wo) break;
-        const float4 a = st[role][p];
+}
+template <bool GELU>
+__device__ __forceinline__ void gh_role(const GhW& w, const float4* __restrict__ src, int nvalid, int pl, int npl, bf16* __restrict__ dst, size_t dstep) {
+#pragma unroll 2
+    for (int p = pl; p < nvalid; p += npl) {
+        const float4 a = src[p];
         uint32_t o1[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float2 u = __fmul2_rn(make_float2(a.x, a.x), wa[j][0]);
-            u = __ffma2_rn(make_float2(a.y, a.y), wa[j][1], u);
-            u = __ffma2_rn(make_float2(a.z, a.z), wa[j][2], u);
-            u = __fadd2_rn(u, ba[j]);
-            if (role == 0) u = gelu2(u);
+            float2 u = __ffma2_rn(make_float2(a.x, a.x), w.wa[j][0], w.ba[j]);
+            u = __ffma2_rn(make_float2(a.y, a.y), w.wa[j][1], u);
+            u = __ffma2_rn(make_float2(a.z, a.z), w.wa[j][2], u);
+            if (GELU) u = gelu2(u);
             __nv_bfloat162 hu = __floats2bfloat162_rn(u.x, u.y);
             o1[j] = *reinterpret_cast<uint32_t*>(&hu);
         }
-        const size_t pix = ((size_t)b * Ho + oh) * Wo + ow;
-        *reinterpret_cast<uint4*>(dst + pix * dld + n) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+        dst += dstep;
+    }
+}
+// Persistent: a block keeps its weights in registers and walks row tiles blockIdx.x, blockIdx.x + gridDim.x, ... (with one tile per
+// block the 32 strided weight loads of every thread and the two barriers were as long as the tile's 48 stores per pixel: halving the
+// loop's instructions alone changed nothing, 547 -> 561 us at 4 images).
+__global__ void __launch_bounds__(GH_THREADS, 3) ga_head_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ dw9,
+                                                      const float* __restrict__ dwb, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, const float* __restrict__ wsk,
+                                                      const float* __restrict__ bsk, int N, bf16* __restrict__ t, int t_ld,
+                                                      bf16* __restrict__ sk, int sk_ld, int ntiles) {
+    __shared__ float sx[3][3][2 * GH_PIX + 2];
+    __shared__ float4 st[2][2][GH_PIX];      // [tile parity][0: depthwise result, 1: the stride-2 sample of x]
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int tiles_w = (Wo + GH_PIX - 1) / GH_PIX;
+    const int ng = N >> 3;
+    const bool conv = threadIdx.x < 192;                                       // warp-uniform
+    const int tr = conv ? threadIdx.x : threadIdx.x - 192, nthr = conv ? 192 : 96;
+    const int g = tr % ng, pl = tr / ng, npl = nthr / ng;
+    const bool active = pl < npl;
+    GhW w;
+    if (active) gh_load(w, g, conv ? w1 : wsk, conv ? b1 : bsk);
+    float dwr[9], dwbias = 0.f;
+    const int dp = threadIdx.x / 3, dc = threadIdx.x % 3;
+    if (threadIdx.x < GH_PIX * 3) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dwr[k] = dw9[k * 3 + dc];
+        dwbias = dwb[dc];
+    }
+    // warp rc = (channel, input row) of the 3 x 3 x 129 window: its 129 floats are fetched one tile AHEAD into registers (5 per lane),
+    // so the DRAM latency of the next tile's window runs under this tile's stores
+    static_assert(GH_THREADS / 32 == 9 && 2 * GH_PIX + 1 <= 5 * 32, "one warp per (channel, row), five floats per lane");
+    const int wr = (threadIdx.x >> 5) % 3, wc = (threadIdx.x >> 5) / 3, lane = threadIdx.x & 31;
+    float xr[5];
+    auto fetch = [&](int tile) {
+        int bid = tile;
+        const int tw = bid % tiles_w; bid /= tiles_w;
+        const int oh = bid % Ho;
+        const int b = bid / Ho;
+        const int ih = 2 * oh - 1 + wr;
+        const float* row = x + (((size_t)b * 3 + wc) * H + ih) * W;
+        const int iw0 = 2 * tw * GH_PIX - 1 + lane;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int iw = iw0 + 32 * i;
+            xr[i] = (lane + 32 * i < 2 * GH_PIX + 1 && ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(row + iw) : 0.f;
+        }
+    };
+    if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
+    int par = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1) {
+        int bid = tile;
+        const int tw = bid % tiles_w; bid /= tiles_w;
+        const int oh = bid % Ho;
+        const int b = bid / Ho;
+        const int ow0 = tw * GH_PIX;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            if (lane + 32 * i < 2 * GH_PIX + 2) sx[wc][wr][lane + 32 * i] = xr[i];
+        __syncthreads();
+        if (threadIdx.x < GH_PIX * 3) {
+            float acc = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) acc = fmaf(sx[dc][ky][2 * dp + kx], dwr[ky * 3 + kx], acc);
+            reinterpret_cast<float*>(&st[par][0][dp])[dc] = acc + dwbias;
+            reinterpret_cast<float*>(&st[par][1][dp])[dc] = sx[dc][1][2 * dp + 1];
+        }
+        if (tile + (int)gridDim.x < ntiles) fetch(tile + (int)gridDim.x);
+        __syncthreads();       // st[par] complete; sx may be refilled (st[par ^ 1] of the previous tile is read before the barrier above)
+        if (active) {
+            const int nvalid = min(GH_PIX, Wo - ow0);
+            const size_t pix0 = ((size_t)b * Ho + oh) * Wo + ow0 + pl;
+            if (conv) gh_role<true>(w, st[par][0], nvalid, pl, npl, t + pix0 * t_ld + g * 8, (size_t)npl * t_ld);
+            else gh_role<false>(w, st[par][1], nvalid, pl, npl, sk + pix0 * sk_ld + g * 8, (size_t)npl * sk_ld);
+        }
     }
 }
 bool ga_head_supported(int H, int W, int N, const Act& t, const Act& sk) {
@@ -322,9 +361,12 @@ bool ga_head_supported(int H, int W, int N, const Act& t, const Act& sk) {
 void launch_ga_head(const float* x, int B, int H, int W, const float* dw9, const float* dwb, const float* w1, const float* b1,
                     const float* wsk, const float* bsk, int N, const Act& t, const Act& sk, cudaStream_t s) {
     const int Ho = H / 2, Wo = W / 2;
-    const long long blocks = (long long)B * Ho * ((Wo + GH_PIX - 1) / GH_PIX);
-    if (blocks == 0) return;
-    ga_head_kernel<<<(unsigned)blocks, GH_THREADS, 0, s>>>(x, H, W, dw9, dwb, w1, b1, wsk, bsk, N, (bf16*)t.p, t.ld, (bf16*)sk.p, sk.ld);
+    const long long tiles = (long long)B * Ho * ((Wo + GH_PIX - 1) / GH_PIX);
+    if (tiles == 0) return;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const long long blocks = std::min<long long>(tiles, (long long)sms * 3);
+    ga_head_kernel<<<(unsigned)blocks, GH_THREADS, 0, s>>>(x, H, W, dw9, dwb, w1, b1, wsk, bsk, N, (bf16*)t.p, t.ld, (bf16*)sk.p, sk.ld, (int)tiles);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -119,4 +119,17 @@ bool ds_pair_supported(const DsPairArgs& a);
 int launch_ds_pair(const DsPairArgs& a, cudaStream_t s);      // 0 ok
 const char* ds_pair_last_error();
 
+// ---- two-SM (cta_group::2) dense 3x3 convolution (conv3_pair.cu), bf16 NHWC, stride 1, pad 1: Cin % 64 == 0, N % 256 == 0
+struct Conv3PairArgs {
+    const void* in; int B, H, W, Cin, ld;   // input view
+    const void* w;                          // bf16 [N][9 * Cin], K-major, tap-major (the packing of TcConv::w; PixelShuffle folded into the column order)
+    const float* bias;                      // [N]
+    int N, act;                             // ACT_NONE | ACT_GELU
+    int shuffle;                            // 1: PixelShuffle(2): out is [B][2H][2W][N / 4], (N / 4) % 64 == 0
+    void* out; int out_ld;
+};
+bool conv3_pair_supported(const Conv3PairArgs& a);
+int launch_conv3_pair(const Conv3PairArgs& a, cudaStream_t s);      // 0 ok
+const char* conv3_pair_last_error();
+
 }  // namespace mlic

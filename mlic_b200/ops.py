@@ -10,7 +10,8 @@ ACT = {None: 0, "none": 0, "gelu": 1, "half_tanh": 2}
 
 def conv2d_nhwc(x, weight, bias=None, stride=1, pad=0, act=None, shuffle=False, residual=None, tensor_cores=True, iters=1):
     """x: CUDA NHWC tensor [B,H,W,Cin], float32 (validation mode) or bfloat16 (fast mode); weight: [N,Cin,ks,ks] (any
-    device, fp32); returns (out NHWC of x.dtype, avg ms of launches 2..iters)."""
+    device, fp32); returns (out NHWC of x.dtype, avg ms of launches 2..iters).  tensor_cores: 0 CUDA cores, 1 tcgen05 one-SM kernel,
+    2 as 1 with the two-SM kernel (conv3_pair.cu) where it applies (3x3, pad 1, Cin % 64 == 0, N % 256 == 0)."""
     assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
     B, H, W, Cin = x.shape
     N, ks = weight.shape[0], weight.shape[2]
@@ -25,7 +26,7 @@ def conv2d_nhwc(x, weight, bias=None, stride=1, pad=0, act=None, shuffle=False, 
     prec = _lib.PREC_BF16 if x.dtype == torch.bfloat16 else _lib.PREC_FP32
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(_lib.lib().mlic_conv2d_nhwc(prec, 1 if tensor_cores else 0, C.c_void_p(x.data_ptr()), B, H, W, Cin,
+        _lib.check(_lib.lib().mlic_conv2d_nhwc(prec, int(tensor_cores), C.c_void_p(x.data_ptr()), B, H, W, Cin,
                                                C.c_void_p(w.data_ptr()), C.c_void_p(b.data_ptr()) if b is not None else None,
                                                N, ks, stride, pad, ACT[act], 1 if shuffle else 0,
                                                C.c_void_p(residual.data_ptr()) if residual is not None else None,

@@ -59,6 +59,29 @@ def test_conv_bf16_tcgen05_kernel(B, H, W, Cin, N, ks, shuffle):
     torch.testing.assert_close(out.float(), simt.float(), atol=2e-2, rtol=1e-2)
 
 
+PAIR_CONV_SHAPES = [  # B, H, W, Cin, N, shuffle, act: ragged edges, an odd tile count (the last pair holds one tile), Cin = 320, no shuffle
+    (1, 16, 24, 192, 768, True, "gelu"), (3, 13, 21, 128, 512, True, None), (1, 20, 37, 64, 256, False, "gelu"),
+    (2, 17, 30, 320, 768, True, "gelu"), (1, 264, 464, 192, 768, True, None), (1, 8, 16, 192, 1024, True, None),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N,shuffle,act", PAIR_CONV_SHAPES)
+def test_conv3x3_two_sm_kernel(B, H, W, Cin, N, shuffle, act):
+    """conv3_pair.cu (tcgen05 cta_group::2, M = 256 over a CTA pair, each CTA staging half of the weight tile): same operands and
+    accumulation as the one-SM kernel, so the two agree to the last bf16 bit up to fp32 summation order; both against torch fp32
+    on the bf16-rounded operands."""
+    torch.manual_seed(5)
+    x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, Cin, 3, 3) / (Cin * 9) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(N) * 0.1
+    out, _ = ops.conv2d_nhwc(x, w, b, 1, 1, act, shuffle, None, tensor_cores=2)
+    one, _ = ops.conv2d_nhwc(x, w, b, 1, 1, act, shuffle, None, tensor_cores=1)
+    ref = _torch_conv(x, w, b, 3, act, shuffle, None)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=1e-2)
+    assert (out.float() - one.float()).abs().max() <= 2.0 ** -6 * max(1.0, float(ref.abs().max()))
+    assert float((out != one).float().mean()) < 0.02
+
+
 def test_gaussian_conditional_kernel_bit_exact_indexes_and_symbols():
     g = torch.Generator().manual_seed(3)
     n = 1 << 18

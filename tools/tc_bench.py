@@ -20,6 +20,9 @@ SHAPES = [  # name, B, H, W, Cin, N, ks, shuffle
     ("hs subpel 480->1920 @34x60", 1, 34, 60, 480, 1920, 3, True),
     ("ragged 100->72 @13x21", 2, 13, 21, 104, 72, 3, False),
     ("pw 320->320 @68x120 b2", 2, 68, 120, 320, 320, 1, False),
+    ("subpel 192->768 @272x480 b4", 4, 272, 480, 192, 768, 3, True),
+    ("ragged3x3 128->512 @13x21 b3", 3, 13, 21, 128, 512, 3, True),
+    ("plain3x3 64->256 @20x37 b1", 1, 20, 37, 64, 256, 3, False),
 ]
 check = "--check" in sys.argv
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
@@ -37,6 +40,10 @@ for name, B, H, W, Cin, N, ks, sh in SHAPES:
     flops = 2.0 * B * H * W * N * Cin * ks * ks
     byts = x.numel() * 2 + out.numel() * 2
     msg = f"{name:32s} {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s  {byts/ms/1e6:8.1f} GB/s(alg)"
+    if ks == 3 and N % 256 == 0 and Cin % 64 == 0 and (not sh or (N // 4) % 64 == 0):
+        outp, msp = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, None, 2, 20)
+        ref1, _ = (out, ms) if res is None else ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, None, 1, 2)
+        msg += f" | two-SM {msp*1e3:9.1f} us {flops/msp/1e9:8.1f} TFLOP/s maxdiff vs one-SM {(outp.float()-ref1.float()).abs().max().item():.3e}"
     if check:
         ref, ms2 = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, res, False, 2)
         d = (out.float() - ref.float()).abs().max().item()
