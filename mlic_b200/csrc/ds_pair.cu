@@ -326,6 +326,9 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
                         const int oy = iy - ky;
+#ifdef MLIC_DP_SKIP_FMA          // development: timing attribution only (wrong results): one tap instead of nine
+                        if (ky != 1) continue;
+#endif
                         if (oy >= 0 && oy < DP_PROD_ROWS) {
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
@@ -429,10 +432,12 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                         v[1] = __fadd2_rn(make_float2(__uint_as_float(raw[sub * 8 + 2]), __uint_as_float(raw[sub * 8 + 3])), make_float2(ba.z, ba.w));
                         v[2] = __fadd2_rn(make_float2(__uint_as_float(raw[sub * 8 + 4]), __uint_as_float(raw[sub * 8 + 5])), make_float2(bb.x, bb.y));
                         v[3] = __fadd2_rn(make_float2(__uint_as_float(raw[sub * 8 + 6]), __uint_as_float(raw[sub * 8 + 7])), make_float2(bb.z, bb.w));
+#ifndef MLIC_DP_SKIP_GELU        // development: timing attribution only (wrong results)
                         if constexpr (ACT == ACT_GELU) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) v[j] = gelu2(v[j]);
                         }
+#endif
                         if constexpr (RES) {
                             const uint4 t = lds128(sb_s + off);
                             v[0] = __fadd2_rn(v[0], bf2_to_f2(t.x)); v[1] = __fadd2_rn(v[1], bf2_to_f2(t.y));

@@ -108,6 +108,7 @@ struct TcMaps {
 };
 
 constexpr int TC_A_BYTES = 128 * 128;       // 128 rows x 64 bf16
+constexpr int TC_SS_PITCH = 116;            // shift-sum: floats per pixel row of the partial-product buffer (464 B: 16-byte stores of 8 consecutive rows hit 8 distinct bank groups)
 constexpr int TC_STG_BYTES = 128 * 128;     // one staged 128-pixel x 64-column bf16 block
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 16;
@@ -608,7 +609,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 const int py = 1 + rest % 14, cr = rest / 14;
                 const int rr = cr & 1, ch = cr >> 1, px = 1 + (j >> 1), sx = j & 1;
                 const int n = (2 * rr + sx) * 3 + ch;
-                const int pofs = ((py - 1) * 8 + (px - 1)) * 109 + n;
+                const int pofs = ((py - 1) * 8 + (px - 1)) * TC_SS_PITCH + n;
                 if (p.store_mode == STORE_SS && idx < 84 * 12)
                     ss_pk[k] = (uint32_t)py | ((uint32_t)px << 4) | ((uint32_t)n << 7) | ((uint32_t)ch << 11) | ((uint32_t)rr << 13) |
                                ((uint32_t)sx << 14) | (1u << 15) | ((uint32_t)pofs << 16);
@@ -718,22 +719,23 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                 // interior pixel p is sum_tap P[p + off(tap)][tap].  Phase 1: TMEM -> shared memory (fp32, odd row pitch);
                 // phase 2: the 14 x 6 interior pixels x 12 outputs are summed over the 9 taps and written as fp32 NCHW with the
                 // pixel shuffle, 12 consecutive floats of one output row per 12 consecutive threads.
-                constexpr int SSP = 109;
-                float* P = reinterpret_cast<float*>(stg);      // one buffer (the operand ring needs the space: two tiles of A in flight)
+                constexpr int SSP = TC_SS_PITCH;
+                const uint32_t Ps = smem_u32(stg);      // one buffer (the operand ring needs the space: two tiles of A in flight)
                 {
-                    float* prow = P + (size_t)r * SSP + cq * 28;
+                    // 28 columns per warp group, as seven 16-byte shared stores (explicit st.shared: the generic stores of the first
+                    // version went through the global-memory queue, "lg throttle" on every one of them; profiles/r02_ncu_final.txt)
+                    const uint32_t prow = Ps + (uint32_t)((r * SSP + cq * 28) * 4);
                     const uint32_t tc0 = trow + (uint32_t)(cq * 28);
                     uint32_t v0[16], v1[8], v2[8];
                     tmem_ld16(tc0, v0);
                     tmem_ld8(tc0 + 16u, v1);
-                    tmem_ld8(tc0 + 20u, v2);          // columns 20..27 (overlaps 20..23 of v1: one ld shape less)
+                    tmem_ld8(tc0 + 20u, v2);          // columns 20..27 (overlaps 20..23 of v1: one ld shape less; columns >= 108 are never read)
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) prow[j] = __uint_as_float(v0[j]);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) prow[16 + j] = __uint_as_float(v1[j]);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) if (cq * 28 + 20 + j < 108) prow[20 + j] = __uint_as_float(v2[j]);
+                    for (int j = 0; j < 4; ++j) sts128(prow + (uint32_t)(j * 16), make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]));
+                    sts128(prow + 64u, make_uint4(v1[0], v1[1], v1[2], v1[3]));
+                    sts128(prow + 80u, make_uint4(v2[0], v2[1], v2[2], v2[3]));
+                    sts128(prow + 96u, make_uint4(v2[4], v2[5], v2[6], v2[7]));
                 }
                 tcgen05_fence_before();
                 __syncwarp();
@@ -747,12 +749,15 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
                         if (ss_pk[k] & (1u << 15)) {
                             const int gh = h0 + (int)(ss_pk[k] & 15u), gw = w0 + (int)((ss_pk[k] >> 4) & 7u);
                             if (gh < e.Hout && gw < e.Wout) {
-                                float acc = sBias[(ss_pk[k] >> 7) & 15u];
-                                const float* pp = P + (ss_pk[k] >> 16);
+                                const uint32_t pp = Ps + (ss_pk[k] >> 16) * 4u;
+                                float t9[9];
 #pragma unroll
                                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                                    for (int kx = 0; kx < 3; ++kx) acc += pp[(ky * 8 + kx) * SSP + (ky * 3 + kx) * 12];
+                                    for (int kx = 0; kx < 3; ++kx) t9[ky * 3 + kx] = __uint_as_float(lds32(pp + (uint32_t)(((ky * 8 + kx) * SSP + (ky * 3 + kx) * 12) * 4)));
+                                float acc = sBias[(ss_pk[k] >> 7) & 15u];
+#pragma unroll
+                                for (int q9 = 0; q9 < 9; ++q9) acc += t9[q9];          // tap order, as the accumulating MMA chain of the plain form
                                 o[(((size_t)img * 3 + ((ss_pk[k] >> 11) & 3u)) * OH + 2 * gh + ((ss_pk[k] >> 13) & 1u)) * OW + 2 * gw + ((ss_pk[k] >> 14) & 1u)] = acc;
                             }
                         }
@@ -1102,7 +1107,7 @@ int launch_conv_gemm_tc(const TcConv& c, const Epi& e, int vec, cudaStream_t s) 
     p.Cin = c.Cin; p.dw_w9 = c.dw_w9; p.dw_bias = c.dw_bias;
     p.raw_bytes = c.prod == PROD_DW ? 128 * (p.TW + 2) * (p.TH + 2) : 0;
     const int extra_bytes = c.prod == PROD_DW ? TC_RAW_SLOTS * p.raw_bytes + 10 * c.Cin * 4
-                                              : (c.ss ? (128 * 109 * 4 + 1023) / 1024 * 1024 : 0);     // shift-sum: the fp32 partial-product buffer
+                                              : (c.ss ? (128 * TC_SS_PITCH * 4 + 1023) / 1024 * 1024 : 0);     // shift-sum: the fp32 partial-product buffer
     const int ksteps = p.ks * p.ks * p.kchunks;
     const int bres_bytes = ksteps * p.BN * 128;
     const int per = (e.out2 || e.gdn) ? 2 : 1;

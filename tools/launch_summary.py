@@ -10,7 +10,7 @@ for row in csv.DictReader(lines):
 L = list(recs.values()); half = len(L) // 2; S = L[half:]
 heads = [i for i, d in enumerate(L) if 'ga_head_kernel' in d['name']]
 if heads:                      # the last forward of the run: from its g_a head kernel on, this repo's kernels only
-    S = [d for d in L[heads[-1]:] if 'mlic::' in d['name']]
+    S = [d for d in L[heads[-1]:] if not d['name'].startswith(('at::', 'void at::'))]
 tot = sum(d['gpu__time_duration.sum'] for d in S)
 print(f"launches in the measured forward: {len(S)}; summed kernel time {tot/1e3:.1f} us")
 agg = collections.defaultdict(lambda: [0, 0.0])
