@@ -180,6 +180,47 @@ struct mlic_engine {
     void* h_io = nullptr; size_t h_io_bytes = 0;
     std::map<std::array<int, 8>, size_t> ws_cache;       // mlic_workspace_bytes results
     cudaStream_t h_stream = nullptr, h_in = nullptr, h_out = nullptr;
+    // Two independent branches of a slice (inter || channel context, intra || local context: mlicpp.py:140-150) run on two streams:
+    // each is a chain of 4-10 launches of 20-500 us that keeps the SMs busy only part of the time (pipeline fill, tails, latency-bound
+    // attention kernels), so the two chains fill each other's gaps.  MLIC_OVERLAP=0 runs them one after the other.
+    std::map<int, cudaStream_t> side_streams;      // per device
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    template <class FA, class FB> void fork2(FA fa, FB fb) {
+        static const int overlap = getenv("MLIC_OVERLAP") ? atoi(getenv("MLIC_OVERLAP")) : 1;
+        // the second branch allocates ABOVE everything the first one touched, in the dry run and the sequential modes too (one
+        // workspace plan whatever the schedule)
+        const size_t base = ws_off, peak_before = ws_peak;
+        const bool two = overlap && go() && !trace && !profile;
+        cudaStream_t s2 = nullptr;
+        if (two) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            auto it = side_streams.find(dev);
+            if (it == side_streams.end()) {
+                cudaStream_t ns = nullptr;
+                if (cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("side stream: %s", cudaGetErrorString(cudaGetLastError())); return; }
+                it = side_streams.emplace(dev, ns).first;
+            }
+            s2 = it->second;
+            if (!ev_fork) { cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming); }
+            cudaEventRecord(ev_fork, st);
+            cudaStreamWaitEvent(s2, ev_fork, 0);
+        }
+        ws_peak = ws_off;
+        fa();
+        const size_t top_a = ws_peak;
+        ws_off = top_a;
+        cudaStream_t keep = st;
+        if (two) st = s2;
+        fb();
+        st = keep;
+        if (two) {
+            cudaEventRecord(ev_join, s2);
+            cudaStreamWaitEvent(st, ev_join, 0);
+        }
+        if (ws_peak < peak_before) ws_peak = peak_before;
+        ws_off = base;
+    }
     std::vector<cudaEvent_t> pipe_ev;
     size_t pipe_used = 0;
     cudaEvent_t pipe_event() {
@@ -197,6 +238,9 @@ struct mlic_engine {
         if (h_in) cudaStreamDestroy(h_in);
         if (h_out) cudaStreamDestroy(h_out);
         for (cudaEvent_t ev : pipe_ev) cudaEventDestroy(ev);
+        for (auto& kv : side_streams) cudaStreamDestroy(kv.second);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
 
     // ------------------------------------------------------------------ parameter access / packing
@@ -1165,8 +1209,7 @@ struct mlic_engine {
             Act ep_n = i ? view(EPW, 0, 10 * C + 2 * Me) : view(EPW, 8 * C, 2 * C + 2 * Me);
             if (i) {
                 Act prev = view(LRPW, Me, i * C);
-                inter_ctx(prev, "global_inter_context." + is, s_inter);
-                channel_ctx(prev, "channel_context." + is, s_chan);
+                fork2([&] { inter_ctx(prev, "global_inter_context." + is, s_inter); }, [&] { channel_ctx(prev, "channel_context." + is, s_chan); });
             }
             const bool esq = ep_squeezed(h, w);
             ep(ep_a, "entropy_parameters_anchor." + is, pa, esq ? PAR_ANCHOR : 0);
@@ -1184,8 +1227,9 @@ struct mlic_engine {
             if (decomp) decode_half(q, true);
             else if (go()) { launch_quant_anchor(bf, q, st); after_launch("quant_anchor"); }
             lrp(lrp_in, "lrp_anchor." + is, slot, PAR_ANCHOR);
-            if (i) intra_ctx(view(LRPW, Me + (i - 1) * C, C), slot, "global_intra_context." + is, s_intra);
-            local_ctx(slot, "local_context." + is, s_local);
+            if (i) fork2([&] { local_ctx(slot, "local_context." + is, s_local); },
+                         [&] { intra_ctx(view(LRPW, Me + (i - 1) * C, C), slot, "global_intra_context." + is, s_intra); });
+            else local_ctx(slot, "local_context." + is, s_local);
             ep(ep_n, "entropy_parameters_nonanchor." + is, pn, esq ? PAR_NONANCHOR : 0);
             if (mode == MLIC_MODE_COMPRESS) { q.sym += half; q.idx += half; }
             if (decomp) decode_half(q, false);

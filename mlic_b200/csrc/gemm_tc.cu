@@ -860,10 +860,17 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
 // through a ring of TMA boxes (zero fill = conv padding and channel tail), so loads of the next items are in flight while
 // the 8 compute warps work, and results go straight to global memory (one full 128-byte line per warp store).
 // ------------------------------------------------------------------------------------------
+// RH = 2 (development switch): 16 compute warps per block, warp = (column pair, half of the tile's rows), 32 compute warps per SM instead
+// of 16.  Measured SLOWER (640 channels at 32 x 68 x 120: 183 -> 224 us; stride 2 at 4 x 544 x 960 x 192: 169 -> 205 us): as in the
+// two-SM fused kernel, more warps do not help -- the kernel is not short of ready warps (tools/dw_bench.py).
+#ifndef MLIC_DW_RH
+#define MLIC_DW_RH 1
+#endif
 template <int S> struct DwT { static constexpr int TH = S == 1 ? 8 : 4, TW = 16, IH = TH * S + 2, IW = TW * S + 2, NX = S == 1 ? 4 : 5,
-                                                   SLOTS = S == 1 ? 4 : 2, BYTES = IH * IW * 128; };
+                                                   RH = MLIC_DW_RH, R = TH / RH, IHW = (R - 1) * S + 3, NCW = 8 * RH, THREADS = (NCW + 1) * 32,
+                                                   SLOTS = S == 1 ? (RH == 2 ? 3 : 4) : 2, BYTES = IH * IW * 128; };
 template <int S>
-__global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, int C, bf16* __restrict__ out, int Ho,
+__global__ void __launch_bounds__(DwT<S>::THREADS, 2) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, int C, bf16* __restrict__ out, int Ho,
                                                             int Wo, int old, const float* __restrict__ w9, const float* __restrict__ bias,
                                                             int act, int tilesW, int tilesH, int chunks, int nitems) {
     using TT = DwT<S>;
@@ -873,13 +880,13 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
     __shared__ int4 item_desc[TT::SLOTS];          // (channel chunk, image, first output row, first output column) of the item in a slot
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TT::SLOTS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+        for (int i = 0; i < TT::SLOTS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], TT::NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     __syncthreads();
     const int tiles_per_img = tilesW * tilesH;
-    if (warp == 8) {
+    if (warp == TT::NCW) {
         if (lane == 0) {
             int n = 0;
             for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
@@ -896,55 +903,50 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
         }
         return;
     }
-    const int pw = warp;
+    const int pw = warp & 7, rh = warp >> 3;
     const size_t row_stride = (size_t)Wo * old;
     int n = 0;
-    // the 9 taps + bias of an item's channel pair come from global memory (L2): those of the NEXT item are requested before the
-    // arithmetic of the current one, so their latency is not paid at the head of every item (the chunk changes item by item)
-    float2 w2[9], b2 = make_float2(0.f, 0.f);
-    auto load_w = [&](int cq, bool live, float2* wv, float2& bv) {
-        const int cn = cq * 64 + 2 * lane;
-        const bool ok = live && cn < C;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) wv[t] = ok ? __ldg(reinterpret_cast<const float2*>(w9 + (size_t)t * C + cn)) : make_float2(0.f, 0.f);
-        bv = ok ? __ldg(reinterpret_cast<const float2*>(bias + cn)) : make_float2(0.f, 0.f);
-    };
     // the chunk index advances by gridDim.x (mod chunks) per item: no division in the item loop; the tile coordinates come from the
     // descriptor the TMA thread left in the slot (the three integer divisions per item and warp were ~15 % of the instructions)
     const int cstep = (int)(gridDim.x % (unsigned)chunks);
     int ccur = (int)(blockIdx.x % (unsigned)chunks);
-    load_w(ccur, (int)blockIdx.x < nitems, w2, b2);
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
         const int slot = n % TT::SLOTS;
         const uint32_t ph = (uint32_t)(n / TT::SLOTS) & 1u;
-        int cnext = ccur + cstep;
-        if (cnext >= chunks) cnext -= chunks;
-        float2 w2n[9], b2n;
-        load_w(cnext, it + (int)gridDim.x < nitems, w2n, b2n);
+        // the 9 taps + bias of the item's channel pair come from global memory (L2), requested before the wait for the patch
+        float2 w2[9], b2;
+        {
+            const int cn = ccur * 64 + 2 * lane;
+            const bool ok = cn < C;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) w2[t] = ok ? __ldg(reinterpret_cast<const float2*>(w9 + (size_t)t * C + cn)) : make_float2(0.f, 0.f);
+            b2 = ok ? __ldg(reinterpret_cast<const float2*>(bias + cn)) : make_float2(0.f, 0.f);
+        }
+        ccur += cstep;
+        if (ccur >= chunks) ccur -= chunks;
         mbar_wait(&full_bar[slot], ph);
         const int4 ds = item_desc[slot];
-        const int cc = ds.x, b = ds.y, oh0 = ds.z, ow0 = ds.w;
-        ccur = cnext;
+        const int cc = ds.x, b = ds.y, oh0 = ds.z + rh * TT::R, ow0 = ds.w;
         const int c = cc * 64 + 2 * lane;
         const bool cok = c < C;
         // output addressing once per item (the per-store 64-bit index arithmetic and bounds tests were a third of this kernel's
         // instructions: profiles/r01_ncu_dwtma.txt): row pointer of the warp's two columns, advanced by one output row per step
         const int ow = ow0 + 2 * pw;
         bf16* orow = out + (((size_t)b * Ho + oh0) * Wo + ow) * old + c;
-        const int nrows = cok ? Ho - oh0 : 0;                                   // rows of this tile inside the image (0: channel tail)
+        const int nrows = cok ? Ho - oh0 : 0;                                   // rows of this warp's share inside the image (<= 0: none / channel tail)
         const bool okq[2] = {ow < Wo, ow + 1 < Wo};
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * TT::BYTES) + (size_t)(2 * pw * S) * 32 + lane;
-        float2 acc[TT::TH][2];
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * TT::BYTES) + (size_t)((rh * TT::R * S) * TT::IW + 2 * pw * S) * 32 + lane;
+        float2 acc[TT::R][2];
 #pragma unroll
-        for (int oy = 0; oy < TT::TH; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
+        for (int oy = 0; oy < TT::R; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
 #pragma unroll
-        for (int iy = 0; iy < TT::IH; ++iy) {
+        for (int iy = 0; iy < TT::IHW; ++iy) {
             float2 x[TT::NX];
 #pragma unroll
             for (int j = 0; j < TT::NX; ++j) x[j] = bf2_to_f2(rp[(size_t)(iy * TT::IW + j) * 32]);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-                if ((iy - ky) >= 0 && ((iy - ky) % S) == 0 && (iy - ky) / S < TT::TH) {
+                if ((iy - ky) >= 0 && ((iy - ky) % S) == 0 && (iy - ky) / S < TT::R) {
                     const int oy = (iy - ky) / S;
 #pragma unroll
                     for (int q = 0; q < 2; ++q)
@@ -968,9 +970,6 @@ __global__ void __launch_bounds__(288) dwconv3x3_tma_kernel(const __grid_constan
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[slot]);
-#pragma unroll
-        for (int t = 0; t < 9; ++t) w2[t] = w2n[t];
-        b2 = b2n;
     }
 }
 
@@ -994,7 +993,7 @@ static int launch_dw_tma(const Act& in, const Act& out, const float* w9, const f
     if (!attr[dev]) { cudaFuncSetAttribute(dwconv3x3_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[dev] = true; }
     const int num_sms = dev_sms(dev);
     const int grid = (int)std::min<long long>(nitems, 2LL * num_sms);
-    dwconv3x3_tma_kernel<S><<<grid, 288, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
+    dwconv3x3_tma_kernel<S><<<grid, TT::THREADS, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
     return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 // bf16 NHWC depthwise 3x3 through the TMA-fed kernel; non-zero: not taken (the caller falls back to the staged kernel)
