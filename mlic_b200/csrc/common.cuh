@@ -77,6 +77,19 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
     return __fmul2_rn(x, make_float2(r0, r1));
 #endif
 }
+// GELU(2 h) from h = x / 2 (tanh form only): with the 1/2 folded into the producer's operands (exact: a power of two) the epilogue saves
+// the multiply by 0.5 -- one of its 6 FP32x2 instructions per value pair, and the FP32x2 pipe (1.3-1.7 instructions per clock and SM,
+// tools/ubench/pipes.cu) is what paces the fused DepthWiseConv kernels.  Bit-identical to gelu2(2 h): every rescaled quantity differs
+// from the original by a power of two (s = t / 4, q' = 2 q with coefficients 32 c2, 8 c1, 2 c0, u = h q' = x q).
+__device__ __forceinline__ float2 gelu2_half(float2 h) {
+    float2 s = __fmul2_rn(h, h);
+    s.x = fminf(s.x, 16.0f); s.y = fminf(s.y, 16.0f);
+    float2 q = __ffma2_rn(s, make_float2(32.0f * -3.51516790e-04f, 32.0f * -3.51516790e-04f), make_float2(8.0f * 3.70056460e-02f, 8.0f * 3.70056460e-02f));
+    q = __ffma2_rn(q, s, make_float2(2.0f * 7.97507884e-01f, 2.0f * 7.97507884e-01f));
+    const float2 u = __fmul2_rn(h, q);
+    const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+    return __ffma2_rn(h, th, h);
+}
 __device__ __forceinline__ float gelu_fast(float x) { return gelu2(make_float2(x, x)).x; }
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 

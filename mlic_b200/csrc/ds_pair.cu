@@ -152,11 +152,15 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
     float* sB1 = reinterpret_cast<float*>(base + Cfg::OFF_B1);
     float* sB2 = reinterpret_cast<float*>(base + Cfg::OFF_B2);
 
+    // GELU layers: the accumulator is made to hold HALF the pre-activation (depthwise taps, depthwise bias and pointwise bias scaled by
+    // 1/2 -- exact), which gelu2_half() turns into the same bits as gelu2() of the full value with one FP32x2 multiply less
+    constexpr bool HALF = (MODE == DP_DS && ACT == ACT_GELU && MLIC_GELU_FORM == 0);
+    constexpr float PS = HALF ? 0.5f : 1.0f;
     for (int i = threadIdx.x; i < 10 * C; i += Cfg::THREADS) {
         const int k = i / 640, rem = i - k * 640, tap = rem >> 6, ch = rem & 63;
-        sDw[i] = tap < 9 ? p.dw_w9[tap * C + k * 64 + ch] : p.dw_bias[k * 64 + ch];
+        sDw[i] = PS * (tap < 9 ? p.dw_w9[tap * C + k * 64 + ch] : p.dw_bias[k * 64 + ch]);
     }
-    for (int i = threadIdx.x; i < C; i += Cfg::THREADS) { sB1[i] = p.b1[i]; sB2[i] = (MODE == DP_TAIL) ? p.b2[i] : 0.f; }
+    for (int i = threadIdx.x; i < C; i += Cfg::THREADS) { sB1[i] = PS * p.b1[i]; sB2[i] = (MODE == DP_TAIL) ? p.b2[i] : 0.f; }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.raw) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.w1) : "memory");
@@ -435,7 +439,7 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
 #ifndef MLIC_DP_SKIP_GELU        // development: timing attribution only (wrong results)
                         if constexpr (ACT == ACT_GELU) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) v[j] = gelu2(v[j]);
+                            for (int j = 0; j < 4; ++j) v[j] = HALF ? gelu2_half(v[j]) : gelu2(v[j]);
                         }
 #endif
                         if constexpr (RES) {
