@@ -104,6 +104,7 @@ struct mlic_engine {
     int stages = 7;          // bit 0: g_a, bit 1: h_a + EntropyBottleneck + h_s + slice loop, bit 2: g_s (row-band sharding runs them apart)
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
     int pair = 1;            // fuse: DepthWiseConv / (I)GDN-tail blocks with C = N = 192 | 128 on the two-SM kernel (ds_pair.cu)
+    int halo5 = 1;           // 5x5 convs with N <= 128 on the halo-patch kernel (conv_halo.cu)
 
     std::vector<void*> dev_allocs;
     std::unordered_map<std::string, ConvW> convs;
@@ -598,6 +599,33 @@ struct mlic_engine {
             if (prod && !sup) return false;
             if (o.ck && !sup) { if (!rc) rc = fail("gemm '%s': checkerboard rows not supported for this layer", key.c_str()); return true; }
             if (!go()) return true;
+            // 5x5 convs with a narrow output (the re-projections of the global contexts): activations staged once per tile as a halo patch,
+            // only the weights stream (conv_halo.cu)
+            if (sup && halo5 && !prod && !o.ck && w->ks == 5 && stride == 1 && pad == 2 && !e.res && !e.gdn && !e.out2 && !e.out_f32 && !e.nchw &&
+                !e.premask && !e.postmask && e.act == ACT_NONE && !w->shuffle) {
+                ConvHaloArgs a;
+                memset(&a, 0, sizeof a);
+                a.in = in.p; a.B = in.B; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ld = in.ld;
+                a.w = w->wbf; a.Cpad = w->Cpad; a.bias = w->bias; a.N = w->N; a.ks = 5; a.out = e.out; a.out_ld = e.out_ld;
+                if (conv_halo_supported(a)) {
+                    cudaEvent_t ev1 = nullptr;
+                    if (profile) {
+                        cudaEventRecord(next_event(), st);
+                        ev1 = next_event();
+                        ev_flops.push_back(2.0 * (double)in.B * e.Hout * e.Wout * (double)w->N * (double)(25 * w->Cin));
+                    }
+                    int r = launch_conv_halo(a, st);
+                    if (ev1) cudaEventRecord(ev1, st);
+                    if (r) { if (!rc) rc = fail("halo conv '%s': %s", key.c_str(), conv_halo_last_error()); return true; }
+                    ++launches;
+                    if (trace) {
+                        char lab[256];
+                        snprintf(lab, sizeof lab, "%s [halo conv5 M=%d N=%d K=25x%d]", key.c_str(), in.B * e.Hout * e.Wout, w->N, w->Cin);
+                        tr(lab);
+                    }
+                    return true;
+                }
+            }
             // wide dense 3x3 convs (the sub-pixel convs of g_s): two-SM kernel, each CTA stages half of the weight tile (conv3_pair.cu)
             if (sup && pair && !prod && !o.ck && w->ks == 3 && stride == 1 && pad == 1 && !e.res && !e.gdn && !e.out2 && !e.out_f32 && !e.nchw &&
                 !e.premask && !e.postmask && w->Cpad == w->Cin) {
@@ -1482,7 +1510,7 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
     e.rc = 0;
     e.pack_conv_raw("w", weight, bias, N, Cin, ks, shuffle);
     if (e.rc) return e.rc;
-    e.bf = precision == MLIC_PREC_BF16; e.use_tc = tensor_cores != 0; e.pair = tensor_cores == 2; e.dry = false; e.st = (cudaStream_t)cuda_stream;      // 2: the two-SM kernels where they apply
+    e.bf = precision == MLIC_PREC_BF16; e.use_tc = tensor_cores != 0; e.pair = tensor_cores == 2; e.halo5 = tensor_cores == 2; e.dry = false; e.st = (cudaStream_t)cuda_stream;      // 2: the two-SM kernels where they apply
     if (e.bf && e.use_tc && tc_init()) return fail("%s", tc_last_error());
     Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin;
     const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;

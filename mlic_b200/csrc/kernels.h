@@ -132,4 +132,16 @@ bool conv3_pair_supported(const Conv3PairArgs& a);
 int launch_conv3_pair(const Conv3PairArgs& a, cudaStream_t s);      // 0 ok
 const char* conv3_pair_last_error();
 
+// ---- halo-patch k x k convolution with a narrow output (conv_halo.cu), bf16 NHWC, stride 1, pad k / 2, k = 3 | 5, N <= 128
+struct ConvHaloArgs {
+    const void* in; int B, H, W, Cin, ld;   // input view
+    const void* w; int Cpad;                // bf16 [N][ks * ks * Cpad] (the packing of TcConv::w)
+    const float* bias;                      // [N] or null
+    int N, ks;
+    void* out; int out_ld;
+};
+bool conv_halo_supported(const ConvHaloArgs& a);
+int launch_conv_halo(const ConvHaloArgs& a, cudaStream_t s);        // 0 ok
+const char* conv_halo_last_error();
+
 }  // namespace mlic

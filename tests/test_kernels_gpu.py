@@ -82,6 +82,21 @@ def test_conv3x3_two_sm_kernel(B, H, W, Cin, N, shuffle, act):
     assert float((out != one).float().mean()) < 0.02
 
 
+@pytest.mark.parametrize("B,H,W,Cin,N", [(1, 68, 120, 288, 96), (3, 13, 21, 96, 96), (2, 17, 30, 32, 64), (1, 9, 40, 160, 96)])
+def test_conv5x5_column_shifted_patch_kernel(B, H, W, Cin, N):
+    """conv_halo.cu (the 5x5 re-projections of the global contexts: activations staged once per (chunk, kx), the row taps are aligned UMMA
+    descriptors into the patch): against torch fp32 on the bf16-rounded operands and against the plain implicit-GEMM kernel."""
+    torch.manual_seed(6)
+    x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, Cin, 5, 5) / (Cin * 25) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(N) * 0.1
+    out, _ = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, tensor_cores=2)
+    one, _ = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, tensor_cores=1)
+    ref = _torch_conv(x, w, b, 5, None, False, None)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=1e-2)
+    assert (out.float() - one.float()).abs().max() <= 2.0 ** -6 * max(1.0, float(ref.abs().max()))
+
+
 def test_gaussian_conditional_kernel_bit_exact_indexes_and_symbols():
     g = torch.Generator().manual_seed(3)
     n = 1 << 18

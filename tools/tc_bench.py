@@ -23,6 +23,10 @@ SHAPES = [  # name, B, H, W, Cin, N, ks, shuffle
     ("subpel 192->768 @272x480 b4", 4, 272, 480, 192, 768, 3, True),
     ("ragged3x3 128->512 @13x21 b3", 3, 13, 21, 128, 512, 3, True),
     ("plain3x3 64->256 @20x37 b1", 1, 20, 37, 64, 256, 3, False),
+    ("reproj5x5 288->96 @68x120 b32", 32, 68, 120, 288, 96, 5, False),
+    ("reproj5x5 160->96 @68x120 b32", 32, 68, 120, 160, 96, 5, False),
+    ("reproj5x5 32->64 @68x120 b32", 32, 68, 120, 32, 64, 5, False),
+    ("reproj5x5 96->96 ragged @13x21 b3", 3, 13, 21, 96, 96, 5, False),
 ]
 check = "--check" in sys.argv
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
@@ -44,6 +48,13 @@ for name, B, H, W, Cin, N, ks, sh in SHAPES:
         outp, msp = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, None, 2, 20)
         ref1, _ = (out, ms) if res is None else ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, None, 1, 2)
         msg += f" | two-SM {msp*1e3:9.1f} us {flops/msp/1e9:8.1f} TFLOP/s maxdiff vs one-SM {(outp.float()-ref1.float()).abs().max().item():.3e}"
+    if ks == 5 and N <= 128:
+        outp, msp = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, 2, 20)
+        ref1, ms1 = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, 1, 20)
+        msg += f" | halo-patch {msp*1e3:9.1f} us vs plain {ms1*1e3:9.1f} us (no act / res) maxdiff {(outp.float()-ref1.float()).abs().max().item():.3e}"
+        if check:
+            y = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().cuda(), b.cuda(), padding=2).permute(0, 2, 3, 1)
+            msg += f" vs torch {(outp.float()-y).abs().max().item():.3e}"
     if check:
         ref, ms2 = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, res, False, 2)
         d = (out.float() - ref.float()).abs().max().item()
