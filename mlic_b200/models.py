@@ -229,6 +229,10 @@ class MLICPlusPlus(nn.Module):
 
     def _run_staged(self, mode, x, B, H, W, gain, want):
         """A full call with per-stage precisions: consecutive stages of equal precision share one engine call."""
+        if H % 64 or W % 64:
+            raise ValueError("H and W must be multiples of 64 (the reference pads, utils/testing.py:130-137)")
+        if not torch.cuda.is_available():
+            raise _lib.MlicError("mlic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         pa, pe, ps = self.precision
         dev = x.device if (x is not None and x.is_cuda) else torch.device("cuda", torch.cuda.current_device())
         host = x is not None and not x.is_cuda

@@ -110,3 +110,17 @@ def test_shard_range():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_set_precision_accepts_per_stage_tuples():
+    """set_precision: "bf16" | "fp32" | "mixed" | (g_a, entropy model, g_s); a uniform tuple collapses to its value; nothing runs on CPU."""
+    net = mlic_b200.get_model("MLICPP_S")
+    assert net.set_precision("mixed").precision == ("fp32", "fp32", "bf16")
+    assert net.set_precision(("bf16", "fp32", "bf16")).precision == ("bf16", "fp32", "bf16")
+    assert net.set_precision(["fp32", "fp32", "fp32"]).precision == "fp32"
+    for bad in ("fp16", ("fp32", "bf16"), ("fp32", "bf16", "tf32"), 3):
+        with pytest.raises((ValueError, TypeError)):
+            net.set_precision(bad)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.MlicError):                  # the staged call has no CPU fallback either
+            net.set_precision("mixed")(torch.zeros(1, 3, 64, 64))
