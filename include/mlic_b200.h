@@ -162,6 +162,15 @@ int mlic_final_subpel(int impl, const void* in, int B, int H, int W, int Cin, co
 int mlic_local_attn(int impl, const void* F, int B, int H, int W, const float* rel_bias, void* O, int iters, float* avg_ms,
                     void* cuda_stream);
 
+/* Stand-alone kernelised ("linear") global attention of LinearGlobalInterContext / LinearGlobalIntraContext
+ * (modules/transform/context.py:169-193,226-245): qkv is a DEVICE NHWC tensor [B,H,W,3*D] (fp32 or bf16 per `precision`) whose
+ * channels are Q | K | V (D each, `heads` heads of `hd` = D / heads channels, hd = 32 | 16); per head K is soft-maxed over the
+ * positions, Q over the head's channels, out[p] = (K^ V^T)^T Q^[p] -> DEVICE NHWC [B,H,W,D] of the same element type.
+ * par_kv / par_q: 0 none, 1 anchor, 2 non-anchor pixels only (the intra context: keys / values on anchors, queries on
+ * non-anchors; filtered-out positions give zeros).  Timing as mlic_conv2d_nhwc.  Kernel-level test / micro-benchmark hook. */
+int mlic_lin_attn(int precision, const void* qkv, int B, int H, int W, int D, int heads, int par_kv, int par_q, void* out, int iters,
+                  float* avg_ms, void* cuda_stream);
+
 /* Stand-alone g_a stage-0 head of the bf16 path (ResidualBlockWithStride(3 -> N, stride 2), modules/layers/res_blk.py:82-93
  * with DepthWiseConv, conv.py:46-63): x DEVICE fp32 NCHW [B,3,H,W] ->
  *   t_out    = GELU(point_conv(depth_conv_s2(x)))   DEVICE bf16 NHWC [B,H/2,W/2,N]

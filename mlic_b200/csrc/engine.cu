@@ -1714,6 +1714,35 @@ int mlic_local_attn(int impl, const void* F, int B, int H, int W, const float* r
     return 0;
 }
 
+int mlic_lin_attn(int precision, const void* qkv, int B, int H, int W, int D, int heads, int par_kv, int par_q, void* out, int iters,
+                  float* avg_ms, void* cuda_stream) {
+    if (!qkv || !out || iters < 1 || heads < 1 || D % heads || B < 1 || H < 1 || W < 1) return fail("bad arguments");
+    const int hd = D / heads, bf = precision == MLIC_PREC_BF16;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    float* scratch = nullptr;
+    CUDA_OK(cudaMalloc((void**)&scratch, lin_attn_scratch_floats(B, heads, hd, H * W) * sizeof(float)));
+    Act q; q.p = const_cast<void*>(qkv); q.B = B; q.H = H; q.W = W; q.C = 3 * D; q.ld = 3 * D;
+    Act o; o.p = out; o.B = B; o.H = H; o.W = W; o.C = D; o.ld = D;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    int r = 0;
+    for (int i = 0; i < iters && !r; ++i) {
+        if (i == 1) CUDA_OK(cudaEventRecord(e0, st));
+        r = launch_lin_attn(bf, q, D, heads, hd, par_kv, par_q, scratch, o, st);
+    }
+    if (iters == 1) CUDA_OK(cudaEventRecord(e0, st));
+    CUDA_OK(cudaEventRecord(e1, st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(scratch);
+    if (r) return fail("linear attention: unsupported head dim %d", hd);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mlic_ga_head(const float* x, int B, int H, int W, const float* dw_weight, const float* dw_bias, const float* pw_weight,
                  const float* pw_bias, const float* skip_weight, const float* skip_bias, int N, void* t_out, void* skip_out,
                  int iters, float* avg_ms, void* cuda_stream) {

@@ -1490,6 +1490,84 @@ __global__ void __launch_bounds__(128) lin_out_kernel(const T* __restrict__ qkv,
     for (int d = 0; d < HD; d += 4) store4(op + d, o + d);
 }
 
+// bf16 fast mode, head dim 32, no parity filter (the inter context): O[p][:] = softmax_c(Q[p][:]) ctx on the warp-level tensor path.
+// The scalar kernel above spends 32 x 32 FMAs and 256 shared loads per pixel-head (265 us at 288 channels, 32 images; the traffic
+// floor is ~50 us).  Here a warp takes 16 pixels per step: lane (g, t) loads the 16 bytes of channels 8t .. 8t+7 of rows g and g + 8
+// (whole 64-byte rows per quad), the softmax over the 32 channels of a row is a quad reduction, and the un-normalised exponentials
+// (rounded to bf16; the normaliser sums the SAME rounded values, as lin_ctx_mma_kernel does) are the A fragments of mma.m16n8k16
+// as they lie -- the k index of both operands is permuted so that fragment slot (t, j) is channel 8t + 4 kb + j; the context
+// matrix is loaded once per warp into B fragments with the same permutation.  Results leave through a per-warp staging tile so that
+// every lane stores 16 contiguous bytes.
+constexpr int LO_TILES = 8;                      // 16-pixel tiles per warp
+__global__ void __launch_bounds__(128) lin_out_mma32_kernel(const bf16* __restrict__ qkv, int ld, int HW, const float* __restrict__ ctx,
+                                                            bf16* __restrict__ out, int old) {
+    __shared__ float sC[32][33];
+    __shared__ __align__(16) uint8_t sO[4][16 * 80];
+    const int g_head = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
+    const float* cp = ctx + ((size_t)b * heads + g_head) * 1024;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sC[i >> 5][i & 31] = cp[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    // B fragments: n = nt * 8 + g; k rows 2t, 2t+1 -> channels 8t + 4kb + {0, 1}; k rows 2t+8, 2t+9 -> channels 8t + 4kb + {2, 3}
+    uint32_t bfr[4][2][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+            const int n = nt * 8 + g, c = 8 * t + 4 * kb;
+            bfr[nt][kb][0] = pack_bf2(sC[c][n], sC[c + 1][n]);
+            bfr[nt][kb][1] = pack_bf2(sC[c + 2][n], sC[c + 3][n]);
+        }
+    uint8_t* myO = sO[warp];
+    const int p_base = (blockIdx.x * 4 + warp) * (16 * LO_TILES);
+#pragma unroll 1
+    for (int tl = 0; tl < LO_TILES; ++tl) {
+        const int p0 = p_base + tl * 16;
+        if (p0 >= HW) break;                                     // warp-uniform
+        float inv[2];
+        uint32_t a[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = p0 + g + 8 * h;
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (p < HW) raw = *reinterpret_cast<const uint4*>(qkv + ((size_t)b * HW + p) * ld + g_head * 32 + 8 * t);
+            float v[8];
+            unpack8_bf16_k(raw, v);
+            float mx = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            uint32_t e2[4];
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                e2[j] = pack_bf2(__expf(v[2 * j] - mx), __expf(v[2 * j + 1] - mx));
+                den += __uint_as_float(e2[j] << 16) + __uint_as_float(e2[j] & 0xffff0000u);
+            }
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            inv[h] = 1.0f / den;
+            a[0][h] = e2[0]; a[0][2 + h] = e2[1];                // kb 0: slots (2t, 2t+1) and (2t+8, 2t+9) of row g + 8h
+            a[1][h] = e2[2]; a[1][2 + h] = e2[3];
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(acc, a[0], bfr[nt][0][0], bfr[nt][0][1]);
+            mma_bf16_16816(acc, a[1], bfr[nt][1][0], bfr[nt][1][1]);
+            *reinterpret_cast<uint32_t*>(myO + g * 80 + nt * 16 + 4 * t) = pack_bf2(acc[0] * inv[0], acc[1] * inv[0]);
+            *reinterpret_cast<uint32_t*>(myO + (g + 8) * 80 + nt * 16 + 4 * t) = pack_bf2(acc[2] * inv[1], acc[3] * inv[1]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = (lane >> 2) + 8 * h, p = p0 + row;
+            if (p < HW) *reinterpret_cast<uint4*>(out + ((size_t)b * HW + p) * old + g_head * 32 + 8 * t) = *reinterpret_cast<const uint4*>(myO + row * 80 + 16 * t);
+        }
+        __syncwarp();
+    }
+}
+
 int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv, int par_q, float* scratch,
                     const Act& out, cudaStream_t s) {
     const int B = qkv.B, H = qkv.H, W = qkv.W, HW = H * W;
@@ -1507,6 +1585,10 @@ int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv
         lin_ctx_kernel<T, HD><<<dim3(nch, heads, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv,   \
                                                                   pmax, pctx);                                     \
         lin_ctx_reduce_kernel<HD><<<dim3(heads, B, 4), 256, 0, s>>>(pctx, nch, ctx);                                  \
+        if (sizeof(T) == 2 && HD == 32 && par_q == PAR_NONE && (qkv.ld % 8) == 0 && (out.ld % 8) == 0 && (((uintptr_t)qkv.p) % 16) == 0 &&      \
+            (((uintptr_t)out.p) % 16) == 0 && !getenv("MLIC_LIN_SIMT"))                                                                      \
+            lin_out_mma32_kernel<<<dim3(cdiv(HW, 4 * 16 * LO_TILES), heads, B), 128, 0, s>>>((const bf16*)qkv.p, qkv.ld, HW, ctx, (bf16*)out.p, out.ld); \
+        else                                                                                                       \
         lin_out_kernel<T, HD><<<dim3(cdiv(HW, 128), heads, B), 128, 0, s>>>((const T*)qkv.p, qkv.ld, H, W, par_q,  \
                                                                             ctx, (T*)out.p, out.ld);               \
     } while (0)

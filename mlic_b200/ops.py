@@ -134,6 +134,23 @@ def local_attn(F, rel_bias, impl=2, iters=1):
     return O, float(ms.value)
 
 
+def lin_attn(qkv, heads, par_kv=0, par_q=0, iters=1):
+    """Kernelised global attention (context.py:169-193,226-245) on a CUDA NHWC tensor [B,H,W,3D] (Q | K | V; fp32 or bf16):
+    K soft-maxed over positions, Q over the head's channels -> (out [B,H,W,D] of the same dtype, avg ms).  par: 0 none, 1 anchor,
+    2 non-anchor positions only."""
+    assert qkv.is_cuda and qkv.is_contiguous() and qkv.dtype in (torch.float32, torch.bfloat16) and qkv.shape[-1] % 3 == 0
+    B, H, W, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty((B, H, W, D), dtype=qkv.dtype, device=qkv.device)
+    ms = C.c_float(0)
+    prec = _lib.PREC_BF16 if qkv.dtype == torch.bfloat16 else _lib.PREC_FP32
+    with torch.cuda.device(qkv.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_lin_attn(prec, C.c_void_p(qkv.data_ptr()), B, H, W, D, heads, par_kv, par_q,
+                                            C.c_void_p(out.data_ptr()), iters, C.byref(ms), C.c_void_p(st)))
+    return out, float(ms.value)
+
+
 def ga_head(x, dw_weight, dw_bias, pw_weight, pw_bias, skip_weight, skip_bias, iters=1):
     """g_a stage-0 head of the bf16 path: x CUDA fp32 NCHW [B,3,H,W] -> (GELU(pw(dw_s2 x)), skip_s2(x)) bf16 NHWC, avg ms."""
     assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32 and x.shape[1] == 3

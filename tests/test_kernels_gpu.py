@@ -97,6 +97,42 @@ def test_conv5x5_column_shifted_patch_kernel(B, H, W, Cin, N):
     assert (out.float() - one.float()).abs().max() <= 2.0 ** -6 * max(1.0, float(ref.abs().max()))
 
 
+def _lin_attn_torch(qkv, heads, par_kv=0, par_q=0):
+    """context.py:169-193,226-245 on an NHWC [B,H,W,3D] tensor: per head softmax of K over positions, of Q over channels."""
+    B, H, W, D3 = qkv.shape
+    D = D3 // 3
+    hd = D // heads
+    q, k, v = (t.reshape(B, H * W, heads, hd).double() for t in qkv.float().split(D, dim=-1))
+    hh, ww = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    anchor = (((hh + ww) % 2) == 1).reshape(-1).to(qkv.device)
+
+    def keep(par):
+        return torch.ones_like(anchor) if par == 0 else (anchor if par == 1 else ~anchor)
+    kk, kq = keep(par_kv), keep(par_q)
+    k = k.masked_fill(~kk[None, :, None, None], float("-inf"))
+    kh = torch.softmax(k, dim=1)
+    qh = torch.softmax(q, dim=-1)
+    ctx = torch.einsum("bphc,bphd->bhcd", kh, v * kk[None, :, None, None])
+    o = torch.einsum("bhcd,bphc->bphd", ctx, qh) * kq[None, :, None, None]
+    return o.reshape(B, H, W, D).float()
+
+
+@pytest.mark.parametrize("B,H,W,D,heads,par_kv,par_q", [(2, 17, 30, 96, 3, 0, 0), (1, 68, 120, 288, 9, 0, 0), (2, 16, 24, 32, 2, 1, 2), (1, 13, 21, 32, 1, 0, 0)])
+def test_linear_attention_kernels(B, H, W, D, heads, par_kv, par_q):
+    """LinearGlobalInterContext / LinearGlobalIntraContext attention: the fp32 kernels against a float64 torch
+    statement, the bf16 kernels (mma.sync context matrix and, for head dim 32 without parity, the mma.sync output kernel) against the
+    same statement on the bf16-rounded input."""
+    torch.manual_seed(7)
+    qkv = torch.randn(B, H, W, 3 * D, device="cuda")
+    ref = _lin_attn_torch(qkv, heads, par_kv, par_q)
+    out, _ = ops.lin_attn(qkv, heads, par_kv, par_q)
+    torch.testing.assert_close(out, ref, atol=2e-5, rtol=1e-4)
+    qb = qkv.to(torch.bfloat16)
+    refb = _lin_attn_torch(qb, heads, par_kv, par_q)
+    outb, _ = ops.lin_attn(qb, heads, par_kv, par_q)
+    torch.testing.assert_close(outb.float(), refb, atol=3e-3 * float(refb.abs().max()) + 1e-4, rtol=2e-2)
+
+
 def test_gaussian_conditional_kernel_bit_exact_indexes_and_symbols():
     g = torch.Generator().manual_seed(3)
     n = 1 << 18
