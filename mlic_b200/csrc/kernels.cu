@@ -990,6 +990,7 @@ __device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+constexpr float LM_LOG2E = 1.4426950408889634f;
 __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __restrict__ F, int f_ld, int H, int W,
                                                              const float* __restrict__ rel_bias, bf16* __restrict__ O) {
     extern __shared__ __align__(16) uint8_t lm_smem[];
@@ -1010,7 +1011,7 @@ __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __re
     if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(sZero)[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) {
         const int col = i & 31, row = (i >> 5) & 31, hh = i >> 10;
-        sB[i] = (col < 25) ? ((row < 25) ? rel_bias[(hh * 25 + row) * 25 + col] : 0.0f) : -30000.0f;
+        sB[i] = (col < 25) ? ((row < 25) ? LM_LOG2E * rel_bias[(hh * 25 + row) * 25 + col] : 0.0f) : -30000.0f;      // log2 domain (exp2 below)
     }
     __syncthreads();
     const uint32_t sF_s = (uint32_t)__cvta_generic_to_shared(sF), sZ_s = (uint32_t)__cvta_generic_to_shared(sZero);
@@ -1028,6 +1029,11 @@ __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __re
             anch = qh >= 0 && qh < H && qw >= 0 && qw < W && (((qh + qw) & 1) == 1);
         }
         const uint32_t am = __ballot_sync(0xffffffffu, anch);
+        float cmask[4][2];                  // mask of this lane's 8 key columns when the query tap is an anchor: 0 | -100 (x log2 e)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) cmask[nt][e] = ((am >> (nt * 8 + 2 * (lane & 3) + e)) & 1u) ? 0.0f : -100.0f * LM_LOG2E;
         // per-lane ldmatrix row addresses (tap -> staged position), shared by both heads
         auto tap_addr = [&](int tap) -> uint32_t {
             return tap < 25 ? sF_s + (uint32_t)(((ph + tap / 5) * LM_HW + (pw + tap % 5)) * LM_PITCH) : 0u;
@@ -1063,8 +1069,12 @@ __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __re
                     for (int j = 0; j < 4; ++j) sc[mt][nt][j] = 0.f;
                     mma_bf16_16816(sc[mt][nt], qf[mt], kf[nt >> 1][(nt & 1) * 2], kf[nt >> 1][(nt & 1) * 2 + 1]);
                 }
-            // scale, + bias, + mask; row softmax (a row lives in the 4 lanes of a quad)
+            // scale, + bias, + mask; row softmax (a row lives in the 4 lanes of a quad).  Everything in the log2 domain (scale and bias
+            // pre-multiplied by log2 e: exp2 is one MUFU after one subtraction), the column part of the mask is 8 floats per lane and
+            // pixel (cmask, shared by both heads), and P stays un-normalised -- 1 / sum is applied to the 16 x 16 output instead of
+            // the 32 x 32 probabilities.
             const float* bh = sB + hh * 1024;
+            float inv_row[2][2];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -1076,8 +1086,8 @@ __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __re
                     for (int nt = 0; nt < 4; ++nt) {
                         const int col = nt * 8 + 2 * t;
                         const float2 bb = *reinterpret_cast<const float2*>(bh + row * 32 + col);
-                        float s0 = fmaf(sc[mt][nt][half * 2], 0.25f, bb.x) + ((qan && ((am >> col) & 1u)) ? 0.0f : -100.0f);
-                        float s1 = fmaf(sc[mt][nt][half * 2 + 1], 0.25f, bb.y) + ((qan && ((am >> (col + 1)) & 1u)) ? 0.0f : -100.0f);
+                        const float s0 = fmaf(sc[mt][nt][half * 2], 0.25f * LM_LOG2E, bb.x) + (qan ? cmask[nt][0] : -100.0f * LM_LOG2E);
+                        const float s1 = fmaf(sc[mt][nt][half * 2 + 1], 0.25f * LM_LOG2E, bb.y) + (qan ? cmask[nt][1] : -100.0f * LM_LOG2E);
                         sc[mt][nt][half * 2] = s0; sc[mt][nt][half * 2 + 1] = s1;
                         mx = fmaxf(mx, fmaxf(s0, s1));
                     }
@@ -1086,15 +1096,15 @@ __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __re
                     float den = 0.f;
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
-                        const float e0 = __expf(sc[mt][nt][half * 2] - mx), e1 = __expf(sc[mt][nt][half * 2 + 1] - mx);
+                        float e0, e1;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(sc[mt][nt][half * 2] - mx));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(sc[mt][nt][half * 2 + 1] - mx));
                         sc[mt][nt][half * 2] = e0; sc[mt][nt][half * 2 + 1] = e1;
                         den += e0 + e1;
                     }
                     den += __shfl_xor_sync(0xffffffffu, den, 1);
                     den += __shfl_xor_sync(0xffffffffu, den, 2);
-                    const float inv = 1.0f / den;
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) { sc[mt][nt][half * 2] *= inv; sc[mt][nt][half * 2 + 1] *= inv; }
+                    inv_row[mt][half] = 1.0f / den;
                 }
             // O = P V: k blocks of 16 key taps; P accumulators re-packed as bf16 A fragments
             uint32_t vf[2][4];
@@ -1116,6 +1126,8 @@ __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __re
                         pf[3] = pack_bf2(sc[mt][2 * kb + 1][2], sc[mt][2 * kb + 1][3]);
                         mma_bf16_16816(oc[mt][dn], pf, vf[kb][dn * 2], vf[kb][dn * 2 + 1]);
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) oc[mt][dn][j] *= inv_row[mt][j >> 1];
                 }
             // rows a < 25 -> staged [25][C] block, channel = hh*16 + d  (context.py:106-107)
 #pragma unroll
