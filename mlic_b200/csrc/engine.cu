@@ -1098,6 +1098,22 @@ struct mlic_engine {
         if (forced > 0) return std::min(forced, B);
         return B >= 16 ? 4 : (B >= 8 ? 2 : 1);
     }
+    // Image groups of the host-buffer pipeline: `pg` images per group, but the groups at the exposed end of the pipe -- the first uploads
+    // (g_a waits for them) or the last downloads (nothing runs behind them) -- ramp 1, 1, 2, ...: the copy that nothing overlaps is one
+    // image, not four (32 images: ~3 ms of a 112 ms step).  MLIC_PIPE_RAMP=0: uniform groups.
+    static std::vector<std::pair<int, int>> pipe_groups(int B, bool ramp_front) {
+        static const int ramp = getenv("MLIC_PIPE_RAMP") ? atoi(getenv("MLIC_PIPE_RAMP")) : 1;
+        const int pg = pipe_group(B);
+        std::vector<int> sizes;
+        int left = B;
+        if (ramp && pg >= 4 && B >= 4 * pg) { for (int r : {1, 1, 2}) { sizes.push_back(r); left -= r; } }
+        while (left > 0) { const int n = std::min(pg, left); sizes.push_back(n); left -= n; }
+        if (!ramp_front) std::reverse(sizes.begin(), sizes.end());
+        std::vector<std::pair<int, int>> g;
+        int b = 0;
+        for (int n : sizes) { g.emplace_back(b, n); b += n; }
+        return g;
+    }
 
     // ------------------------------------------------------------------ the whole call
     int run(int mode, int precision, int B, int H, int W, float gain, const mlic_buffers* io, void* ws, size_t ws_bytes,
@@ -1156,16 +1172,16 @@ struct mlic_engine {
             } else if (hp && hp->hx && head_fused() && !dry) {
                 // host call: upload in groups of `pg` images, g_a on a group as soon as it has landed
                 const size_t img = (size_t)3 * H * W;
-                const int pg = pipe_group(B);
+                const auto groups = pipe_groups(B, true);
                 std::vector<cudaEvent_t> ev;
-                for (int b = 0; b < B; b += pg) {
-                    const int nb = std::min(pg, B - b);
+                for (const auto& gr : groups) {
+                    const int b = gr.first, nb = gr.second;
                     cudaMemcpyAsync(const_cast<float*>(io->x) + b * img, hp->hx + b * img, nb * img * 4, cudaMemcpyHostToDevice, hp->s_in);
                     ev.push_back(pipe_event());
                     cudaEventRecord(ev.back(), hp->s_in);
                 }
-                for (int b = 0, gi = 0; b < B && !rc; b += pg, ++gi) {
-                    const int nb = std::min(pg, B - b);
+                for (size_t gi = 0; gi < groups.size() && !rc; ++gi) {
+                    const int b = groups[gi].first, nb = groups[gi].second;
                     cudaStreamWaitEvent(st, ev[gi], 0);
                     Act x; x.p = nullptr; x.B = nb; x.H = H; x.W = W; x.C = 3; x.ld = 3;
                     g_a(x, y32 + (size_t)b * h * w * M, io->x + b * img);
@@ -1279,9 +1295,9 @@ struct mlic_engine {
         }
         if (hp && hp->hx_hat && io->x_hat && go()) {          // (hp implies all stages)
             const size_t img = (size_t)3 * H * W;
-            const int pg = pipe_group(B);
-            for (int b = 0; b < B && !rc; b += pg) {
-                const int nb = std::min(pg, B - b);
+            for (const auto& gr : pipe_groups(B, false)) {
+                if (rc) break;
+                const int b = gr.first, nb = gr.second;
                 Act yb = yhat; yb.B = nb; yb.p = (uint8_t*)yhat.p + (size_t)b * h * w * yhat.ld * esz();
                 g_s(yb, io->x_hat + b * img);
                 cudaEvent_t ev = pipe_event();
