@@ -60,13 +60,14 @@ __device__ __forceinline__ void tma_load_2d_cl(uint32_t dst, const CUtensorMap* 
         : "memory");
 }
 
-template <int ACT>
+template <int ACT, bool RES>
 __global__ void __launch_bounds__(CP_THREADS, 1)
 conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned long long* __restrict__ dbg) {
     extern __shared__ uint8_t cp_smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)cp_smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full[CP_NSTAGE], empty[CP_NSTAGE];      // full: the leader's instance is the live one
     __shared__ uint64_t d_full[2], d_empty[2];                  // d_empty: the leader's instance is the live one
+    __shared__ uint64_t stg_bar[4];                             // RES: the tile's current output block has landed in the staging block
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,6 +83,7 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < CP_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 2 * CP_EPI_WARPS); }
+        for (int s = 0; s < 4; ++s) mbar_init(&stg_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -183,8 +185,17 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
             // the previous TMA store of this group has finished reading the staging block
             if (gissuer) tma_store_wait_read(0);
             asm volatile("bar.sync %0, 128;" ::"r"(eb + 1) : "memory");
+            const int g = col0 / p.Cq, cc = col0 - g * p.Cq;            // PixelShuffle group of this column block and its offset inside it
+            if constexpr (RES) {
+                // out += conv(x): the block the tile will overwrite is fetched into the staging block while the main loop still runs
+                if (gissuer) {
+                    mbar_expect_tx(&stg_bar[eb], (uint32_t)CP_STG_BYTES);
+                    tma_load_4d(sb, &tm.o[g], &stg_bar[eb], cc, w0, h0, img);
+                }
+            }
             CP_TIMED(tw0, mbar_wait(&d_full[acc], (uint32_t)(it >> 1) & 1u));
             tcgen05_fence_after();
+            if constexpr (RES) mbar_wait(&stg_bar[eb], (uint32_t)it & 1u);
             const uint32_t trow = lane_base + (uint32_t)(acc * 256 + eb * 64);
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll 1
@@ -211,6 +222,11 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
 #pragma unroll
                         for (int j = 0; j < 4; ++j) v[j] = gelu2(v[j]);
                     }
+                    if constexpr (RES) {
+                        const uint4 t4 = lds128(sb_s + off);
+                        v[0] = __fadd2_rn(v[0], bf2_to_f2(t4.x)); v[1] = __fadd2_rn(v[1], bf2_to_f2(t4.y));
+                        v[2] = __fadd2_rn(v[2], bf2_to_f2(t4.z)); v[3] = __fadd2_rn(v[3], bf2_to_f2(t4.w));
+                    }
                     uint4 o;
                     { __nv_bfloat162 h0b = __floats2bfloat162_rn(v[0].x, v[0].y), h1b = __floats2bfloat162_rn(v[1].x, v[1].y),
                                      h2b = __floats2bfloat162_rn(v[2].x, v[2].y), h3b = __floats2bfloat162_rn(v[3].x, v[3].y);
@@ -222,7 +238,6 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, 128;" ::"r"(eb + 1) : "memory");
             if (gissuer) {
-                const int g = col0 / p.Cq, cc = col0 - g * p.Cq;        // PixelShuffle group of this column block and its offset inside it
                 if (tvalid) tma_store_4d(&tm.o[g], sb, cc, w0, h0, img);
                 tma_store_commit();
             }
@@ -261,9 +276,9 @@ bool conv3_pair_supported(const Conv3PairArgs& a) {
     return true;
 }
 
-template <int ACT>
+template <int ACT, bool RES>
 static int cp_launch(const CpMaps& tm, const CpParams& p, int nclusters, cudaStream_t s) {
-    auto fn = conv3_pair_kernel<ACT>;
+    auto fn = conv3_pair_kernel<ACT, RES>;
     static bool attr[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -368,8 +383,9 @@ int launch_conv3_pair(const Conv3PairArgs& a, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < 2) sms = 148;
     const int nclusters = p.nitems < sms / 2 ? p.nitems : sms / 2;
-    if (a.act == ACT_GELU) return cp_launch<ACT_GELU>(tm, p, nclusters, s);
-    return cp_launch<ACT_NONE>(tm, p, nclusters, s);
+    if (a.res_inplace) return a.act == ACT_GELU ? cp_launch<ACT_GELU, true>(tm, p, nclusters, s) : cp_launch<ACT_NONE, true>(tm, p, nclusters, s);
+    if (a.act == ACT_GELU) return cp_launch<ACT_GELU, false>(tm, p, nclusters, s);
+    return cp_launch<ACT_NONE, false>(tm, p, nclusters, s);
 }
 
 }  // namespace mlic

@@ -627,12 +627,14 @@ struct mlic_engine {
                 }
             }
             // wide dense 3x3 convs (the sub-pixel convs of g_s): two-SM kernel, each CTA stages half of the weight tile (conv3_pair.cu)
-            if (sup && pair && !prod && !o.ck && w->ks == 3 && stride == 1 && pad == 1 && !e.res && !e.gdn && !e.out2 && !e.out_f32 && !e.nchw &&
+            const bool res_inplace = e.res && e.res == e.out && e.res_ld == e.out_ld;
+            if (sup && pair && !prod && !o.ck && w->ks == 3 && stride == 1 && pad == 1 && (!e.res || res_inplace) && !e.gdn && !e.out2 && !e.out_f32 && !e.nchw &&
                 !e.premask && !e.postmask && w->Cpad == w->Cin) {
                 Conv3PairArgs a;
                 memset(&a, 0, sizeof a);
                 a.in = in.p; a.B = in.B; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ld = in.ld;
                 a.w = w->wbf; a.bias = w->bias; a.N = w->N; a.act = e.act; a.shuffle = w->shuffle; a.out = e.out; a.out_ld = e.out_ld;
+                a.res_inplace = res_inplace ? 1 : 0;
                 if (conv3_pair_supported(a)) {
                     cudaEvent_t ev1 = nullptr;
                     if (profile) {
@@ -860,6 +862,19 @@ struct mlic_engine {
         Act t = act(out.B, out.H, out.W, out.C);
         gemm(x, p + ".subpel_conv.0", 1, 1, &t, g);
         Act v = act(out.B, out.H, out.W, out.C);
+        // bf16 + two-SM kernels: the `+ upsample(x)` of res_blk.py:121 moves from the memory-bound tail kernel (one tensor pass less there)
+        // into the epilogue of the tensor-bound upsample conv, which has the bandwidth to spare: out = IGDN(conv(t)); out += upsample(x)
+        const ConvW* wu = bf && use_tc && pair ? cw(p + ".upsample.0") : nullptr;
+        const bool up_adds = wu && wu->ks == 3 && wu->shuffle && wu->Cpad == wu->Cin && (wu->Cin % 64) == 0 && wu->Cin >= 64 && (wu->N % 256) == 0 &&
+                             ((wu->N / 4) % 64) == 0 && (out.ld % 8) == 0 && ((uintptr_t)out.p % 16) == 0 && (x.ld % 8) == 0 && ((uintptr_t)x.p % 16) == 0;
+        if (up_adds) {
+            EpiOpt og; og.gdn = GDN_INV; og.gdn_x = &v;
+            gdn_block(t, p + ".conv", false, v, p + ".igdn", out, og);
+            EpiOpt ou; ou.res = &out;
+            gemm(x, p + ".upsample.0", 1, 1, &out, ou);
+            ws_off = mark;
+            return;
+        }
         Act up = act(out.B, out.H, out.W, out.C);
         gemm(x, p + ".upsample.0", 1, 1, &up, EpiOpt());
         EpiOpt og; og.gdn = GDN_INV; og.gdn_x = &v; og.res = &up;

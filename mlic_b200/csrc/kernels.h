@@ -127,6 +127,7 @@ struct Conv3PairArgs {
     int N, act;                             // ACT_NONE | ACT_GELU
     int shuffle;                            // 1: PixelShuffle(2): out is [B][2H][2W][N / 4], (N / 4) % 64 == 0
     void* out; int out_ld;
+    int res_inplace;                        // 1: out += act(conv(in) + bias): the output's current contents are the residual (read through the store maps)
 };
 bool conv3_pair_supported(const Conv3PairArgs& a);
 int launch_conv3_pair(const Conv3PairArgs& a, cudaStream_t s);      // 0 ok
