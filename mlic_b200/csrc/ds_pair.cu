@@ -43,6 +43,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+                 "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // non-volatile shared loads for the producer's inner loop (the compiler may schedule them; the caller pins them behind
 // the barrier wait by laundering the base address through an asm statement that follows the wait)
@@ -281,7 +287,7 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)              // 16 bf16 of K = 8 TMEM columns per step
                                 umma2_ts(tmem_base + (uint32_t)Cfg::TM_D2, tmem_base + (uint32_t)(Cfg::TM_A2 + (k * 4 + kk) * 8), bdesc + (uint64_t)(kk * 2), idesc,
-                                         (k | kk) ? 1u : 0u);
+                                         1u);                 // onto beta, which phase 1 of the epilogue has written into the accumulator
                         }
                         commit_pair(&d_full[1]);
                     }
@@ -456,12 +462,15 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                     }
                 }
             } else {
-                // ---- phase 1: v = acc1 + b1 ; v^2 -> bf16 A operand of the GDN GEMM, in TMEM
+                // ---- phase 1: v = acc1 + b1, written back in place; v^2 -> bf16 A operand of the GDN GEMM, in TMEM; the GDN accumulator is
+                // preloaded with beta (the second MMA accumulates onto it).  Phase 2 is the serial stretch of the tile (MMA 1 -> phase 1 -> MMA 2
+                // -> phase 2, one accumulator set): both biases are paid here, 6 instructions per 16 values, instead of 16 there.
                 const uint32_t ph = (uint32_t)it & 1u;
                 DP_TIMED(tw0, mbar_wait(&d_full[0], ph));
                 tcgen05_fence_after();
                 const uint32_t trow1 = lane_base + (uint32_t)(eb * 64);
                 const uint32_t trowa = lane_base + (uint32_t)(Cfg::TM_A2 + eb * 32);
+                const uint32_t trow2 = lane_base + (uint32_t)(Cfg::TM_D2 + eb * 64);
 #pragma unroll 1
                 for (int pr = 0; pr < 4; ++pr) {
                     uint32_t raw[16], sq[8];
@@ -471,21 +480,29 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                     for (int j = 0; j < 8; ++j) {
                         const float2 b = lds_f2(sB1s + (uint32_t)((pr * 16 + 2 * j) * 4));
                         float2 v = __fadd2_rn(make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1])), b);
+                        raw[2 * j] = __float_as_uint(v.x); raw[2 * j + 1] = __float_as_uint(v.y);
                         v = __fmul2_rn(v, v);
                         __nv_bfloat162 hv = __floats2bfloat162_rn(v.x, v.y);
                         sq[j] = *reinterpret_cast<uint32_t*>(&hv);
                     }
                     tmem_st8(trowa + (uint32_t)(pr * 8), sq);
+                    tmem_st16(trow1 + (uint32_t)(pr * 16), raw);
+                    uint32_t be[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 t = lds128(sB2s + (uint32_t)((pr * 16 + 4 * j) * 4));
+                        be[4 * j] = t.x; be[4 * j + 1] = t.y; be[4 * j + 2] = t.z; be[4 * j + 3] = t.w;
+                    }
+                    tmem_st16(trow2 + (uint32_t)(pr * 16), be);
                 }
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(a2_full_leader);
-                // ---- phase 2: out = v * (r)sqrt(acc2 + beta) + res
+                // ---- phase 2: out = v * (r)sqrt(gamma v^2 + beta) + res
                 DP_TIMED(tw2, mbar_wait(&d_full[1], ph));
                 tcgen05_fence_after();
                 if constexpr (RES) DP_TIMED(tw1, mbar_wait(sbar, sbar_ph));
-                const uint32_t trow2 = lane_base + (uint32_t)(Cfg::TM_D2 + eb * 64);
 #pragma unroll 1
                 for (int pr = 0; pr < 4; ++pr) {
                     uint32_t rv[16], rn[16];
@@ -507,17 +524,14 @@ ds_pair_kernel(const __grid_constant__ DpMaps tm, const DpParams p, unsigned lon
                         const uint32_t tw4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int cidx = jj * 8 + 2 * j;
-                            const float2 b1v = lds_f2(sB1s + (uint32_t)(cidx * 4)), b2v = lds_f2(sB2s + (uint32_t)(cidx * 4));
-                            const float2 v = __fadd2_rn(make_float2(__uint_as_float(rv[sub * 8 + 2 * j]), __uint_as_float(rv[sub * 8 + 2 * j + 1])), b1v);
-                            const float2 nm = __fadd2_rn(make_float2(__uint_as_float(rn[sub * 8 + 2 * j]), __uint_as_float(rn[sub * 8 + 2 * j + 1])), b2v);
+                            const float2 v = make_float2(__uint_as_float(rv[sub * 8 + 2 * j]), __uint_as_float(rv[sub * 8 + 2 * j + 1]));
                             float s0, s1;
                             if constexpr (GDN == GDN_FWD) {
-                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(nm.x));
-                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(nm.y));
+                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "r"(rn[sub * 8 + 2 * j]));
+                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "r"(rn[sub * 8 + 2 * j + 1]));
                             } else {
-                                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(nm.x));
-                                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(nm.y));
+                                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "r"(rn[sub * 8 + 2 * j]));
+                                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "r"(rn[sub * 8 + 2 * j + 1]));
                             }
                             float2 o = __fmul2_rn(v, make_float2(s0, s1));
                             if constexpr (RES) o = __fadd2_rn(o, bf2_to_f2(tw4[j]));
