@@ -62,6 +62,10 @@ int mlic_engine_finalize(mlic_engine* e);
  *        stages 2 | 6: `y` is an INPUT (the gathered bands), outputs as usual plus the `y_hat` tap; stages 4: `y_hat` is an
  *        INPUT (a band of latent rows, H = 16 x rows) -> x_hat band.  Stage subsets take device buffers (mlic_run) only. */
 int mlic_engine_set_option(mlic_engine* e, const char* name, int value);
+/* Float knobs: "z_qstep" -- quantisation step of the hyper prior z for the calls that follow (MLICPlusPlusVbr / MLICPlusPlusSDVbr with
+ * vr_entbttlnck=True: EntropyBottleneckVbr(z, qs), models/mlicpp_vbr.py:253-259,553-559): z_hat = round((z - median) / qs) qs + median,
+ * likelihood over [z_hat - qs / 2, z_hat + qs / 2], z symbols = round((z - median) / qs).  1 (default) is the plain EntropyBottleneck. */
+int mlic_engine_set_option_f(mlic_engine* e, const char* name, float value);
 
 /* Device workspace needed by one call of the given mode / precision / shape. */
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes);

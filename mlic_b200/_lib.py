@@ -13,7 +13,7 @@ MODE_FORWARD, MODE_COMPRESS, MODE_DECODER, MODE_DECOMPRESS = 0, 1, 2, 3
 # every symbol include/mlic_b200.h declares (tests check the library exports exactly these)
 EXPORTS = (
     "mlic_engine_create", "mlic_engine_destroy", "mlic_engine_set_param", "mlic_engine_finalize",
-    "mlic_engine_set_option", "mlic_workspace_bytes", "mlic_run", "mlic_run_host", "mlic_last_launch_count",
+    "mlic_engine_set_option", "mlic_engine_set_option_f", "mlic_workspace_bytes", "mlic_run", "mlic_run_host", "mlic_last_launch_count",
     "mlic_profile_read", "mlic_profile_read_top", "mlic_trace_dump", "mlic_conv2d_nhwc", "mlic_dwconv3x3_nhwc", "mlic_dsconv_nhwc", "mlic_ds_gdn_nhwc", "mlic_final_subpel", "mlic_local_attn", "mlic_lin_attn", "mlic_ga_head", "mlic_gaussian_conditional", "mlic_last_error", "mlic_version",
     "mlic_engine_set_cdf", "mlic_decompress", "mlic_pmf_to_quantized_cdf", "mlic_rans_encode_bound", "mlic_rans_encode",
     "mlic_rans_decoder_create", "mlic_rans_decoder_destroy", "mlic_rans_decode_stream",
@@ -51,6 +51,7 @@ def lib():
     L.mlic_engine_set_param.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
     L.mlic_engine_finalize.argtypes = [vp]
     L.mlic_engine_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.mlic_engine_set_option_f.argtypes = [vp, C.c_char_p, f32]
     L.mlic_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(sz)]
     L.mlic_run.argtypes = [vp, i32, i32, i32, i32, i32, f32, C.POINTER(Buffers), vp, sz, vp]
     L.mlic_run_host.argtypes = [vp, i32, i32, i32, i32, i32, f32, C.POINTER(Buffers), i32]

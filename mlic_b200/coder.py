@@ -73,16 +73,19 @@ def gaussian_tables(scale_table):
     return cdf, (pmf_length + 2).numpy().astype(np.int32), (-pmf_center).numpy().astype(np.int32)
 
 
-def bottleneck_tables(eb):
-    """EntropyBottleneck.update() on the module's parameters (matrices / biases / factors / quantiles)."""
+def bottleneck_tables(eb, qs=1.0):
+    """EntropyBottleneck.update() on the module's parameters (matrices / biases / factors / quantiles); qs != 1: the tables of
+    EntropyBottleneckVbr.update_variable(qs) -- the same construction on a grid of step qs around the medians (symbols are
+    round((z - median) / qs); restated from CompressAI's published behaviour, unpinned like the rest of the coder)."""
     q = eb.quantiles.detach().float().cpu()
+    qs = float(qs)
     medians = q[:, 0, 1]
-    minima = torch.clamp(torch.ceil(medians - q[:, 0, 0]).int(), min=0)
-    maxima = torch.clamp(torch.ceil(q[:, 0, 2] - medians).int(), min=0)
-    pmf_start = medians - minima
+    minima = torch.clamp(torch.ceil((medians - q[:, 0, 0]) / qs).int(), min=0)
+    maxima = torch.clamp(torch.ceil((q[:, 0, 2] - medians) / qs).int(), min=0)
+    pmf_start = medians - minima * qs
     pmf_length = maxima + minima + 1
     max_length = int(pmf_length.max())
-    samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]            # [C,1,L]
+    samples = torch.arange(max_length)[None, :] * qs + pmf_start[:, None, None]       # [C,1,L]
 
     def cum(x):
         logits = x
@@ -95,7 +98,7 @@ def bottleneck_tables(eb):
                 logits = logits + torch.tanh(f) * torch.tanh(logits)
         return logits
 
-    lower, upper = cum(samples - 0.5), cum(samples + 0.5)
+    lower, upper = cum(samples - 0.5 * qs), cum(samples + 0.5 * qs)
     # CompressAI EntropyBottleneck.update(): the difference is taken on the side of the sigmoid where it does not cancel
     # (sign = -sign(lower + upper)); equal to sigmoid(upper) - sigmoid(lower) in exact arithmetic, not in fp32 in the upper tail
     sign = -torch.sign(lower + upper)

@@ -105,6 +105,7 @@ struct mlic_engine {
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
     int pair = 1;            // fuse: DepthWiseConv / (I)GDN-tail blocks with C = N = 192 | 128 on the two-SM kernel (ds_pair.cu)
     int halo5 = 1;           // 5x5 convs with N <= 128 on the halo-patch kernel (conv_halo.cu)
+    float z_qstep = 1.0f;    // quantisation step of the hyper prior (EntropyBottleneckVbr, vr_entbttlnck=True); 1: the plain EntropyBottleneck
 
     std::vector<void*> dev_allocs;
     std::unordered_map<std::string, ConvW> convs;
@@ -1176,7 +1177,7 @@ struct mlic_engine {
         }
         if (decomp) {                                     // z_hat from the decoded z symbols (EntropyBottleneck.decompress)
             if (!dry && !io->z_symbols) return fail("decompress needs z_symbols");
-            if (go()) { launch_zsym_to_zhat(bf, io->z_symbols, eb_medians, zh, st); after_launch("z_hat_in"); }
+            if (go()) { launch_zsym_to_zhat(bf, io->z_symbols, eb_medians, zh, st, z_qstep); after_launch("z_hat_in"); }
         } else if (mode != MLIC_MODE_DECODER) {
             size_t mark = ws_off;
             if (!(stg & 1)) {                             // g_a ran elsewhere (its row bands were gathered): y is an input
@@ -1220,7 +1221,7 @@ struct mlic_engine {
             h_a(ya, z);
             if (go()) {
                 launch_entropy_bottleneck(bf, z, zh, eb_packed, eb_medians, mode == MLIC_MODE_FORWARD ? io->z_likelihoods : nullptr,
-                                          mode == MLIC_MODE_COMPRESS ? io->z_symbols : nullptr, st);
+                                          mode == MLIC_MODE_COMPRESS ? io->z_symbols : nullptr, st, z_qstep);
                 after_launch("entropy_bottleneck");
             }
             ws_off = mark;
@@ -1382,6 +1383,16 @@ int mlic_engine_set_option(mlic_engine* e, const char* name, int value) {
     if (!strcmp(name, "trace")) { e->trace = value; return 0; }
     if (!strcmp(name, "stages")) { e->stages = value & 7; return 0; }
     return fail("unknown option '%s'", name);
+}
+
+int mlic_engine_set_option_f(mlic_engine* e, const char* name, float value) {
+    if (!e || !name) return fail("bad arguments");
+    if (!strcmp(name, "z_qstep")) {
+        if (!(value > 0.0f) || !std::isfinite(value)) return fail("z_qstep must be a positive number");
+        e->z_qstep = value;
+        return 0;
+    }
+    return fail("unknown float option '%s'", name);
 }
 int mlic_workspace_bytes(mlic_engine* e, int mode, int precision, int B, int H, int W, size_t* bytes) {
     if (!e || !bytes) return fail("bad arguments");

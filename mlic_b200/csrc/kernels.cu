@@ -748,7 +748,7 @@ template <typename T>
 __global__ void entropy_bottleneck_kernel(const T* __restrict__ z, int zld, T* __restrict__ zh, int zhld, int C,
                                           int HW, long long total, const float* __restrict__ packed,
                                           const float* __restrict__ med, float* __restrict__ lik_nchw,
-                                          int32_t* __restrict__ sym_nchw) {
+                                          int32_t* __restrict__ sym_nchw, float qs) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long p = i / C;
@@ -756,47 +756,50 @@ __global__ void entropy_bottleneck_kernel(const T* __restrict__ z, int zld, T* _
         int b = (int)(p / HW);
         int hw = (int)(p - (long long)b * HW);
         float m = med[c];
-        float q = rintf(to_f<T>(z[p * zld + c]) - m);
-        float v = q + m;
+        // qs: quantisation step of the variable-rate hyper prior (EntropyBottleneckVbr, mlicpp_vbr.py:253-259); 1 for the plain bottleneck,
+        // where the division, the product and the half step below are exact.  Product and sum rounded separately, as torch evaluates them.
+        float q = rintf((to_f<T>(z[p * zld + c]) - m) / qs);
+        float v = __fadd_rn(__fmul_rn(q, qs), m);
         if (zh) zh[p * zhld + c] = from_f<T>(v);
         size_t o = ((size_t)b * C + c) * HW + hw;
         if (sym_nchw) sym_nchw[o] = (int32_t)q;
         if (lik_nchw) {
             const float* P = packed + (size_t)c * 58;
-            float lo = eb_logits(P, v - 0.5f), up = eb_logits(P, v + 0.5f);
+            const float half = 0.5f * qs;
+            float lo = eb_logits(P, v - half), up = eb_logits(P, v + half);
             float l = sigmoidf_(up) - sigmoidf_(lo);
             lik_nchw[o] = fmaxf(l, 1e-9f);
         }
     }
 }
 void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const float* packed, const float* medians,
-                               float* z_lik_nchw, int32_t* z_sym_nchw, cudaStream_t s) {
+                               float* z_lik_nchw, int32_t* z_sym_nchw, cudaStream_t s, float qs) {
     long long total = (long long)z.B * z.H * z.W * z.C;
     if (!total) return;
     int blocks = cdiv(total, 128);
-    if (bf) entropy_bottleneck_kernel<bf16><<<blocks, 128, 0, s>>>((const bf16*)z.p, z.ld, (bf16*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw);
-    else entropy_bottleneck_kernel<float><<<blocks, 128, 0, s>>>((const float*)z.p, z.ld, (float*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw);
+    if (bf) entropy_bottleneck_kernel<bf16><<<blocks, 128, 0, s>>>((const bf16*)z.p, z.ld, (bf16*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw, qs);
+    else entropy_bottleneck_kernel<float><<<blocks, 128, 0, s>>>((const float*)z.p, z.ld, (float*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw, qs);
 }
 
 // EntropyBottleneck.decompress after the range decoder (CompressAI: dequantize(values, medians)): z_hat = sym + median
 template <typename T>
 __global__ void zsym_to_zhat_kernel(const int32_t* __restrict__ sym_nchw, T* __restrict__ zh, int zhld, int C, int HW,
-                                    long long total, const float* __restrict__ med) {
+                                    long long total, const float* __restrict__ med, float qs) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long p = i / C;
         int c = (int)(i - p * C);
         int b = (int)(p / HW);
         int hw = (int)(p - (long long)b * HW);
-        zh[p * zhld + c] = from_f<T>((float)sym_nchw[((size_t)b * C + c) * HW + hw] + med[c]);
+        zh[p * zhld + c] = from_f<T>(__fadd_rn(__fmul_rn((float)sym_nchw[((size_t)b * C + c) * HW + hw], qs), med[c]));
     }
 }
-void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians, const Act& z_hat, cudaStream_t s) {
+void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians, const Act& z_hat, cudaStream_t s, float qs) {
     long long total = (long long)z_hat.B * z_hat.H * z_hat.W * z_hat.C;
     if (!total) return;
     int blocks = cdiv(total, 128);
-    if (bf) zsym_to_zhat_kernel<bf16><<<blocks, 128, 0, s>>>(z_sym_nchw, (bf16*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians);
-    else zsym_to_zhat_kernel<float><<<blocks, 128, 0, s>>>(z_sym_nchw, (float*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians);
+    if (bf) zsym_to_zhat_kernel<bf16><<<blocks, 128, 0, s>>>(z_sym_nchw, (bf16*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians, qs);
+    else zsym_to_zhat_kernel<float><<<blocks, 128, 0, s>>>(z_sym_nchw, (float*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians, qs);
 }
 
 // ------------------------------------------------------------------------------------------

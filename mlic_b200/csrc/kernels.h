@@ -30,9 +30,9 @@ void launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
 
 // EntropyBottleneck: z (NHWC act) -> z_hat (NHWC act), z_lik (fp32 NCHW), z_sym (int32 NCHW, optional)
 void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const float* packed /*[N][58]*/,
-                               const float* medians, float* z_lik_nchw, int32_t* z_sym_nchw, cudaStream_t s);
+                               const float* medians, float* z_lik_nchw, int32_t* z_sym_nchw, cudaStream_t s, float qs = 1.0f);
 
-void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians, const Act& z_hat, cudaStream_t s);
+void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians, const Act& z_hat, cudaStream_t s, float qs = 1.0f);
 
 // LocalContext windowed attention: F[pix][3C] fp32 (q|k|v) -> O[pix][25][C] (activation type); C = 32 or 64.
 // returns non-zero for an unsupported C.

@@ -90,7 +90,7 @@ class MLICPlusPlus(nn.Module):
 
     KIND = "base"
 
-    def __init__(self, config, name=None, **kwargs):
+    def __init__(self, config, name=None, _vr_entbttlnck=False, **kwargs):
         super().__init__()
         self.N, self.M = int(config.N), int(config.M)
         self.slice_num = int(config.slice_num)
@@ -101,7 +101,7 @@ class MLICPlusPlus(nn.Module):
         self.precision = "bf16"          # "bf16" fast mode | "fp32" validation mode
         self.tensor_cores = True
         self.fuse = True                 # bf16 mode: depthwise 3x3 / x^2 produced inside the GEMM kernel
-        for key, ent in build_entries(self.model_name).items():
+        for key, ent in build_entries(self.model_name, bool(_vr_entbttlnck)).items():
             self._place(key, _init_tensor(ent), ent.is_param)
         # attributes the reference exposes on sub-modules
         for i in range(self.slice_num):
@@ -227,7 +227,7 @@ class MLICPlusPlus(nn.Module):
         self.precision = precision
         return self
 
-    def _run_staged(self, mode, x, B, H, W, gain, want):
+    def _run_staged(self, mode, x, B, H, W, gain, want, zq=1.0):
         """A full call with per-stage precisions: consecutive stages of equal precision share one engine call."""
         if H % 64 or W % 64:
             raise ValueError("H and W must be multiples of 64 (the reference pads, utils/testing.py:130-137)")
@@ -251,11 +251,11 @@ class MLICPlusPlus(nn.Module):
             self.precision = pe
             first = 2 if (y is not None or mode == _lib.MODE_DECODER) else 3
             if pe == ps:
-                o = self._run(mode, None if y is not None else x, B, H, W, gain, tuple(want), stages=first | 4, y=y)
+                o = self._run(mode, None if y is not None else x, B, H, W, gain, tuple(want), stages=first | 4, y=y, zq=zq)
                 out.update(o)
             else:
                 w2 = tuple(set(want) | {"y_hat"})
-                o = self._run(mode, None if first == 2 else x, B, H, W, gain, w2, stages=first, y=y)
+                o = self._run(mode, None if first == 2 else x, B, H, W, gain, w2, stages=first, y=y, zq=zq)
                 y_hat = o["y_hat"]
                 out.update({k: v for k, v in o.items() if k != "y_hat" or "y_hat" in want})
                 self.precision = ps
@@ -315,14 +315,14 @@ class MLICPlusPlus(nn.Module):
     def _gain(self, stage, s, inputscale, absolute=False):
         return 0.0
 
-    def _run(self, mode, x, B, H, W, gain=0.0, want=(), stages=7, y=None, y_hat=None):
+    def _run(self, mode, x, B, H, W, gain=0.0, want=(), stages=7, y=None, y_hat=None, zq=1.0):
         """One engine call.  x: CUDA tensor (device path) or CPU tensor (host path through mlic_run_host).
         stages: bit mask of include/mlic_b200.h option "stages" (1 g_a | 2 entropy model | 4 g_s); `y` / `y_hat` are the
         device INPUTS of the calls that start after g_a / at g_s (row-band sharding, mlic_b200/dist.py)."""
         if isinstance(self.precision, tuple):
             if stages != 7:
                 raise _lib.MlicError("stage-subset calls take one precision (set_precision('bf16' | 'fp32'))")
-            return self._run_staged(mode, x, B, H, W, gain, want)
+            return self._run_staged(mode, x, B, H, W, gain, want, zq)
         hmul = 64 if stages & 2 else 16
         if H % hmul or W % 64:
             raise ValueError("H and W must be multiples of 64 (the reference pads, utils/testing.py:130-137)")
@@ -339,6 +339,7 @@ class MLICPlusPlus(nn.Module):
         _lib.check(L.mlic_engine_set_option(self._engine, b"fuse", 1 if self.fuse else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"trace", 1 if self._trace else 0))
         _lib.check(L.mlic_engine_set_option(self._engine, b"stages", int(stages)))
+        _lib.check(L.mlic_engine_set_option_f(self._engine, b"z_qstep", float(zq)))
         prec = _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
         odev = "cpu" if host else dev
         h, w, hz, wz = H // 16, W // 16, H // 64, W // 64
@@ -467,13 +468,27 @@ class MLICPlusPlus(nn.Module):
             torch.cuda.current_stream(next(t for t in tensors if t.is_cuda).device).synchronize()
         return out
 
-    def _strings(self, o, B):
+    def _z_tables(self, zq=1.0):
+        """Quantised CDF tables of the hyper prior: those of update() for the plain bottleneck, per-step tables (cached) for the
+        variable-rate one (CompressAI EntropyBottleneckVbr.update_variable)."""
+        if zq == 1.0:
+            return self._tables(self.entropy_bottleneck)
+        from . import coder
+        if not hasattr(self, "_zq_tables"):
+            self._zq_tables = {}
+        key = (float(zq), tuple((v.data_ptr(), v._version) for v in self.entropy_bottleneck.parameters()))
+        if key not in self._zq_tables:
+            self._zq_tables.clear()
+            self._zq_tables[key] = coder.bottleneck_tables(self.entropy_bottleneck, float(zq))
+        return self._zq_tables[key]
+
+    def _strings(self, o, B, zq=1.0):
         """The coder side of compress() (models/mlicpp.py:205-206,279-280): ONE y string for the whole batch (the symbol
         lists are flattened over [B,C,H,W/2] per half-slice), one z string per image (EntropyBottleneck.compress)."""
         from . import coder
         sym, idx, zs = self._to_host(o["symbols"], o["indexes"], o["z_symbols"])
         y_string = coder.encode_with_indexes(sym, idx, *self._tables(self.gaussian_conditional))
-        ztab = self._tables(self.entropy_bottleneck)
+        ztab = self._z_tables(zq)
         zidx = np.broadcast_to(np.arange(self.N, dtype=np.int32)[:, None, None], zs.shape[1:])
         return [[y_string], [coder.encode_with_indexes(zs[b], zidx, *ztab) for b in range(B)]]
 
@@ -492,7 +507,7 @@ class MLICPlusPlus(nn.Module):
         return o
 
     @torch.no_grad()
-    def decompress(self, strings, shape, *, taps=(), _gain=0.0):
+    def decompress(self, strings, shape, *, taps=(), _gain=0.0, _zq=1.0):
         """models/mlicpp.py:292-378 -> {"x_hat", "cost_time"}: z strings decoded on the host, then the decoder-side walk with
         the range decoder inside the slice loop (C ABI mlic_decompress)."""
         from . import coder
@@ -502,7 +517,7 @@ class MLICPlusPlus(nn.Module):
         y_string, z_strings = strings[0][0], strings[1]
         B, (hz, wz) = len(z_strings), shape
         H, W = 64 * int(hz), 64 * int(wz)
-        ztab = self._tables(self.entropy_bottleneck)
+        ztab = self._z_tables(_zq)
         zidx = np.broadcast_to(np.arange(self.N, dtype=np.int32)[:, None, None], (self.N, hz, wz))
         dec = coder.RansDecoder()
         zs = np.stack([dec.decode_with_indexes(s, zidx, *ztab).reshape(self.N, hz, wz) for s in z_strings])
@@ -518,6 +533,7 @@ class MLICPlusPlus(nn.Module):
                                          off.ctypes.data_as(C.c_void_p), cdf.shape[0]))
         for name, val in ((b"tensor_cores", self.tensor_cores), (b"profile", False), (b"fuse", self.fuse), (b"trace", self._trace), (b"stages", 7)):
             _lib.check(L.mlic_engine_set_option(self._engine, name, int(val)))
+        _lib.check(L.mlic_engine_set_option_f(self._engine, b"z_qstep", float(_zq)))
         # per-stage precisions: the decoder must reproduce the encoder's mu / sigma, so the whole walk runs in the entropy stage's
         one = self.precision[1] if isinstance(self.precision, tuple) else self.precision
         prec = _lib.PREC_BF16 if one == "bf16" else _lib.PREC_FP32
@@ -607,12 +623,12 @@ class MLICPlusPlusVbr(MLICPlusPlus):
     KIND = "vbr"
     LAMBDAS = VBR_LAMBDAS
 
-    def __init__(self, config, name=None, **kwargs):
-        super().__init__(config, name=name, **kwargs)
+    def __init__(self, config, name=None, vr_entbttlnck=None, **kwargs):
+        super().__init__(config, name=name, _vr_entbttlnck=bool(vr_entbttlnck), **kwargs)
         self.lmbda = list(self.LAMBDAS)
         self.levels = len(self.lmbda)
         self.no_quantoffset = True
-        self.vr_entbttlnck = None
+        self.vr_entbttlnck = vr_entbttlnck          # mlicpp_vbr.py:103-117: variable-rate hyper prior (EntropyBottleneckVbr + gayn2zqstep)
 
     def _scale(self, s, inputscale, absolute):
         if inputscale != 0:
@@ -623,13 +639,27 @@ class MLICPlusPlusVbr(MLICPlusPlus):
         s = max(0, min(int(s), self.Gain.numel() - 1))  # mlicpp_vbr.py:122-135
         return float(self.Gain[s].detach())
 
+    def _zqstep(self, scale):
+        """mlicpp_vbr.py:255-256,554-555: z_qstep = LowerBound(0.5)(gayn2zqstep(1 / scale)), a 1-10-10-1 ReLU network with a Softplus
+        on top, evaluated on the host in fp32 exactly as the reference's nn.Sequential does (CPU torch); 1.0 without vr_entbttlnck."""
+        if not self.vr_entbttlnck:
+            return 1.0
+        g = self.gayn2zqstep
+        t = 1.0 / torch.tensor([float(scale)], dtype=torch.float32)
+        for j in (0, 2, 4):
+            lin = getattr(g, str(j))
+            t = nn.functional.linear(t, lin.weight.detach().float().cpu(), lin.bias.detach().float().cpu())
+            t = torch.relu(t) if j < 4 else nn.functional.softplus(t)
+        return float(torch.clamp(t, min=float(self.lower_bound_zqstep.bound))[0])
+
     @torch.no_grad()
     def forward(self, x, stage=2, s=1, inputscale=0, *, taps=()):
         if stage not in (1, 2):
             raise ValueError(f"Invalid stage (stage={stage}) parameter for this model.")     # mlicpp_vbr.py:119-120
         B, _, H, W = x.shape
         gain = self._scale(s, inputscale, False) if stage == 2 else 0.0
-        o = self._run(_lib.MODE_FORWARD, x, B, H, W, gain, taps)
+        zq = self._zqstep(gain) if stage == 2 else 1.0             # stage 1 runs the plain bottleneck (mlicpp_vbr.py:160)
+        o = self._run(_lib.MODE_FORWARD, x, B, H, W, gain, taps, zq=zq)
         res = {"x_hat": o["x_hat"], "likelihoods": {"y_likelihoods": o["y_likelihoods"], "z_likelihoods": o["z_likelihoods"]}}
         res.update({k: o[k] for k in taps})
         return res
@@ -638,17 +668,22 @@ class MLICPlusPlusVbr(MLICPlusPlus):
     def compress(self, x, stage=2, s=1, inputscale=0, *, taps=()):
         t0 = time.time()
         B, _, H, W = x.shape
-        o = self._run(_lib.MODE_COMPRESS, x, B, H, W, self._scale(s, inputscale, True), taps)
+        scale = self._scale(s, inputscale, True)
+        zq = self._zqstep(scale) if stage == 2 else 1.0            # mlicpp_vbr.py:550-559
+        o = self._run(_lib.MODE_COMPRESS, x, B, H, W, scale, taps, zq=zq)
         if x.is_cuda:
             torch.cuda.synchronize(x.device)
-        strings = self._strings(o, B) if self.gaussian_conditional._offset.numel() else None
+        strings = self._strings(o, B, zq) if self.gaussian_conditional._offset.numel() else None
         o.update(strings=strings, shape=(H // 64, W // 64), cost_time=time.time() - t0)
         return o
 
     @torch.no_grad()
     def decompress(self, strings, shape, stage=2, s=1, inputscale=0, *, taps=()):
-        """models/mlicpp_vbr.py:889-1040 (stage 2 arithmetic: indexes from sigma * gain, y_hat = symbols / gain + means)."""
-        return super().decompress(strings, shape, taps=taps, _gain=self._scale(s, inputscale, True))
+        """models/mlicpp_vbr.py:889-1040 (stage 2 arithmetic: indexes from sigma * gain, y_hat = symbols / gain + means).  With
+        vr_entbttlnck the z strings are decoded on the step compress() used (the reference's decompress() omits `qs` there,
+        mlicpp_vbr.py:905, and cannot read its own vr streams)."""
+        scale = self._scale(s, inputscale, True)
+        return super().decompress(strings, shape, taps=taps, _gain=scale, _zq=self._zqstep(scale) if stage == 2 else 1.0)
 
 
 class MLICPlusPlusSDVbr(MLICPlusPlusVbr):

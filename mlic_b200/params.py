@@ -99,8 +99,9 @@ class _Builder:
         self.conv(p + ".4", hidden, cout, 1)
 
 
-def build_entries(name):
-    """name -> OrderedDict[str, Entry] covering every state_dict key of the reference model."""
+def build_entries(name, vr_entbttlnck=False):
+    """name -> OrderedDict[str, Entry] covering every state_dict key of the reference model.  vr_entbttlnck (Vbr kinds only): the
+    variable-rate hyper-prior branch of mlicpp_vbr.py:104-117 -- its gain -> z quantisation-step network and lower bound."""
     cfg = MODEL_TABLE[name]
     N, M, S, kind = cfg["N"], cfg["M"], cfg["slice_num"], cfg["kind"]
     C = M // S
@@ -224,4 +225,10 @@ def build_entries(name):
         e["Gain"] = Entry((len(SDVBR_GAINS if sd else VBR_GAINS),), init=("vbr_gain", None))
         for j, (ci, co) in zip((0, 2, 4), ((2, 12), (12, 12), (12, 1))):
             b.linear(f"QuantABCD.{j}", ci, co)
+        if vr_entbttlnck:                              # mlicpp_vbr.py:105-117 / mlicpp_sd_vbr.py:114-126
+            for j, (ci, co) in zip((0, 2, 4), ((1, 10), (10, 10), (10, 1))):
+                b.linear(f"gayn2zqstep.{j}", ci, co)
+            e["lower_bound_zqstep.bound"] = Entry((1,), False, ("const", 0.5))
+    elif vr_entbttlnck:
+        raise ValueError("vr_entbttlnck belongs to the Vbr models (mlicpp_vbr.py, mlicpp_sd_vbr.py)")
     return e

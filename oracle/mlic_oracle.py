@@ -110,6 +110,8 @@ class Oracle:
         self.table = scale_table()
         self.trace = None
         self._mask_cache = {}
+        # mlicpp_vbr.py:103-117: the variable-rate hyper prior exists iff its gain -> step network is in the state_dict
+        self.vr_entbttlnck = self.vbr and "gayn2zqstep.0.weight" in self.w
 
     # ---------------------------------------------------------------- primitive layers
     def _conv(self, x, p, stride=1, pad=0, groups=1):
@@ -195,11 +197,27 @@ class Oracle:
             x = self._rb(x, p + str(i + 1))
         return self._subpel(x, p + "7")
 
-    def entropy_bottleneck(self, z):
-        """CompressAI EntropyBottleneck eval forward (mlicpp.py:96-98): returns (z_hat, z_lik)."""
+    def z_qstep(self, scale):
+        """mlicpp_vbr.py:255-256,554-555: LowerBound(0.5)(Softplus(Linear(ReLU(Linear(ReLU(Linear(1 / scale))))))); None without vr_entbttlnck."""
+        if not self.vr_entbttlnck or scale is None:
+            return None
+        t = 1.0 / scale.reshape(1)
+        for j in (0, 2, 4):
+            t = F.linear(t, self.w[f"gayn2zqstep.{j}.weight"], self.w[f"gayn2zqstep.{j}.bias"])
+            t = torch.relu(t) if j < 4 else F.softplus(t)
+        return torch.clamp(t, min=float(self.w["lower_bound_zqstep.bound"]))[0]
+
+    def entropy_bottleneck(self, z, qs=None):
+        """CompressAI EntropyBottleneck eval forward (mlicpp.py:96-98): returns (z_hat, z_lik).  qs: quantisation step of
+        EntropyBottleneckVbr (restated, unpinned): z_hat = round((z - med) / qs) qs + med, likelihood over [z_hat - qs/2, z_hat + qs/2]."""
         B, Cc, H, W = z.shape
         med = self.w["entropy_bottleneck.quantiles"][:, 0, 1].view(1, Cc, 1, 1)
-        z_hat = torch.round(z - med) + med
+        if qs is None:
+            z_hat = torch.round(z - med) + med
+            half = 0.5
+        else:
+            z_hat = torch.round((z - med) / qs) * qs + med
+            half = 0.5 * qs
         v = z_hat.permute(1, 0, 2, 3).reshape(Cc, 1, -1)
 
         def cum(t):
@@ -210,7 +228,7 @@ class Oracle:
                     t = t + torch.tanh(self.w[f"entropy_bottleneck.factors.{i}"]) * torch.tanh(t)
             return t
 
-        lik = torch.sigmoid(cum(v + 0.5)) - torch.sigmoid(cum(v - 0.5))
+        lik = torch.sigmoid(cum(v + half)) - torch.sigmoid(cum(v - half))
         lik = torch.clamp_min(lik, LIK_FLOOR).reshape(Cc, B, H, W).permute(1, 0, 2, 3).contiguous()
         return z_hat, lik
 
@@ -428,7 +446,7 @@ class Oracle:
         rec = {} if trace else None
         y = self.g_a(x)
         z = self.h_a(y)
-        z_hat, z_lik = self.entropy_bottleneck(z)
+        z_hat, z_lik = self.entropy_bottleneck(z, self.z_qstep(self._gain(s, inputscale)))
         hyper = self.h_s(z_hat)
         y_hat, y_lik, _, _ = self._entropy_loop(y, hyper, "forward", self._gain(s, inputscale), rec)
         x_hat = self.g_s(y_hat)
@@ -450,12 +468,17 @@ class Oracle:
         y = self.g_a(x)
         z = self.h_a(y)
         med = self.w["entropy_bottleneck.quantiles"][:, 0, 1].view(1, -1, 1, 1)
-        z_sym = torch.round(z - med).to(torch.int32)
-        z_hat = z_sym.to(self.dtype) + med
-        hyper = self.h_s(z_hat)
         g = self._gain(s, inputscale)
         if g is not None:
             g = torch.abs(g)                               # mlicpp_vbr.py:543
+        qs = self.z_qstep(g)                               # mlicpp_vbr.py:553-559 (EntropyBottleneckVbr.compress / decompress with qs)
+        if qs is None:
+            z_sym = torch.round(z - med).to(torch.int32)
+            z_hat = z_sym.to(self.dtype) + med
+        else:
+            z_sym = torch.round((z - med) / qs).to(torch.int32)
+            z_hat = z_sym.to(self.dtype) * qs + med
+        hyper = self.h_s(z_hat)
         y_hat, _, sym, idx = self._entropy_loop(y, hyper, "compress", g, rec)
         out = {"symbols": sym, "indexes": idx, "z_symbols": z_sym, "y_hat": y_hat, "x_hat": self.g_s(y_hat)}
         if trace:

@@ -28,11 +28,14 @@ def _prepare():
         torch.cuda.synchronize = lambda *a, **k: None
 
 
-def get_reference_model(name):
+def get_reference_model(name, vr_entbttlnck=False):
     _prepare()
     import config.config as cf          # reference: config/config.py:19-62
     import models as ref_models         # reference: models/__init__.py
-    if name == "MLICPP_L_VBR":          # not registered upstream (model_loader.py:8-15)
+    if vr_entbttlnck:                   # model_loader.py never passes it: the class is built directly (mlicpp_vbr.py:15, mlicpp_sd_vbr.py:20)
+        cls = {"MLICPP_S_VBR": ref_models.MLICPlusPlusVbr, "MLICPP_M_SMALL_DEC_VBR": ref_models.MLICPlusPlusSDVbr}[name]
+        net = cls(config=cf.model_config(name), vr_entbttlnck=True)
+    elif name == "MLICPP_L_VBR":        # not registered upstream (model_loader.py:8-15)
         net = ref_models.MLICPlusPlusVbr(config=cf.model_config("MLICPP_L"))
     else:
         net = ref_models.get_model(name)

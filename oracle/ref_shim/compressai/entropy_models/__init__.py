@@ -97,8 +97,48 @@ class EntropyBottleneck(EntropyModel):
         return strings.to(med.dtype) + med
 
 
-class EntropyBottleneckVbr(EntropyBottleneck):  # only reachable with vr_entbttlnck=True (default None)
-    pass
+class EntropyBottleneckVbr(EntropyBottleneck):
+    """compressai.entropy_models.EntropyBottleneckVbr (1.2.x), restated from its published behaviour (the package is not installable
+    here: UNPINNED like the rest of this shim): the factorised prior evaluated on a grid of step `qs` instead of 1 --
+    quantise  z_hat = round((z - median) / qs) * qs + median,  likelihood = sigmoid(c(z_hat + qs / 2)) - sigmoid(c(z_hat - qs / 2)).
+    Only reachable with vr_entbttlnck=True (mlicpp_vbr.py:104-117,253-259,553-559); qs=None is the plain bottleneck."""
+
+    def update_variable(self, force=False, qs=1.0):
+        return False  # quantised-CDF tables feed the rANS coder only
+
+    def forward(self, x, training=None, qs=None, ste=False):
+        if qs is None:
+            return super().forward(x, training)
+        perm = list(range(x.dim()))
+        perm[0], perm[1] = 1, 0
+        xp = x.permute(*perm).contiguous()
+        shape = xp.size()
+        values = xp.reshape(xp.size(0), 1, -1)
+        med = self._get_medians()
+        outputs = torch.round((values - med) / qs) * qs + med
+        half = 0.5 * qs
+        lower = self._logits_cumulative(outputs - half)
+        upper = self._logits_cumulative(outputs + half)
+        likelihood = torch.sigmoid(upper) - torch.sigmoid(lower)
+        if self.use_likelihood_bound:
+            likelihood = self.likelihood_lower_bound(likelihood)
+        outputs = outputs.reshape(shape).permute(*perm).contiguous()
+        likelihood = likelihood.reshape(shape).permute(*perm).contiguous()
+        return outputs, likelihood
+
+    def compress(self, x, qs=None, **kw):
+        if qs is None:
+            return super().compress(x)
+        med = self._get_medians().reshape(1, -1, 1, 1)
+        return torch.round((x - med) / qs).int(), qs
+
+    def decompress(self, strings, size, qs=None, **kw):
+        if isinstance(strings, tuple):          # what compress(qs=...) above returned
+            strings = strings[0]
+        med = self._get_medians().reshape(1, -1, 1, 1)
+        if qs is None:
+            return strings.to(med.dtype) + med
+        return strings.to(med.dtype) * qs + med
 
 
 class GaussianConditional(EntropyModel):

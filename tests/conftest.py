@@ -47,6 +47,25 @@ def load_case(name, B, H, W):
     return g, sd, x
 
 
+VR_CASE = ("MLICPP_S_VBR", 1, 64, 128)          # the vr_entbttlnck=True fixture (tests/golden/MLICPP_S_VBR_VRZ_*.npz)
+
+
+def vr_model():
+    """MLICPlusPlusVbr(config, vr_entbttlnck=True): model_loader.get_model never passes the flag (mlicpp_vbr.py:15)."""
+    from mlic_b200 import models
+    return models.MLICPlusPlusVbr(models.model_config(VR_CASE[0]), name=VR_CASE[0], vr_entbttlnck=True)
+
+
+def load_vr_case():
+    import mlic_b200
+    from oracle import weights
+    name, B, H, W = VR_CASE
+    g = np.load(os.path.join(GOLDEN, f"{name}_VRZ_b{B}_{H}x{W}.npz"))
+    sd = weights.seeded_state_dict(vr_model().state_dict(), int(g["meta"][3]), y_gain=float(g["y_gain"]), sigma_spread=float(g["sigma_spread"]))
+    sd["gaussian_conditional.scale_table"] = mlic_b200.get_scale_table()
+    return g, sd, weights.synthetic_image(B, H, W, seed=2024)
+
+
 def build_model(name, sd, device=None):
     import mlic_b200
     net = mlic_b200.get_model(name)

@@ -124,3 +124,26 @@ def test_set_precision_accepts_per_stage_tuples():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.MlicError):                  # the staged call has no CPU fallback either
             net.set_precision("mixed")(torch.zeros(1, 3, 64, 64))
+
+
+def test_variable_rate_hyper_prior_model_layout_and_tables():
+    """MLICPlusPlusVbr(config, vr_entbttlnck=True): the extra state_dict entries of mlicpp_vbr.py:105-117, the gain -> step network, and
+    the per-step z tables (EntropyBottleneckVbr.update_variable): a finer grid has more bins and still sums to 2^16 per channel."""
+    import numpy as np
+    from conftest import vr_model
+    from mlic_b200 import coder
+    net = vr_model()
+    keys = list(net.state_dict().keys())
+    assert keys[-7:] == [f"gayn2zqstep.{j}.{w}" for j in (0, 2, 4) for w in ("weight", "bias")] + ["lower_bound_zqstep.bound"]
+    assert tuple(net.gayn2zqstep[0].weight.shape) == (10, 1) and tuple(net.gayn2zqstep[4].weight.shape) == (1, 10)
+    assert "gayn2zqstep.0.weight" not in mlic_b200.get_model("MLICPP_S_VBR").state_dict()
+    qs = [net._zqstep(net._scale(s, 0, True)) for s in range(6)]
+    assert all(q >= 0.5 for q in qs) and mlic_b200.get_model("MLICPP_S_VBR")._zqstep(0.5) == 1.0
+    with pytest.raises(ValueError):
+        mlic_b200.models.MLICPlusPlus(mlic_b200.models.model_config("MLICPP_S"), name="MLICPP_S", _vr_entbttlnck=True)
+    c1, l1, o1 = coder.bottleneck_tables(net.entropy_bottleneck, 1.0)
+    c2, l2, o2 = coder.bottleneck_tables(net.entropy_bottleneck, 0.5)
+    assert (l2 > l1).all() and (o2 <= o1).all()
+    for cdf, ln in ((c1, l1), (c2, l2)):
+        for ch in range(0, cdf.shape[0], 17):
+            assert cdf[ch, 0] == 0 and cdf[ch, ln[ch] - 1] == 65536 and (np.diff(cdf[ch, :ln[ch]]) > 0).all()

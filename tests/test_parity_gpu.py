@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import CASES, build_model, load_case, vbr_levels
+from conftest import CASES, VR_CASE, build_model, load_case, load_vr_case, vbr_levels, vr_model
 from oracle import mlic_oracle as mo
 from oracle import weights
 
@@ -46,6 +46,36 @@ def test_fp32_mode_bit_exact_symbols_and_tight_outputs(name, B, H, W):
     d = net.net_decoder_forward(x.cuda())
     np.testing.assert_allclose(d.cpu().numpy(), g["decoder_x_hat"], atol=1e-4, rtol=0)
     assert net.last_launch_count > 100
+
+
+def test_variable_rate_hyper_prior_fp32_bit_exact_and_round_trip():
+    """vr_entbttlnck=True (MLICPlusPlusVbr with EntropyBottleneckVbr + gayn2zqstep, mlicpp_vbr.py:103-117,253-259,553-559): z symbols on
+    the level's own quantisation step, y symbols / CDF indexes and likelihoods against the reference fixture at all six levels
+    (fp32 validation mode: bit-exact), then compress -> decompress through the per-step z tables (bit-identical x_hat)."""
+    g, sd, x = load_vr_case()
+    net = vr_model()
+    net.load_state_dict(sd)
+    net.update(force=True)
+    net = net.cuda().set_precision("fp32")
+    lv0 = int(g["fwd_level"])
+    out = net(x.cuda(), stage=2, s=lv0)
+    np.testing.assert_allclose(out["x_hat"].cpu().numpy(), g["x_hat"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(out["likelihoods"]["z_likelihoods"].cpu().numpy(), g["z_likelihoods"], atol=1e-5, rtol=0)
+    for lv in vbr_levels(g):
+        assert net._zqstep(net._scale(lv, 0, True)) == float(g[f"z_qstep_s{lv}"])
+        c = net.compress(x.cuda(), stage=2, s=lv)
+        assert np.array_equal(c["z_symbols"].cpu().numpy(), g[f"z_symbols_s{lv}"]), lv
+        assert np.array_equal(c["symbols"].cpu().numpy(), g[f"symbols_s{lv}"]), lv
+        assert np.array_equal(c["indexes"].cpu().numpy(), g[f"indexes_s{lv}"]), lv
+        zl = net(x.cuda(), stage=2, s=lv)["likelihoods"]["z_likelihoods"]
+        np.testing.assert_allclose(zl.cpu().numpy(), g[f"z_likelihoods_s{lv}"], atol=1e-5, rtol=0)
+        d = net.decompress(c["strings"], c["shape"], stage=2, s=lv)
+        assert torch.equal(d["x_hat"], c["x_hat"]), lv
+    # stage 1 runs the plain bottleneck (mlicpp_vbr.py:160): same z likelihoods as a model without the branch
+    plain = build_model(VR_CASE[0], {k: v for k, v in sd.items() if not k.startswith(("gayn2zqstep", "lower_bound_zqstep"))}, "cuda").set_precision("fp32")
+    a = net(x.cuda(), stage=1)["likelihoods"]["z_likelihoods"]
+    b = plain(x.cuda(), stage=1)["likelihoods"]["z_likelihoods"]
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("tensor_cores", [False, True])
