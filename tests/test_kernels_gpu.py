@@ -16,7 +16,7 @@ CONV_SHAPES = [  # B, H, W, Cin, N, ks, shuffle
     (1, 24, 40, 192, 192, 1, False), (2, 17, 30, 320, 128, 1, False), (1, 16, 24, 192, 768, 3, True),
     (1, 20, 28, 288, 96, 5, False), (2, 13, 21, 104, 72, 3, False), (1, 16, 16, 64, 12, 3, True),
     (1, 9, 33, 800, 64, 1, False), (1, 34, 60, 480, 1920, 3, True),
-    # large enough for the 2-CTA cluster mode (weight tile multicast); 957 M tiles: the last pair has a single tile
+    # large shapes: 957 M tiles (an odd count: the last CTA pair of the two-SM kernels holds a single tile) and Cin = 320
     (1, 264, 464, 192, 768, 3, True), (1, 136, 240, 320, 256, 3, False),
 ]
 
