@@ -1676,21 +1676,21 @@ __device__ __forceinline__ float gauss_lik(float yq, float sigma, float mu) {
 // that the encoder-side and the decoder-side walks rebuild bit-identical y_hat whatever the compiler fuses elsewhere
 __device__ __forceinline__ float vbr_deq(float sq, float rgain, float mu) { return __fadd_rn(__fmul_rn(sq, rgain), mu); }
 
-template <typename T>
+// I: index type -- int when B*H*W*C < 2^31 (the four divisions per element are 64-bit otherwise: a third of the kernel's instructions)
+template <typename T, typename I>
 __global__ void quant_anchor_kernel(QuantArgs a) {
     const int C = a.C;
-    const long long total = (long long)a.B * a.H * a.W * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long p = i / C;
+    const I total = (I)a.B * a.H * a.W * C;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        I p = i / C;
         int c = (int)(i - p * C);
         int w = (int)(p % a.W);
-        long long q = p / a.W;
+        I q = p / a.W;
         int h = (int)(q % a.H);
         int b = (int)(q / a.H);
-        T* slot = reinterpret_cast<T*>(a.slot.p) + p * a.slot.ld + c;
+        T* slot = reinterpret_cast<T*>(a.slot.p) + (long long)p * a.slot.ld + c;
         if (((h + w) & 1) == 0) { if (a.mode != 3) *slot = from_f<T>(0.f); continue; }
-        const long long pe = a.sq ? (q * (a.W >> 1) + (w >> 1)) : p;       // row of this pixel in the entropy-parameter buffer
+        const long long pe = a.sq ? ((long long)q * (a.W >> 1) + (w >> 1)) : (long long)p;       // row of this pixel in the entropy-parameter buffer
         const float sigma = a.pa[pe * 2 * C + c];
         const float mu = a.pa[pe * 2 * C + C + c];
         float out;
@@ -1702,7 +1702,7 @@ __global__ void quant_anchor_kernel(QuantArgs a) {
             const float sq = (float)a.sym[o];
             out = a.vbr ? vbr_deq(sq, a.rgain, mu) : sq + mu;
         } else {
-            const float y = a.y[p * a.y_ld + c];
+            const float y = a.y[(long long)p * a.y_ld + c];
             if (a.mode == 0) {
                 out = a.vbr ? vbr_deq(rintf((y - mu) * a.gain), a.rgain, mu) : rintf(y - mu) + mu;
             } else {
@@ -1717,22 +1717,22 @@ __global__ void quant_anchor_kernel(QuantArgs a) {
     }
 }
 
-template <typename T>
+// I: index type -- int when B*H*W*C < 2^31 (the four divisions per element are 64-bit otherwise: a third of the kernel's instructions)
+template <typename T, typename I>
 __global__ void quant_nonanchor_kernel(QuantArgs a) {
     const int C = a.C;
-    const long long total = (long long)a.B * a.H * a.W * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        long long p = i / C;
+    const I total = (I)a.B * a.H * a.W * C;
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        I p = i / C;
         int c = (int)(i - p * C);
         int w = (int)(p % a.W);
-        long long q = p / a.W;
+        I q = p / a.W;
         int h = (int)(q % a.H);
         int b = (int)(q / a.H);
         const bool anchor = ((h + w) & 1) == 1;
-        T* slot = reinterpret_cast<T*>(a.slot.p) + p * a.slot.ld + c;
+        T* slot = reinterpret_cast<T*>(a.slot.p) + (long long)p * a.slot.ld + c;
         const float* pp = anchor ? a.pa : a.pn;
-        const long long pe = a.sq ? (q * (a.W >> 1) + (w >> 1)) : p;
+        const long long pe = a.sq ? ((long long)q * (a.W >> 1) + (w >> 1)) : (long long)p;
         const float sigma = pp[pe * 2 * C + c];
         const float mu = pp[pe * 2 * C + C + c];
         if (a.mode == 2) {           // decoder walk: both halves take means_anchor (mlicpp.py:405,418)
@@ -1746,7 +1746,7 @@ __global__ void quant_nonanchor_kernel(QuantArgs a) {
             else { const float sq = (float)a.sym[o]; *slot = from_f<T>(a.vbr ? vbr_deq(sq, a.rgain, mu) : sq + mu); }
             continue;
         }
-        const float y = a.y[p * a.y_ld + c];
+        const float y = a.y[(long long)p * a.y_ld + c];
         if (a.mode == 0) {
             float lik;
             if (a.vbr) {
@@ -1755,7 +1755,7 @@ __global__ void quant_nonanchor_kernel(QuantArgs a) {
             } else {
                 lik = gauss_lik(rintf(y - mu) + mu, sigma, mu);
             }
-            a.lik[p * a.lik_ld + c] = lik;
+            a.lik[(long long)p * a.lik_ld + c] = lik;
             if (!anchor) *slot = from_f<T>(a.vbr ? vbr_deq(rintf((y - mu) * a.gain), a.rgain, mu) : rintf(y - mu) + mu);
         } else if (!anchor) {
             float sq = rintf(y - mu);
@@ -1771,15 +1771,17 @@ void launch_quant_anchor(int bf, const QuantArgs& a, cudaStream_t s) {
     long long total = (long long)a.B * a.H * a.W * a.C;
     if (!total) return;
     int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
-    if (bf) quant_anchor_kernel<bf16><<<blocks, 256, 0, s>>>(a);
-    else quant_anchor_kernel<float><<<blocks, 256, 0, s>>>(a);
+    const bool small = total + (long long)blocks * 256 < 0x7fffffffLL;
+    if (bf) { if (small) quant_anchor_kernel<bf16, int><<<blocks, 256, 0, s>>>(a); else quant_anchor_kernel<bf16, long long><<<blocks, 256, 0, s>>>(a); }
+    else { if (small) quant_anchor_kernel<float, int><<<blocks, 256, 0, s>>>(a); else quant_anchor_kernel<float, long long><<<blocks, 256, 0, s>>>(a); }
 }
 void launch_quant_nonanchor(int bf, const QuantArgs& a, cudaStream_t s) {
     long long total = (long long)a.B * a.H * a.W * a.C;
     if (!total) return;
     int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
-    if (bf) quant_nonanchor_kernel<bf16><<<blocks, 256, 0, s>>>(a);
-    else quant_nonanchor_kernel<float><<<blocks, 256, 0, s>>>(a);
+    const bool small = total + (long long)blocks * 256 < 0x7fffffffLL;
+    if (bf) { if (small) quant_nonanchor_kernel<bf16, int><<<blocks, 256, 0, s>>>(a); else quant_nonanchor_kernel<bf16, long long><<<blocks, 256, 0, s>>>(a); }
+    else { if (small) quant_nonanchor_kernel<float, int><<<blocks, 256, 0, s>>>(a); else quant_nonanchor_kernel<float, long long><<<blocks, 256, 0, s>>>(a); }
 }
 
 // Stand-alone flat version (any layout, elementwise): the GaussianConditional boundary of the C ABI.
