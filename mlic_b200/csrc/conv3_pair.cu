@@ -24,7 +24,7 @@
 
 namespace mlic {
 
-constexpr int CP_TH = 8, CP_TW = 16;
+// (tile shape TH x TW = 128 pixels: CpParams, chosen per launch)
 constexpr int CP_A_BYTES = 128 * 128, CP_B_BYTES = 128 * 128;
 constexpr int CP_STAGE_BYTES = CP_A_BYTES + CP_B_BYTES;
 constexpr int CP_NSTAGE = 5;
@@ -35,11 +35,15 @@ constexpr int CP_SMEM = CP_NSTAGE * CP_STAGE_BYTES + 4 * CP_STG_BYTES + 1024;
 static_assert(CP_SMEM + 512 <= 232448, "shared-memory plan exceeds 227 KB");
 
 struct CpParams {
-    int tilesH, tilesW, ntiles, npairs;     // 8 x 16 pixel tiles; a pair = tiles 2 pp, 2 pp + 1
+    int tilesH, tilesW, ntiles, npairs;     // TH x TW pixel tiles (TH * TW = 128); a pair = tiles 2 pp, 2 pp + 1
+    int TH, TW;
     int tilesN, nitems;                     // 256-column tiles; work items = npairs * tilesN (column tile fastest)
     int kchunks;                            // Cpad / 64
     int Cq;                                 // columns per output tensor map (N / 4 with PixelShuffle, else N)
     const float* bias;                      // [N]
+    int ks, pad;                            // 3 / 1 (the sub-pixel convs) or 1 / 0 (wide 1x1 GEMMs of the entropy model)
+    int BN, N;                              // columns per tile (multiple of 16, <= 256; each CTA stages BN / 2 weight rows) and in all
+    int ck;                                 // 1 | 2: A rows are the anchor | non-anchor pixels of the input, squeezed (5-D map, gemm_tc.cu TcConv::ck)
 };
 struct CpMaps {
     CUtensorMap a, b;
@@ -57,6 +61,13 @@ __device__ __forceinline__ void tma_load_2d_cl(uint32_t dst, const CUtensorMap* 
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d_cl(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 
@@ -82,7 +93,7 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < CP_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 2 * CP_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], (uint32_t)(2 * 4 * ((p.BN + 63) / 64))); }
         for (int s = 0; s < 4; ++s) mbar_init(&stg_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -101,7 +112,7 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
 
     const int tiles_per_img = p.tilesH * p.tilesW;
     const int item_first = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
-    const int ksteps = 9 * p.kchunks;
+    const int ksteps = p.ks * p.ks * p.kchunks;
     // work item -> (pixel-tile pair, column tile); tile of this CTA = 2 pp + rank (an odd tile count leaves the last pair's second CTA
     // a duplicate of the last tile, computed but not stored)
 #define CP_ITEM(item)                                                                         \
@@ -112,7 +123,7 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
     const int img = tix / tiles_per_img;                                                      \
     const int trem = tix - img * tiles_per_img;                                               \
     const int th = trem / p.tilesW, tw = trem - th * p.tilesW;                                \
-    const int h0 = th * CP_TH, w0 = tw * CP_TW;                                               \
+    const int h0 = th * p.TH, w0 = tw * p.TW;                                                 \
     (void)tvalid; (void)h0; (void)w0; (void)img; (void)nt
 
     long long tw0 = 0, tw1 = 0;
@@ -127,15 +138,17 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
             uint32_t ph = 0;
             for (int item = item_first; item < p.nitems; item += item_step) {
                 CP_ITEM(item);
-                const int nrow = nt * 256 + (int)rank * 128;
+                const int nrow = nt * p.BN + (int)rank * (p.BN >> 1);
+                const uint32_t stage_tx = (uint32_t)(CP_A_BYTES + (p.BN >> 1) * 128);
                 int ks = 0;
-                for (int ky = 0; ky < 3; ++ky)
-                    for (int kx = 0; kx < 3; ++kx)
+                for (int ky = 0; ky < p.ks; ++ky)
+                    for (int kx = 0; kx < p.ks; ++kx)
                         for (int k = 0; k < p.kchunks; ++k, ++ks) {
                             CP_TIMED(tw0, mbar_wait(&empty[s], ph ^ 1));
-                            if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * CP_STAGE_BYTES));     // the loads of BOTH CTAs land on this barrier
+                            if (leader) mbar_expect_tx(&full[s], 2u * stage_tx);      // the loads of BOTH CTAs land on this barrier
                             const uint32_t dst = sbase + (uint32_t)(s * CP_STAGE_BYTES);
-                            tma_load_4d_cl(dst, &tm.a, full_leader0 + (uint32_t)(s * 8), k * 64, w0 + kx - 1, h0 + ky - 1, img);
+                            if (p.ck) tma_load_5d_cl(dst, &tm.a, full_leader0 + (uint32_t)(s * 8), k * 64, w0, 0, h0 >> 1, img);
+                            else tma_load_4d_cl(dst, &tm.a, full_leader0 + (uint32_t)(s * 8), k * 64, w0 + kx - p.pad, h0 + ky - p.pad, img);
                             tma_load_2d_cl(dst + CP_A_BYTES, &tm.b, full_leader0 + (uint32_t)(s * 8), ks * 64, nrow);
                             if (++s == CP_NSTAGE) { s = 0; ph ^= 1; }
                         }
@@ -144,8 +157,8 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
-            // instruction descriptor: D = f32, A = B = bf16, K-major, N = 256, M = 256 (128 rows per CTA)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+            // instruction descriptor: D = f32, A = B = bf16, K-major, N = BN, M = 256 (128 rows per CTA)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((256u >> 4) << 24);
             const uint32_t sbase = smem_u32(base);
             int s = 0, it = 0;
             uint32_t ph = 0;
@@ -177,11 +190,12 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
         const uint32_t d_empty_leader0 = mapa_u32(smem_u32(&d_empty[0]), 0);
         uint8_t* sb = stg + (size_t)eb * CP_STG_BYTES;
         const uint32_t sb_s = smem_u32(sb);
+        const int ncol = min(64, p.BN - eb * 64);                  // accumulator columns of this group (<= 0: the group owns none)
         int it = 0;
-        for (int item = item_first; item < p.nitems; item += item_step, ++it) {
+        for (int item = item_first; item < p.nitems && ncol > 0; item += item_step, ++it) {
             CP_ITEM(item);
             const int acc = it & 1;
-            const int col0 = nt * 256 + eb * 64;
+            const int col0 = nt * p.BN + eb * 64;
             // the previous TMA store of this group has finished reading the staging block
             if (gissuer) tma_store_wait_read(0);
             asm volatile("bar.sync %0, 128;" ::"r"(eb + 1) : "memory");
@@ -201,8 +215,13 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
 #pragma unroll 1
             for (int pr = 0; pr < 4; ++pr) {
                 uint32_t raw[16];
-                tmem_ld16(trow + (uint32_t)(pr * 16), raw);
-                tmem_ld_wait();
+                if (pr * 16 < ncol) {
+                    tmem_ld16(trow + (uint32_t)(pr * 16), raw);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) raw[j] = 0u;
+                }
                 if (pr == 3) {                  // accumulator fully read by this warp
                     tcgen05_fence_before();
                     __syncwarp();
@@ -212,7 +231,8 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
                 for (int sub = 0; sub < 2; ++sub) {
                     const int jj = pr * 2 + sub;
                     const uint32_t off = (uint32_t)(r * 128 + ((jj ^ (r & 7)) << 4));
-                    const float4 ba = __ldg(bias4 + jj * 2), bb = __ldg(bias4 + jj * 2 + 1);
+                    const bool cin = col0 + jj * 8 + 8 <= p.N;                 // (a ragged last column tile: nothing beyond N is read or stored)
+                    const float4 ba = cin ? __ldg(bias4 + jj * 2) : make_float4(0.f, 0.f, 0.f, 0.f), bb = cin ? __ldg(bias4 + jj * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float2 v[4];
                     v[0] = __fadd2_rn(make_float2(__uint_as_float(raw[sub * 8 + 0]), __uint_as_float(raw[sub * 8 + 1])), make_float2(ba.x, ba.y));
                     v[1] = __fadd2_rn(make_float2(__uint_as_float(raw[sub * 8 + 2]), __uint_as_float(raw[sub * 8 + 3])), make_float2(ba.z, ba.w));
@@ -238,7 +258,7 @@ conv3_pair_kernel(const __grid_constant__ CpMaps tm, const CpParams p, unsigned 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync %0, 128;" ::"r"(eb + 1) : "memory");
             if (gissuer) {
-                if (tvalid) tma_store_4d(&tm.o[g], sb, cc, w0, h0, img);
+                if (tvalid && col0 < p.N) tma_store_4d(&tm.o[g], sb, cc, w0, h0, img);
                 tma_store_commit();
             }
         }
@@ -264,13 +284,29 @@ typedef CUresult (*PFN_encodeTiled_cp)(CUtensorMap*, CUtensorMapDataType, cuuint
 static thread_local char g_cp_err[256] = "";
 const char* conv3_pair_last_error() { return g_cp_err; }
 
+static int cp_pick_bn(int N) {
+    // one tile: N rounded up to 32 (16 weight rows per CTA; the last 64-column store block is clipped by the output map).  Several tiles:
+    // a multiple of 64, so that every epilogue group stores a whole 64-column block of ITS tile, the one that wastes the fewest columns
+    if (N <= 256) return (N + 31) / 32 * 32;
+    int best = 256, waste = (N + 255) / 256 * 256 - N;
+    for (int bn = 192; bn >= 128; bn -= 64) {
+        const int w = (N + bn - 1) / bn * bn - N;
+        if (w < waste) { waste = w; best = bn; }
+    }
+    return best;
+}
+
 bool conv3_pair_supported(const Conv3PairArgs& a) {
     if (!a.in || !a.w || !a.bias || !a.out) return false;
     if (a.B <= 0 || a.H <= 0 || a.W <= 0) return false;
-    if (a.Cin < 64 || (a.Cin % 64) != 0 || a.Cin > 1024) return false;
-    if (a.N < 256 || (a.N % 256) != 0) return false;
+    if (a.ks != 1 && a.ks != 3) return false;
+    if (a.Cin < 8 || (a.Cin % 8) != 0 || a.Cpad < a.Cin || (a.Cpad % 64) != 0 || a.Cpad > 2048) return false;
+    if (a.ks == 3 && (a.Cpad != a.Cin || (a.N % 256) != 0)) return false;
+    if (a.N < 64 || (a.N % 8) != 0) return false;
     if (a.act != ACT_NONE && a.act != ACT_GELU) return false;
-    if (a.shuffle && ((a.N / 4) % 64) != 0) return false;
+    if (a.shuffle && (a.ks != 3 || ((a.N / 4) % 64) != 0)) return false;
+    if (a.res_inplace && a.ks != 3) return false;
+    if (a.ck && (a.ks != 1 || (a.ck != 1 && a.ck != 2) || (a.H % 2) != 0 || (a.W % 2) != 0)) return false;
     if (((uintptr_t)a.in % 16) != 0 || (a.ld % 8) != 0 || ((uintptr_t)a.out % 16) != 0 || (a.out_ld % 8) != 0 || ((uintptr_t)a.w % 16) != 0) return false;
     if (((uintptr_t)a.bias % 16) != 0) return false;
     return true;
@@ -333,29 +369,53 @@ int launch_conv3_pair(const Conv3PairArgs& a, cudaStream_t s) {
     memset(&tm, 0, sizeof tm);
     CpParams p;
     memset(&p, 0, sizeof p);
-    p.tilesH = (a.H + CP_TH - 1) / CP_TH; p.tilesW = (a.W + CP_TW - 1) / CP_TW;
+    // GEMM rows: the output pixels; checkerboard mode: the anchor | non-anchor pixels of the input in squeezed order [B][H][W/2]
+    const int Wout = a.ck ? a.W / 2 : a.W;
+    {   // tile shape: the one with the fewest tiles (a flat [1, 1, M] matrix takes 1 x 128; checkerboard rows need an even TH)
+        const int cand[4][2] = {{8, 16}, {4, 32}, {2, 64}, {1, 128}};
+        long long best = -1;
+        for (int i = 0; i < (a.ck ? 3 : 4); ++i) {
+            const long long t = (long long)((a.H + cand[i][0] - 1) / cand[i][0]) * ((Wout + cand[i][1] - 1) / cand[i][1]);
+            if (best < 0 || t < best) { best = t; p.TH = cand[i][0]; p.TW = cand[i][1]; }
+        }
+    }
+    p.tilesH = (a.H + p.TH - 1) / p.TH; p.tilesW = (Wout + p.TW - 1) / p.TW;
     const long long nt = (long long)a.B * p.tilesH * p.tilesW;
-    p.tilesN = a.N / 256;
+    p.ks = a.ks; p.pad = a.ks / 2; p.N = a.N; p.ck = a.ck;
+    p.BN = a.ks == 3 ? 256 : cp_pick_bn(a.N);
+    p.tilesN = (a.N + p.BN - 1) / p.BN;
     if (nt <= 0 || nt * p.tilesN > 0x3fffffffLL) { snprintf(g_cp_err, sizeof g_cp_err, "conv3_pair: tile count out of range"); return 3; }
     p.ntiles = (int)nt; p.npairs = (p.ntiles + 1) / 2;
     p.nitems = p.npairs * p.tilesN;
-    p.kchunks = a.Cin / 64;
+    p.kchunks = a.Cpad / 64;
     p.Cq = a.shuffle ? a.N / 4 : a.N;
     p.bias = a.bias;
     const cuuint32_t estr4[4] = {1, 1, 1, 1};
-    {
+    if (a.ck) {
+        // anchor (ck 1): row h keeps w = 2j + 1 - (h & 1); non-anchor (ck 2): w = 2j + (h & 1)   (anchor = (h + w) odd); dims (c, j, h & 1, h >> 1, b)
+        const size_t ld = (size_t)a.ld;
+        const bf16* basep = reinterpret_cast<const bf16*>(a.in) + (a.ck == 1 ? ld : 0);
+        const size_t hp_stride = a.ck == 1 ? ((size_t)a.W - 1) * ld : ((size_t)a.W + 1) * ld;
+        cuuint64_t dims[5] = {(cuuint64_t)a.Cin, (cuuint64_t)(a.W / 2), 2, (cuuint64_t)(a.H / 2), (cuuint64_t)a.B};
+        cuuint64_t strides[4] = {(cuuint64_t)(2 * ld) * 2, (cuuint64_t)hp_stride * 2, (cuuint64_t)(2 * (size_t)a.W * ld) * 2, (cuuint64_t)a.H * a.W * ld * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)p.TW, 2, (cuuint32_t)(p.TH / 2), 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(basep), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(g_cp_err, sizeof g_cp_err, "conv3_pair: encode(A, checkerboard) failed: %d", (int)r); return 2; }
+    } else {
         cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
         cuuint64_t strides[3] = {(cuuint64_t)a.ld * 2, (cuuint64_t)a.W * a.ld * 2, (cuuint64_t)a.H * a.W * a.ld * 2};
-        cuuint32_t box[4] = {64, CP_TW, CP_TH, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
         CUresult r = enc(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in), dims, strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { snprintf(g_cp_err, sizeof g_cp_err, "conv3_pair: encode(A) failed: %d", (int)r); return 2; }
     }
     {
-        const cuuint64_t Ktot = (cuuint64_t)9 * a.Cin;
+        const cuuint64_t Ktot = (cuuint64_t)a.ks * a.ks * a.Cpad;
         cuuint64_t dims[2] = {Ktot, (cuuint64_t)a.N};
         cuuint64_t strides[1] = {Ktot * 2};
-        cuuint32_t box[2] = {64, 128};
+        cuuint32_t box[2] = {64, (cuuint32_t)(p.BN / 2)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tm.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -368,11 +428,11 @@ int launch_conv3_pair(const Conv3PairArgs& a, cudaStream_t s) {
         for (int g = 0; g < ng; ++g) {          // group g = 2r + s -> output pixel (2h + r, 2w + s)
             const size_t OW = 2 * (size_t)a.W, OH = 2 * (size_t)a.H;
             bf16* bp = a.shuffle ? ob + ((size_t)(g >> 1) * OW + (size_t)(g & 1)) * ld : ob;
-            cuuint64_t dims[4] = {(cuuint64_t)p.Cq, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+            cuuint64_t dims[4] = {(cuuint64_t)p.Cq, (cuuint64_t)Wout, (cuuint64_t)a.H, (cuuint64_t)a.B};
             cuuint64_t strides[3];
             if (a.shuffle) { strides[0] = 2 * ld * 2; strides[1] = 2 * OW * ld * 2; strides[2] = OH * OW * ld * 2; }
-            else { strides[0] = ld * 2; strides[1] = (cuuint64_t)a.W * ld * 2; strides[2] = (cuuint64_t)a.H * a.W * ld * 2; }
-            cuuint32_t box[4] = {64, CP_TW, CP_TH, 1};
+            else { strides[0] = ld * 2; strides[1] = (cuuint64_t)Wout * ld * 2; strides[2] = (cuuint64_t)a.H * Wout * ld * 2; }
+            cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
             CUresult r = enc(&tm.o[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bp, dims, strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { snprintf(g_cp_err, sizeof g_cp_err, "conv3_pair: encode(out %d) failed: %d", g, (int)r); return 2; }

@@ -105,6 +105,7 @@ struct mlic_engine {
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
     int pair = 1;            // fuse: DepthWiseConv / (I)GDN-tail blocks with C = N = 192 | 128 on the two-SM kernel (ds_pair.cu)
     int halo5 = 1;           // 5x5 convs with N <= 128 on the halo-patch kernel (conv_halo.cu)
+    int wide_pair = getenv("MLIC_WIDE_PAIR") ? atoi(getenv("MLIC_WIDE_PAIR")) : 1;      // wide 1x1 GEMMs on the two-SM kernel (conv3_pair.cu)
     float z_qstep = 1.0f;    // quantisation step of the hyper prior (EntropyBottleneckVbr, vr_entbttlnck=True); 1: the plain EntropyBottleneck
 
     std::vector<void*> dev_allocs;
@@ -629,11 +630,17 @@ struct mlic_engine {
             }
             // wide dense 3x3 convs (the sub-pixel convs of g_s): two-SM kernel, each CTA stages half of the weight tile (conv3_pair.cu)
             const bool res_inplace = e.res && e.res == e.out && e.res_ld == e.out_ld;
-            if (sup && pair && !prod && !o.ck && w->ks == 3 && stride == 1 && pad == 1 && (!e.res || res_inplace) && !e.gdn && !e.out2 && !e.out_f32 && !e.nchw &&
-                !e.premask && !e.postmask && w->Cpad == w->Cin) {
+            // ... and the wide 1x1 GEMMs whose weight matrix does not fit one SM (EntropyParameters / LRP first layers, the q|k|v projection):
+            // re-streaming the weights per 128-pixel tile is what bounds them (L2 -> shared memory), a CTA pair stages half each
+            // (up to two column tiles: with more, the activation tile is re-read per column tile and the one-SM kernel's wider spread wins: q|k|v, N = 864)
+            const bool wide1 = w->ks == 1 && stride == 1 && pad == 0 && !e.res && w->N >= 192 && w->N <= 384 && w->Cin >= 256 && !w->shuffle &&
+                               (size_t)w->Cpad * w->N * 2 > 80 * 1024 && in.B * e.Hout * e.Wout >= 4 * 148 * 128 && wide_pair;
+            const bool conv3 = w->ks == 3 && stride == 1 && pad == 1 && (!e.res || res_inplace) && w->Cpad == w->Cin && !o.ck;
+            if (sup && pair && !prod && (conv3 || wide1) && !e.gdn && !e.out2 && !e.out_f32 && !e.nchw && !e.premask && !e.postmask) {
                 Conv3PairArgs a;
                 memset(&a, 0, sizeof a);
                 a.in = in.p; a.B = in.B; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ld = in.ld;
+                a.ks = w->ks; a.Cpad = w->Cpad; a.ck = o.ck;
                 a.w = w->wbf; a.bias = w->bias; a.N = w->N; a.act = e.act; a.shuffle = w->shuffle; a.out = e.out; a.out_ld = e.out_ld;
                 a.res_inplace = res_inplace ? 1 : 0;
                 if (conv3_pair_supported(a)) {
@@ -641,7 +648,7 @@ struct mlic_engine {
                     if (profile) {
                         cudaEventRecord(next_event(), st);
                         ev1 = next_event();
-                        ev_flops.push_back(2.0 * (double)in.B * e.Hout * e.Wout * (double)w->N * (double)(9 * w->Cin));
+                        ev_flops.push_back(2.0 * (double)in.B * e.Hout * e.Wout * (double)w->N * (double)(w->ks * w->ks * w->Cin));
                     }
                     int r = launch_conv3_pair(a, st);
                     if (ev1) cudaEventRecord(ev1, st);
@@ -649,7 +656,7 @@ struct mlic_engine {
                     ++launches;
                     if (trace) {
                         char lab[256];
-                        snprintf(lab, sizeof lab, "%s [pair conv3 M=%d N=%d K=9x%d]", key.c_str(), in.B * e.Hout * e.Wout, w->N, w->Cin);
+                        snprintf(lab, sizeof lab, "%s [pair conv%d M=%d N=%d K=%dx%d]", key.c_str(), w->ks, in.B * e.Hout * e.Wout, w->N, w->ks * w->ks, w->Cin);
                         tr(lab);
                     }
                     return true;

@@ -119,10 +119,13 @@ bool ds_pair_supported(const DsPairArgs& a);
 int launch_ds_pair(const DsPairArgs& a, cudaStream_t s);      // 0 ok
 const char* ds_pair_last_error();
 
-// ---- two-SM (cta_group::2) dense 3x3 convolution (conv3_pair.cu), bf16 NHWC, stride 1, pad 1: Cin % 64 == 0, N % 256 == 0
+// ---- two-SM (cta_group::2) dense convolution (conv3_pair.cu), bf16 NHWC, stride 1: 3x3 pad 1 (Cin % 64 == 0, N % 256 == 0: the sub-pixel
+//      convs of g_s) or 1x1 (any Cin % 8, N % 8: the wide GEMMs of the entropy model whose weights do not fit one SM)
 struct Conv3PairArgs {
     const void* in; int B, H, W, Cin, ld;   // input view
-    const void* w;                          // bf16 [N][9 * Cin], K-major, tap-major (the packing of TcConv::w; PixelShuffle folded into the column order)
+    int ks, Cpad;                           // 3 | 1; channels per tap in `w` (Cin rounded up to 64)
+    int ck;                                 // 1x1 only: 1 | 2 = GEMM rows are the anchor | non-anchor pixels of the input, squeezed ([B][H][W/2]), out likewise
+    const void* w;                          // bf16 [N][ks * ks * Cpad], K-major, tap-major (the packing of TcConv::w; PixelShuffle folded into the column order)
     const float* bias;                      // [N]
     int N, act;                             // ACT_NONE | ACT_GELU
     int shuffle;                            // 1: PixelShuffle(2): out is [B][2H][2W][N / 4], (N / 4) % 64 == 0

@@ -133,6 +133,21 @@ def test_linear_attention_kernels(B, H, W, D, heads, par_kv, par_q):
     torch.testing.assert_close(outb.float(), refb, atol=3e-3 * float(refb.abs().max()) + 1e-4, rtol=2e-2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,N", [(12, 68, 120, 352, 224), (24, 68, 60, 960, 320), (48, 37, 53, 264, 200)])
+def test_wide_1x1_gemm_two_sm_kernel(B, H, W, Cin, N):
+    """conv3_pair.cu with ks = 1: the wide 1x1 GEMMs of the entropy model (EntropyParameters / LRP first layers) on a CTA pair, each CTA
+    staging half of the weight rows; one column tile (N = 224: a 32-column tail group), two (N = 320: 192 + 128) and a ragged N / Cin."""
+    torch.manual_seed(8)
+    x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, Cin, 1, 1) / Cin ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(N) * 0.1
+    out, _ = ops.conv2d_nhwc(x, w, b, 1, 0, "gelu", False, None, tensor_cores=2)
+    one, _ = ops.conv2d_nhwc(x, w, b, 1, 0, "gelu", False, None, tensor_cores=1)
+    ref = _torch_conv(x, w, b, 1, "gelu", False, None)
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=1e-2)
+    assert torch.equal(out, one)                       # same operands, same accumulation order
+
+
 def test_gaussian_conditional_kernel_bit_exact_indexes_and_symbols():
     g = torch.Generator().manual_seed(3)
     n = 1 << 18

@@ -216,6 +216,27 @@ def test_mixed_precision_equals_its_stages():
     assert net.set_precision(("bf16", "bf16", "bf16")).precision == "bf16"
 
 
+def test_two_sm_gemms_of_the_slice_loop_change_no_bit(monkeypatch):
+    """At the bench batch the first layers of EntropyParameters (checkerboard-squeezed rows: the 5-D TMA gather) and of LRP run on the
+    two-SM GEMM (conv3_pair.cu, ks = 1); with MLIC_WIDE_PAIR=0 they run on the one-SM kernel.  Same operands and accumulation order:
+    the whole forward must come out bit for bit the same (10 images of 1920x1088, above the kernel's pixel threshold)."""
+    import mlic_b200
+    name, H, W, B = "MLICPP_L", 1088, 1920, 10
+    x = weights.synthetic_image(B, H, W, seed=11, kind="rand").cuda()
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MLIC_WIDE_PAIR", flag)
+        net = mlic_b200.get_model(name)
+        net.load_state_dict(weights.seeded_state_dict(net.state_dict(), 1234, y_gain=8.0, sigma_spread=3.0))
+        net.update(force=True)
+        net = net.cuda().set_precision("bf16")
+        o = net(x, taps=("y_hat",))
+        outs.append((o["y_hat"].clone(), o["likelihoods"]["y_likelihoods"].clone(), o["x_hat"].clone(), net.last_launch_count))
+        del net
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_full_size_properties(precision):
     """BASELINE size (MLICPP_L, 1920x1088): size-independent properties -- determinism, batch invariance (images are

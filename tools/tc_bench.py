@@ -27,6 +27,13 @@ SHAPES = [  # name, B, H, W, Cin, N, ks, shuffle
     ("reproj5x5 160->96 @68x120 b32", 32, 68, 120, 160, 96, 5, False),
     ("reproj5x5 32->64 @68x120 b32", 32, 68, 120, 32, 64, 5, False),
     ("reproj5x5 96->96 ragged @13x21 b3", 3, 13, 21, 96, 96, 5, False),
+    ("wide1x1 lrp0 640->224 @68x120 b32", 32, 68, 120, 640, 224, 1, False),
+    ("wide1x1 lrp0 352->224 @68x120 b32", 32, 68, 120, 352, 224, 1, False),
+    ("wide1x1 ep0 960->320 @68x60 b32", 32, 68, 60, 960, 320, 1, False),
+    ("wide1x1 ep2 320->256 @68x60 b32", 32, 68, 60, 320, 256, 1, False),
+    ("wide1x1 qkv 288->864 @68x120 b32", 32, 68, 120, 288, 864, 1, False),
+    ("wide1x1 pw 320->320 @68x120 b32", 32, 68, 120, 320, 320, 1, False),
+    ("wide1x1 ragged 264->200 @37x53 b48", 48, 37, 53, 264, 200, 1, False),
 ]
 check = "--check" in sys.argv
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
@@ -48,6 +55,10 @@ for name, B, H, W, Cin, N, ks, sh in SHAPES:
         outp, msp = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, None, 2, 20)
         ref1, _ = (out, ms) if res is None else ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, None, 1, 2)
         msg += f" | two-SM {msp*1e3:9.1f} us {flops/msp/1e9:8.1f} TFLOP/s maxdiff vs one-SM {(outp.float()-ref1.float()).abs().max().item():.3e}"
+    if ks == 1 and N >= 192 and Cin >= 256 and B * H * W >= 4 * 148 * 128:
+        outp, msp = ops.conv2d_nhwc(x, w, b, 1, 0, "gelu", False, None, 2, 20)
+        ref1, ms1 = ops.conv2d_nhwc(x, w, b, 1, 0, "gelu", False, None, 1, 20)
+        msg += f" | two-SM {msp*1e3:9.1f} us vs one-SM {ms1*1e3:9.1f} us (no res) maxdiff {(outp.float()-ref1.float()).abs().max().item():.3e}"
     if ks == 5 and N <= 128:
         outp, msp = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, 2, 20)
         ref1, ms1 = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, 1, 20)
