@@ -910,20 +910,26 @@ __global__ void __launch_bounds__(DwT<S>::THREADS, 2) dwconv3x3_tma_kernel(const
     // descriptor the TMA thread left in the slot (the three integer divisions per item and warp were ~15 % of the instructions)
     const int cstep = (int)(gridDim.x % (unsigned)chunks);
     int ccur = (int)(blockIdx.x % (unsigned)chunks);
+    // the 9 taps + bias of the channel pair come from global memory (L2).  The launcher makes the grid a multiple of the chunk count
+    // whenever it can: cstep is then 0, every block stays on ONE 64-channel chunk and loads its taps once (per item, the ten loads with
+    // their 64-bit address arithmetic were ~100 of the ~700 warp instructions of an item)
+    float2 w2[9], b2;
+    auto load_w = [&](int cq) {
+        const int cn = cq * 64 + 2 * lane;
+        const bool ok = cn < C;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w2[t] = ok ? __ldg(reinterpret_cast<const float2*>(w9 + (size_t)t * C + cn)) : make_float2(0.f, 0.f);
+        b2 = ok ? __ldg(reinterpret_cast<const float2*>(bias + cn)) : make_float2(0.f, 0.f);
+    };
+    load_w(ccur);
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
         const int slot = n % TT::SLOTS;
         const uint32_t ph = (uint32_t)(n / TT::SLOTS) & 1u;
-        // the 9 taps + bias of the item's channel pair come from global memory (L2), requested before the wait for the patch
-        float2 w2[9], b2;
-        {
-            const int cn = ccur * 64 + 2 * lane;
-            const bool ok = cn < C;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) w2[t] = ok ? __ldg(reinterpret_cast<const float2*>(w9 + (size_t)t * C + cn)) : make_float2(0.f, 0.f);
-            b2 = ok ? __ldg(reinterpret_cast<const float2*>(bias + cn)) : make_float2(0.f, 0.f);
+        if (cstep != 0 && n > 0) {
+            ccur += cstep;
+            if (ccur >= chunks) ccur -= chunks;
+            load_w(ccur);
         }
-        ccur += cstep;
-        if (ccur >= chunks) ccur -= chunks;
         mbar_wait(&full_bar[slot], ph);
         const int4 ds = item_desc[slot];
         const int cc = ds.x, b = ds.y, oh0 = ds.z + rh * TT::R, ow0 = ds.w;
@@ -935,15 +941,25 @@ __global__ void __launch_bounds__(DwT<S>::THREADS, 2) dwconv3x3_tma_kernel(const
         bf16* orow = out + (((size_t)b * Ho + oh0) * Wo + ow) * old + c;
         const int nrows = cok ? Ho - oh0 : 0;                                   // rows of this warp's share inside the image (<= 0: none / channel tail)
         const bool okq[2] = {ow < Wo, ow + 1 < Wo};
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * TT::BYTES) + (size_t)((rh * TT::R * S) * TT::IW + 2 * pw * S) * 32 + lane;
+        // explicit shared-state-space loads with immediate offsets (the first version read the ring through a generic pointer: generic LD plus
+        // R2UR / IMAD / LEA address arithmetic were 38 % of the kernel's warp instructions, profiles/r02_ncu_dwtma.txt), the words of input row
+        // iy + 1 requested before the arithmetic of row iy
+        const uint32_t rp = smem_u32(ring) + (uint32_t)(slot * TT::BYTES + (((rh * TT::R * S) * TT::IW + 2 * pw * S) * 32 + lane) * 4);
         float2 acc[TT::R][2];
 #pragma unroll
         for (int oy = 0; oy < TT::R; ++oy) { acc[oy][0] = b2; acc[oy][1] = b2; }
+        uint32_t wv[2][TT::NX];
+#pragma unroll
+        for (int j = 0; j < TT::NX; ++j) wv[0][j] = lds32(rp + (uint32_t)(j * 128));
 #pragma unroll
         for (int iy = 0; iy < TT::IHW; ++iy) {
+            if (iy + 1 < TT::IHW) {
+#pragma unroll
+                for (int j = 0; j < TT::NX; ++j) wv[(iy + 1) & 1][j] = lds32(rp + (uint32_t)(((iy + 1) * TT::IW + j) * 128));
+            }
             float2 x[TT::NX];
 #pragma unroll
-            for (int j = 0; j < TT::NX; ++j) x[j] = bf2_to_f2(rp[(size_t)(iy * TT::IW + j) * 32]);
+            for (int j = 0; j < TT::NX; ++j) x[j] = bf2_to_f2(wv[iy & 1][j]);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 if ((iy - ky) >= 0 && ((iy - ky) % S) == 0 && (iy - ky) / S < TT::R) {
@@ -992,7 +1008,8 @@ static int launch_dw_tma(const Act& in, const Act& out, const float* w9, const f
     static bool attr[TC_MAX_DEV] = {};
     if (!attr[dev]) { cudaFuncSetAttribute(dwconv3x3_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[dev] = true; }
     const int num_sms = dev_sms(dev);
-    const int grid = (int)std::min<long long>(nitems, 2LL * num_sms);
+    int grid = (int)std::min<long long>(nitems, 2LL * num_sms);
+    if (grid >= 2 * chunks) grid = grid / chunks * chunks;        // a block then stays on one channel chunk: taps loaded once (see the kernel)
     dwconv3x3_tma_kernel<S><<<grid, TT::THREADS, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
     return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
