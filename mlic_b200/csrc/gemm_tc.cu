@@ -869,7 +869,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
 template <int S> struct DwT { static constexpr int TH = S == 1 ? 8 : 4, TW = 16, IH = TH * S + 2, IW = TW * S + 2, NX = S == 1 ? 4 : 5,
                                                    RH = MLIC_DW_RH, R = TH / RH, IHW = (R - 1) * S + 3, NCW = 8 * RH, THREADS = (NCW + 1) * 32,
                                                    SLOTS = S == 1 ? (RH == 2 ? 3 : 4) : 2, BYTES = IH * IW * 128; };
-template <int S>
+template <int S, bool GELU>
 __global__ void __launch_bounds__(DwT<S>::THREADS, 2) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap, int C, bf16* __restrict__ out, int Ho,
                                                             int Wo, int old, const float* __restrict__ w9, const float* __restrict__ bias,
                                                             int act, int tilesW, int tilesH, int chunks, int nitems) {
@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(DwT<S>::THREADS, 2) dwconv3x3_tma_kernel(const
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     float2 v = acc[oy][q];
-                    if (act == ACT_GELU) v = gelu2(v);
+                    if (GELU) v = gelu2(v);
                     if (oy < nrows && okq[q]) {
                         __nv_bfloat162 hv = __floats2bfloat162_rn(v.x, v.y);
                         *reinterpret_cast<uint32_t*>(orow + (q ? old : 0)) = *reinterpret_cast<uint32_t*>(&hv);
@@ -1006,11 +1006,16 @@ static int launch_dw_tma(const Act& in, const Act& out, const float* w9, const f
     const int smem = TT::SLOTS * TT::BYTES + 128;
     const int dev = cur_dev();
     static bool attr[TC_MAX_DEV] = {};
-    if (!attr[dev]) { cudaFuncSetAttribute(dwconv3x3_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[dev] = true; }
+    if (!attr[dev]) {
+        cudaFuncSetAttribute(dwconv3x3_tma_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(dwconv3x3_tma_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr[dev] = true;
+    }
     const int num_sms = dev_sms(dev);
     int grid = (int)std::min<long long>(nitems, 2LL * num_sms);
     if (grid >= 2 * chunks) grid = grid / chunks * chunks;        // a block then stays on one channel chunk: taps loaded once (see the kernel)
-    dwconv3x3_tma_kernel<S><<<grid, TT::THREADS, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
+    if (act == ACT_GELU) dwconv3x3_tma_kernel<S, true><<<grid, TT::THREADS, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
+    else dwconv3x3_tma_kernel<S, false><<<grid, TT::THREADS, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
     return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 // bf16 NHWC depthwise 3x3 through the TMA-fed kernel; non-zero: not taken (the caller falls back to the staged kernel)
