@@ -104,7 +104,7 @@ struct mlic_engine {
     int stages = 7;          // bit 0: g_a, bit 1: h_a + EntropyBottleneck + h_s + slice loop, bit 2: g_s (row-band sharding runs them apart)
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
     int pair = 1;            // fuse: DepthWiseConv / (I)GDN-tail blocks with C = N = 192 | 128 on the two-SM kernel (ds_pair.cu)
-    int halo5 = 1;           // 5x5 convs with N <= 128 on the halo-patch kernel (conv_halo.cu)
+    int halo5 = getenv("MLIC_HALO5") ? atoi(getenv("MLIC_HALO5")) : 2;      // 5x5 convs with N <= 128 on the halo-patch kernels (conv_halo.cu): 1 pixels as M, 2 roles swapped (weights as M, 256 pixels as N)
     int wide_pair = getenv("MLIC_WIDE_PAIR") ? atoi(getenv("MLIC_WIDE_PAIR")) : 1;      // wide 1x1 GEMMs on the two-SM kernel (conv3_pair.cu)
     float z_qstep = 1.0f;    // quantisation step of the hyper prior (EntropyBottleneckVbr, vr_entbttlnck=True); 1: the plain EntropyBottleneck
 
@@ -609,6 +609,8 @@ struct mlic_engine {
                 memset(&a, 0, sizeof a);
                 a.in = in.p; a.B = in.B; a.H = in.H; a.W = in.W; a.Cin = in.C; a.ld = in.ld;
                 a.w = w->wbf; a.Cpad = w->Cpad; a.bias = w->bias; a.N = w->N; a.ks = 5; a.out = e.out; a.out_ld = e.out_ld;
+                // roles swapped (256 pixels per tile) once the 128-pixel tiles would need a second wave; the two kernels agree bit for bit
+                a.swap = halo5 == 3 || (halo5 == 2 && (long long)in.B * ((in.H + 7) / 8) * ((in.W + 15) / 16) > 148);
                 if (conv_halo_supported(a)) {
                     cudaEvent_t ev1 = nullptr;
                     if (profile) {
@@ -1559,7 +1561,7 @@ int mlic_conv2d_nhwc(int precision, int tensor_cores, const void* in, int B, int
     e.rc = 0;
     e.pack_conv_raw("w", weight, bias, N, Cin, ks, shuffle);
     if (e.rc) return e.rc;
-    e.bf = precision == MLIC_PREC_BF16; e.use_tc = tensor_cores != 0; e.pair = tensor_cores == 2; e.halo5 = tensor_cores == 2; e.dry = false; e.st = (cudaStream_t)cuda_stream;      // 2: the two-SM kernels where they apply
+    e.bf = precision == MLIC_PREC_BF16; e.use_tc = tensor_cores != 0; e.pair = tensor_cores >= 2; e.halo5 = tensor_cores == 2 ? 1 : tensor_cores == 3 ? 3 : 0; e.dry = false; e.st = (cudaStream_t)cuda_stream;      // 2: the two-SM kernels where they apply
     if (e.bf && e.use_tc && tc_init()) return fail("%s", tc_last_error());
     Act a; a.p = const_cast<void*>(in); a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin;
     const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;

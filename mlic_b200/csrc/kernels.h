@@ -143,6 +143,7 @@ struct ConvHaloArgs {
     const float* bias;                      // [N] or null
     int N, ks;
     void* out; int out_ld;
+    int swap;                               // 1: roles swapped (weights as the M operand, 256 pixels as N: conv_halo_t_kernel)
 };
 bool conv_halo_supported(const ConvHaloArgs& a);
 int launch_conv_halo(const ConvHaloArgs& a, cudaStream_t s);        // 0 ok

@@ -82,15 +82,17 @@ def test_conv3x3_two_sm_kernel(B, H, W, Cin, N, shuffle, act):
     assert float((out != one).float().mean()) < 0.02
 
 
-@pytest.mark.parametrize("B,H,W,Cin,N", [(1, 68, 120, 288, 96), (3, 13, 21, 96, 96), (2, 17, 30, 32, 64), (1, 9, 40, 160, 96)])
-def test_conv5x5_column_shifted_patch_kernel(B, H, W, Cin, N):
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("B,H,W,Cin,N", [(1, 68, 120, 288, 96), (3, 13, 21, 96, 96), (2, 17, 30, 32, 64), (1, 9, 40, 160, 96), (2, 33, 70, 104, 72)])
+def test_conv5x5_column_shifted_patch_kernel(B, H, W, Cin, N, variant):
     """conv_halo.cu (the 5x5 re-projections of the global contexts: activations staged once per (chunk, kx), the row taps are aligned UMMA
-    descriptors into the patch): against torch fp32 on the bf16-rounded operands and against the plain implicit-GEMM kernel."""
+    descriptors into the patch; variant 2 = pixels as the M operand, 3 = roles swapped: weights as M, 256 pixels as N, direct NHWC stores):
+    against torch fp32 on the bf16-rounded operands and against the plain implicit-GEMM kernel."""
     torch.manual_seed(6)
     x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16)
     w = (torch.randn(N, Cin, 5, 5) / (Cin * 25) ** 0.5).to(torch.bfloat16).float()
     b = torch.randn(N) * 0.1
-    out, _ = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, tensor_cores=2)
+    out, _ = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, tensor_cores=variant)
     one, _ = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, tensor_cores=1)
     ref = _torch_conv(x, w, b, 5, None, False, None)
     torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=1e-2)

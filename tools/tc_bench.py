@@ -62,10 +62,11 @@ for name, B, H, W, Cin, N, ks, sh in SHAPES:
     if ks == 5 and N <= 128:
         outp, msp = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, 2, 20)
         ref1, ms1 = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, 1, 20)
-        msg += f" | halo-patch {msp*1e3:9.1f} us vs plain {ms1*1e3:9.1f} us (no act / res) maxdiff {(outp.float()-ref1.float()).abs().max().item():.3e}"
+        outt, mst = ops.conv2d_nhwc(x, w, b, 1, 2, None, False, None, 3, 20)
+        msg += f" | swapped {mst*1e3:9.1f} us  halo-patch {msp*1e3:9.1f} us  plain {ms1*1e3:9.1f} us (no act / res) maxdiff {(outp.float()-ref1.float()).abs().max().item():.3e} swapped vs halo {(outt.float()-outp.float()).abs().max().item():.3e} differ {float((outt != outp).float().mean()):.2e}"
         if check:
             y = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().cuda(), b.cuda(), padding=2).permute(0, 2, 3, 1)
-            msg += f" vs torch {(outp.float()-y).abs().max().item():.3e}"
+            msg += f" vs torch {(outp.float()-y).abs().max().item():.3e} / {(outt.float()-y).abs().max().item():.3e}"
     if check:
         ref, ms2 = ops.conv2d_nhwc(x, w, b, 1, ks // 2, "gelu", sh, res, False, 2)
         d = (out.float() - ref.float()).abs().max().item()
