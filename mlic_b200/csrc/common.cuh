@@ -19,6 +19,14 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_HALF_TANH = 2 };
 enum { PAR_NONE = 0, PAR_ANCHOR = 1, PAR_NONANCHOR = 2 };
 enum { GDN_NONE = 0, GDN_FWD = 1, GDN_INV = 2 };
 
+// Programmatic dependent launch: every kernel starts with pdl_wait() -- it blocks until the preceding grids of the stream have
+// completed and flushed (a no-op for a plain launch), then lets the next grid of the stream be scheduled so that its own launch
+// latency and prologue overlap this grid's execution (that grid again waits here for this one to finish).
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // anchor = (row + col) odd  (reference: MLIC++/utils/ckbd.py:35-45)
 __device__ __forceinline__ bool parity_keep(int par, int h, int w) {
     return par == PAR_NONE || (((h + w) & 1) == (par == PAR_ANCHOR ? 1 : 0));

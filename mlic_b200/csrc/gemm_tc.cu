@@ -885,6 +885,7 @@ __global__ void __launch_bounds__(DwT<S>::THREADS, 2) dwconv3x3_tma_kernel(const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     __syncthreads();
+    pdl_wait();                 // (everything above touches parameters only)
     const int tiles_per_img = tilesW * tilesH;
     if (warp == TT::NCW) {
         if (lane == 0) {
@@ -1014,8 +1015,8 @@ static int launch_dw_tma(const Act& in, const Act& out, const float* w9, const f
     const int num_sms = dev_sms(dev);
     int grid = (int)std::min<long long>(nitems, 2LL * num_sms);
     if (grid >= 2 * chunks) grid = grid / chunks * chunks;        // a block then stays on one channel chunk: taps loaded once (see the kernel)
-    if (act == ACT_GELU) dwconv3x3_tma_kernel<S, true><<<grid, TT::THREADS, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
-    else dwconv3x3_tma_kernel<S, false><<<grid, TT::THREADS, smem, s>>>(tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
+    if (act == ACT_GELU) launch_k(dwconv3x3_tma_kernel<S, true>, dim3(grid), dim3(TT::THREADS), smem, s, tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
+    else launch_k(dwconv3x3_tma_kernel<S, false>, dim3(grid), dim3(TT::THREADS), smem, s, tmap, in.C, (bf16*)out.p, out.H, out.W, out.ld, w9, bias, act, tilesW, tilesH, chunks, (int)nitems);
     return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 // bf16 NHWC depthwise 3x3 through the TMA-fed kernel; non-zero: not taken (the caller falls back to the staged kernel)

@@ -15,6 +15,11 @@
 
 namespace mlic {
 
+bool pdl_enabled() {
+    static const int pdl = getenv("MLIC_PDL") ? atoi(getenv("MLIC_PDL")) : 1;
+    return pdl != 0;
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------
@@ -28,6 +33,7 @@ constexpr int GM = 128, GN = 64, GK = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const T* __restrict__ in, ConvGeom g,
                                                              const float* __restrict__ Wt, Epi e, int vec) {
+    pdl_wait();
     __shared__ __align__(16) float As[2][GK][GM + 4];
     __shared__ __align__(16) float Bs[2][GK][GN + 4];
     const int tid = threadIdx.x;
@@ -171,6 +177,7 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) pw_small_cin_kernel(const T* __restrict__ in, ConvGeom g, const float* __restrict__ Wt,
                                                            Epi e, int vec) {
+    pdl_wait();
     // thread = (pixel lane, 8-column group); the group's weights stay in registers across the pixel loop
     const int ng = (e.N + 7) / 8;
     const int cgp = threadIdx.x % ng, pl = threadIdx.x / ng, npl = blockDim.x / ng;
@@ -224,13 +231,13 @@ void launch_conv_gemm_simt(int bf, const void* in, const ConvGeom& g, const floa
     if (g.ks == 1 && g.pad == 0 && g.Cin <= 4 && e.N <= 2048 && Mtot < (1LL << 31)) {
         const int npl = 256 / ((e.N + 7) / 8);
         int blocks = (int)std::min<long long>(cdiv(Mtot, npl), 148LL * 16);
-        if (bf) pw_small_cin_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)in, g, Wt, e, vec);
-        else pw_small_cin_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, g, Wt, e, vec);
+        if (bf) launch_k(pw_small_cin_kernel<bf16>, dim3(blocks), dim3(256), 0, s, (const bf16*)in, g, Wt, e, vec);
+        else launch_k(pw_small_cin_kernel<float>, dim3(blocks), dim3(256), 0, s, (const float*)in, g, Wt, e, vec);
         return;
     }
     dim3 grid(cdiv(Mtot, GM), cdiv(e.N, GN));
-    if (bf) conv_gemm_simt_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, g, Wt, e, vec);
-    else conv_gemm_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)in, g, Wt, e, vec);
+    if (bf) launch_k(conv_gemm_simt_kernel<bf16>, dim3(grid), dim3(256), 0, s, (const bf16*)in, g, Wt, e, vec);
+    else launch_k(conv_gemm_simt_kernel<float>, dim3(grid), dim3(256), 0, s, (const float*)in, g, Wt, e, vec);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -287,6 +294,7 @@ __global__ void __launch_bounds__(GH_THREADS, 3) ga_head_kernel(const float* __r
                                                       const float* __restrict__ b1, const float* __restrict__ wsk,
                                                       const float* __restrict__ bsk, int N, bf16* __restrict__ t, int t_ld,
                                                       bf16* __restrict__ sk, int sk_ld, int ntiles) {
+    pdl_wait();
     __shared__ float sx[3][3][2 * GH_PIX + 2];
     __shared__ float4 st[2][2][GH_PIX];      // [tile parity][0: depthwise result, 1: the stride-2 sample of x]
     const int Ho = H >> 1, Wo = W >> 1;
@@ -367,7 +375,7 @@ void launch_ga_head(const float* x, int B, int H, int W, const float* dw9, const
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const long long blocks = std::min<long long>(tiles, (long long)sms * 3);
-    ga_head_kernel<<<(unsigned)blocks, GH_THREADS, 0, s>>>(x, H, W, dw9, dwb, w1, b1, wsk, bsk, N, (bf16*)t.p, t.ld, (bf16*)sk.p, sk.ld, (int)tiles);
+    launch_k(ga_head_kernel, dim3((unsigned)blocks), dim3(GH_THREADS), 0, s, x, H, W, dw9, dwb, w1, b1, wsk, bsk, N, (bf16*)t.p, t.ld, (bf16*)sk.p, sk.ld, (int)tiles);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -380,6 +388,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in
                                                         T* __restrict__ out, int Ho, int Wo, int old,
                                                         const float* __restrict__ w9, const float* __restrict__ bias,
                                                         int stride, int act) {
+    pdl_wait();
     const int cg = (C + VEC - 1) / VEC;
     const long long total = (long long)B * Ho * Wo * cg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -438,6 +447,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tiled_kernel(const bf16* __r
                                                               bf16* __restrict__ out, int Ho, int Wo, int old,
                                                               const float* __restrict__ w9, const float* __restrict__ bias,
                                                               int act, int tilesW, int tilesH) {
+    pdl_wait();
     using TT = DwTile<S>;
     __shared__ __align__(16) bf16 sIn[TT::IH * TT::IW * 64];
     const int cb = blockIdx.y * 64;                 // channel block
@@ -516,6 +526,7 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_lane2_kernel(const bf16* __r
                                                               bf16* __restrict__ out, int Ho, int Wo, int old,
                                                               const float* __restrict__ w9, const float* __restrict__ bias,
                                                               int act, int tilesW) {
+    pdl_wait();
     using TT = DwLane<S>;
     __shared__ __align__(16) uint32_t sIn[TT::IH * TT::IW * 32];
     const int cb = blockIdx.y * 64;
@@ -589,12 +600,12 @@ void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, co
         if (stride == 1) {
             const int tw = cdiv(out.W, DwLane<1>::TW), th = cdiv(out.H, DwLane<1>::TH);
             dim3 grid(tw * th, cdiv(in.C, 64), out.B);
-            dwconv3x3_lane2_kernel<1><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+            launch_k(dwconv3x3_lane2_kernel<1>, dim3(grid), dim3(256), 0, s, (const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
                                                            out.ld, w9, bias, act, tw);
         } else {
             const int tw = cdiv(out.W, DwLane<2>::TW), th = cdiv(out.H, DwLane<2>::TH);
             dim3 grid(tw * th, cdiv(in.C, 64), out.B);
-            dwconv3x3_lane2_kernel<2><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+            launch_k(dwconv3x3_lane2_kernel<2>, dim3(grid), dim3(256), 0, s, (const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
                                                            out.ld, w9, bias, act, tw);
         }
         return;
@@ -604,12 +615,12 @@ void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, co
         if (stride == 1) {
             const int tw = cdiv(out.W, DwTile<1>::TW), th = cdiv(out.H, DwTile<1>::TH);
             dim3 grid(tw * th, cdiv(in.C, 64), out.B);
-            dwconv3x3_tiled_kernel<1><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+            launch_k(dwconv3x3_tiled_kernel<1>, dim3(grid), dim3(256), 0, s, (const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
                                                            out.ld, w9, bias, act, tw, th);
         } else {
             const int tw = cdiv(out.W, DwTile<2>::TW), th = cdiv(out.H, DwTile<2>::TH);
             dim3 grid(tw * th, cdiv(in.C, 64), out.B);
-            dwconv3x3_tiled_kernel<2><<<grid, 256, 0, s>>>((const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
+            launch_k(dwconv3x3_tiled_kernel<2>, dim3(grid), dim3(256), 0, s, (const bf16*)in.p, in.H, in.W, in.C, in.ld, (bf16*)out.p, out.H, out.W,
                                                            out.ld, w9, bias, act, tw, th);
         }
         return;
@@ -621,7 +632,7 @@ void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, co
     if (total == 0) return;
     int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 32);
 #define DW_LAUNCH(T, V)                                                                                             \
-    dwconv3x3_kernel<T, V><<<blocks, 256, 0, s>>>((const T*)in.p, in.B, in.H, in.W, in.C, in.ld, (T*)out.p, out.H, \
+    launch_k(dwconv3x3_kernel<T, V>, dim3(blocks), dim3(256), 0, s, (const T*)in.p, in.B, in.H, in.W, in.C, in.ld, (T*)out.p, out.H, \
                                                   out.W, out.ld, w9, bias, stride, act)
     if (bf) { if (vec) DW_LAUNCH(bf16, 4); else DW_LAUNCH(bf16, 1); }
     else { if (vec) DW_LAUNCH(float, 4); else DW_LAUNCH(float, 1); }
@@ -634,6 +645,7 @@ void launch_dwconv3x3(int bf, const Act& in, const Act& out, const float* w9, co
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW, T* __restrict__ dst, int ld) {
+    pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -649,6 +661,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW
 }
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int ld, int C, int HW, float* __restrict__ dst) {
+    pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -667,26 +680,27 @@ void launch_nchw_to_nhwc(int bf, const float* src, const Act& dst, int Csrc, cud
     int HW = dst.H * dst.W;
     if (HW == 0 || dst.B == 0) return;
     dim3 grid(cdiv(HW, 32), cdiv(Csrc, 32), dst.B), blk(32, 8);
-    if (bf) nchw_to_nhwc_kernel<bf16><<<grid, blk, 0, s>>>(src, Csrc, HW, (bf16*)dst.p, dst.ld);
-    else nchw_to_nhwc_kernel<float><<<grid, blk, 0, s>>>(src, Csrc, HW, (float*)dst.p, dst.ld);
+    if (bf) launch_k(nchw_to_nhwc_kernel<bf16>, dim3(grid), dim3(blk), 0, s, src, Csrc, HW, (bf16*)dst.p, dst.ld);
+    else launch_k(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(blk), 0, s, src, Csrc, HW, (float*)dst.p, dst.ld);
 }
 void launch_nhwc_to_nchw(int bf, const Act& src, float* dst, cudaStream_t s) {
     int HW = src.H * src.W;
     if (HW == 0 || src.B == 0) return;
     dim3 grid(cdiv(HW, 32), cdiv(src.C, 32), src.B), blk(32, 8);
-    if (bf) nhwc_to_nchw_kernel<bf16><<<grid, blk, 0, s>>>((const bf16*)src.p, src.ld, src.C, HW, dst);
-    else nhwc_to_nchw_kernel<float><<<grid, blk, 0, s>>>((const float*)src.p, src.ld, src.C, HW, dst);
+    if (bf) launch_k(nhwc_to_nchw_kernel<bf16>, dim3(grid), dim3(blk), 0, s, (const bf16*)src.p, src.ld, src.C, HW, dst);
+    else launch_k(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(blk), 0, s, (const float*)src.p, src.ld, src.C, HW, dst);
 }
 void launch_nhwc_f32_to_nchw(const float* src, int ld, int B, int H, int W, int C, float* dst, cudaStream_t s) {
     int HW = H * W;
     if (HW == 0 || B == 0) return;
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), B), blk(32, 8);
-    nhwc_to_nchw_kernel<float><<<grid, blk, 0, s>>>(src, ld, C, HW, dst);
+    launch_k(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(blk), 0, s, src, ld, C, HW, dst);
 }
 
 template <typename TS, typename TD>
 __global__ void copy_channels_kernel(const TS* __restrict__ src, int sld, TD* __restrict__ dst, int dld, int C,
                                      long long npix) {
+    pdl_wait();
     long long total = npix * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -699,15 +713,15 @@ void launch_copy_channels(int bf, const Act& src, const Act& dst, cudaStream_t s
     long long npix = (long long)src.B * src.H * src.W;
     if (npix * src.C == 0) return;
     int blocks = (int)std::min<long long>(cdiv(npix * src.C, 256), 148LL * 16);
-    if (bf) copy_channels_kernel<bf16, bf16><<<blocks, 256, 0, s>>>((const bf16*)src.p, src.ld, (bf16*)dst.p, dst.ld, src.C, npix);
-    else copy_channels_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)src.p, src.ld, (float*)dst.p, dst.ld, src.C, npix);
+    if (bf) launch_k(copy_channels_kernel<bf16, bf16>, dim3(blocks), dim3(256), 0, s, (const bf16*)src.p, src.ld, (bf16*)dst.p, dst.ld, src.C, npix);
+    else launch_k(copy_channels_kernel<float, float>, dim3(blocks), dim3(256), 0, s, (const float*)src.p, src.ld, (float*)dst.p, dst.ld, src.C, npix);
 }
 void launch_copy_f32_to_act(int bf, const float* src, int ld, const Act& dst, cudaStream_t s) {
     long long npix = (long long)dst.B * dst.H * dst.W;
     if (npix * dst.C == 0) return;
     int blocks = (int)std::min<long long>(cdiv(npix * dst.C, 256), 148LL * 16);
-    if (bf) copy_channels_kernel<float, bf16><<<blocks, 256, 0, s>>>(src, ld, (bf16*)dst.p, dst.ld, dst.C, npix);
-    else copy_channels_kernel<float, float><<<blocks, 256, 0, s>>>(src, ld, (float*)dst.p, dst.ld, dst.C, npix);
+    if (bf) launch_k(copy_channels_kernel<float, bf16>, dim3(blocks), dim3(256), 0, s, src, ld, (bf16*)dst.p, dst.ld, dst.C, npix);
+    else launch_k(copy_channels_kernel<float, float>, dim3(blocks), dim3(256), 0, s, src, ld, (float*)dst.p, dst.ld, dst.C, npix);
 }
 void launch_fill_zero(void* p, size_t bytes, cudaStream_t s) { if (bytes) cudaMemsetAsync(p, 0, bytes, s); }
 
@@ -749,6 +763,7 @@ __global__ void entropy_bottleneck_kernel(const T* __restrict__ z, int zld, T* _
                                           int HW, long long total, const float* __restrict__ packed,
                                           const float* __restrict__ med, float* __restrict__ lik_nchw,
                                           int32_t* __restrict__ sym_nchw, float qs) {
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long p = i / C;
@@ -777,14 +792,15 @@ void launch_entropy_bottleneck(int bf, const Act& z, const Act& z_hat, const flo
     long long total = (long long)z.B * z.H * z.W * z.C;
     if (!total) return;
     int blocks = cdiv(total, 128);
-    if (bf) entropy_bottleneck_kernel<bf16><<<blocks, 128, 0, s>>>((const bf16*)z.p, z.ld, (bf16*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw, qs);
-    else entropy_bottleneck_kernel<float><<<blocks, 128, 0, s>>>((const float*)z.p, z.ld, (float*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw, qs);
+    if (bf) launch_k(entropy_bottleneck_kernel<bf16>, dim3(blocks), dim3(128), 0, s, (const bf16*)z.p, z.ld, (bf16*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw, qs);
+    else launch_k(entropy_bottleneck_kernel<float>, dim3(blocks), dim3(128), 0, s, (const float*)z.p, z.ld, (float*)z_hat.p, z_hat.ld, z.C, z.H * z.W, total, packed, medians, z_lik_nchw, z_sym_nchw, qs);
 }
 
 // EntropyBottleneck.decompress after the range decoder (CompressAI: dequantize(values, medians)): z_hat = sym + median
 template <typename T>
 __global__ void zsym_to_zhat_kernel(const int32_t* __restrict__ sym_nchw, T* __restrict__ zh, int zhld, int C, int HW,
                                     long long total, const float* __restrict__ med, float qs) {
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long p = i / C;
@@ -798,8 +814,8 @@ void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians
     long long total = (long long)z_hat.B * z_hat.H * z_hat.W * z_hat.C;
     if (!total) return;
     int blocks = cdiv(total, 128);
-    if (bf) zsym_to_zhat_kernel<bf16><<<blocks, 128, 0, s>>>(z_sym_nchw, (bf16*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians, qs);
-    else zsym_to_zhat_kernel<float><<<blocks, 128, 0, s>>>(z_sym_nchw, (float*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians, qs);
+    if (bf) launch_k(zsym_to_zhat_kernel<bf16>, dim3(blocks), dim3(128), 0, s, z_sym_nchw, (bf16*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians, qs);
+    else launch_k(zsym_to_zhat_kernel<float>, dim3(blocks), dim3(128), 0, s, z_sym_nchw, (float*)z_hat.p, z_hat.ld, z_hat.C, z_hat.H * z_hat.W, total, medians, qs);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -808,6 +824,7 @@ void launch_zsym_to_zhat(int bf, const int32_t* z_sym_nchw, const float* medians
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, int xld, int C, long long npix, const float* __restrict__ g,
                                  const float* __restrict__ b, T* __restrict__ out, int old) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -845,6 +862,7 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int xld, int C, long l
 template <int LP>
 __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const bf16* __restrict__ x, int xld, long long npix, const float* __restrict__ g,
                                                                  const float* __restrict__ b, bf16* __restrict__ out, int old) {
+    pdl_wait();
     constexpr int C = 8 * LP, PPW = 32 / LP;
     const int lane = threadIdx.x & 31, sub = lane % LP, pl = lane / LP;
     float gg[8], bb[8];
@@ -877,13 +895,13 @@ void launch_layernorm(int bf, const Act& x, const float* g, const float* b, cons
     if (bf && (x.C == 32 || x.C == 64) && (x.ld % 8) == 0 && (out.ld % 8) == 0 && ((uintptr_t)x.p % 16) == 0 && ((uintptr_t)out.p % 16) == 0) {
         const int ppw = x.C == 32 ? 8 : 4;
         const int blocks = (int)std::min<long long>(cdiv(npix, 8LL * ppw), 148LL * 8);
-        if (x.C == 32) layernorm_bf16_vec_kernel<4><<<blocks, 256, 0, s>>>((const bf16*)x.p, x.ld, npix, g, b, (bf16*)out.p, out.ld);
-        else layernorm_bf16_vec_kernel<8><<<blocks, 256, 0, s>>>((const bf16*)x.p, x.ld, npix, g, b, (bf16*)out.p, out.ld);
+        if (x.C == 32) launch_k(layernorm_bf16_vec_kernel<4>, dim3(blocks), dim3(256), 0, s, (const bf16*)x.p, x.ld, npix, g, b, (bf16*)out.p, out.ld);
+        else launch_k(layernorm_bf16_vec_kernel<8>, dim3(blocks), dim3(256), 0, s, (const bf16*)x.p, x.ld, npix, g, b, (bf16*)out.p, out.ld);
         return;
     }
     int blocks = (int)std::min<long long>(cdiv(npix, 8), 148LL * 16);
-    if (bf) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)x.p, x.ld, x.C, npix, g, b, (bf16*)out.p, out.ld);
-    else layernorm_kernel<float><<<blocks, 256, 0, s>>>((const float*)x.p, x.ld, x.C, npix, g, b, (float*)out.p, out.ld);
+    if (bf) launch_k(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, s, (const bf16*)x.p, x.ld, x.C, npix, g, b, (bf16*)out.p, out.ld);
+    else launch_k(layernorm_kernel<float>, dim3(blocks), dim3(256), 0, s, (const float*)x.p, x.ld, x.C, npix, g, b, (float*)out.p, out.ld);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -902,6 +920,7 @@ constexpr int LTH = LT + 4;     // with halo
 template <typename T, int HD>
 __global__ void __launch_bounds__(256) local_attn_kernel(const float* __restrict__ F, int H, int W,
                                                          const float* __restrict__ rel_bias, T* __restrict__ O) {
+    pdl_wait();
     constexpr int C = 2 * HD;
     extern __shared__ float sm[];
     float* sF = sm;                          // [LTH*LTH][3C + 1]
@@ -985,7 +1004,7 @@ int launch_local_attn(int bf, const float* F, int B, int H, int W, int C, const 
 #define LA_LAUNCH(T, HD)                                                                                      \
     do {                                                                                                      \
         cudaFuncSetAttribute(local_attn_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        local_attn_kernel<T, HD><<<grid, 256, smem, s>>>(F, H, W, rel_bias, (T*)O);                           \
+        launch_k(local_attn_kernel<T, HD>, dim3(grid), dim3(256), smem, s, F, H, W, rel_bias, (T*)O);                           \
     } while (0)
     if (C == 32) { if (bf) LA_LAUNCH(bf16, 16); else LA_LAUNCH(float, 16); }
     else if (C == 64) { if (bf) LA_LAUNCH(bf16, 32); else LA_LAUNCH(float, 32); }
@@ -1035,6 +1054,7 @@ __device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
 constexpr float LM_LOG2E = 1.4426950408889634f;
 __global__ void __launch_bounds__(256, 2) local_attn_mma_kernel(const bf16* __restrict__ F, int f_ld, int H, int W,
                                                              const float* __restrict__ rel_bias, bf16* __restrict__ O) {
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t lm_smem[];
     uint8_t* sF = lm_smem;
     uint8_t* sZero = lm_smem + LM_F_BYTES;                       // 16 zero bytes: rows of the padded taps 25..31
@@ -1202,13 +1222,14 @@ int launch_local_attn_mma(const Act& F, const float* rel_bias, void* O, cudaStre
     if (dev < 0 || dev >= 64) dev = 0;
     if (!attr[dev]) { cudaFuncSetAttribute(local_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM); attr[dev] = true; }
     dim3 grid(cdiv(F.W, LM_TW), cdiv(F.H, LM_TH), F.B);
-    local_attn_mma_kernel<<<grid, 256, LM_SMEM, s>>>((const bf16*)F.p, F.ld, F.H, F.W, rel_bias, (bf16*)O);
+    launch_k(local_attn_mma_kernel, dim3(grid), dim3(256), LM_SMEM, s, (const bf16*)F.p, F.ld, F.H, F.W, rel_bias, (bf16*)O);
     return 0;
 }
 
 // squeezed non-anchor rows [B][H][W/2][C] -> full NHWC view (non-anchor pixels; anchor pixels are zeroed)
 __global__ void unsqueeze_nonanchor_kernel(const bf16* __restrict__ src, int sld, bf16* __restrict__ dst, int dld, int H, int W,
                                            int C8, long long total) {
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8);
         const long long pix = i / C8;
@@ -1224,7 +1245,7 @@ void launch_unsqueeze_nonanchor(const Act& src /*[1,1,B*H*W/2,C]*/, const Act& d
     const long long total = (long long)dst.B * dst.H * dst.W * (dst.C / 8);
     if (total == 0) return;
     int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 8);
-    unsqueeze_nonanchor_kernel<<<blocks, 256, 0, s>>>((const bf16*)src.p, src.ld, (bf16*)dst.p, dst.ld, dst.H, dst.W, dst.C / 8, total);
+    launch_k(unsqueeze_nonanchor_kernel, dim3(blocks), dim3(256), 0, s, (const bf16*)src.p, src.ld, (bf16*)dst.p, dst.ld, dst.H, dst.W, dst.C / 8, total);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1256,6 +1277,7 @@ size_t lin_attn_scratch_floats(int B, int heads, int hd, int HW) {
 template <typename T>
 __global__ void __launch_bounds__(256) lin_colmax_kernel(const T* __restrict__ qkv, int ld, int D, int H, int W, int nch,
                                                          int par, float* __restrict__ pmax) {
+    pdl_wait();
     // block = (chunk, 32-channel group, b); thread = (position lane 0..7, channel 0..31)
     __shared__ float sm[8][33];
     const int ch = blockIdx.x, b = blockIdx.z;
@@ -1290,6 +1312,7 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(256) lin_ctx_kernel(const T* __restrict__ qkv, int ld, int D, int H, int W, int nch,
                                                       int par, const float* __restrict__ pmax,
                                                       float* __restrict__ pctx) {
+    pdl_wait();
     constexpr int TP = 128;              // positions staged per step
     __shared__ float sE[TP][HD + 1];
     __shared__ float sV[TP][HD + 1];
@@ -1381,6 +1404,7 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t& r0, uint3
 template <int HD>
 __global__ void __launch_bounds__(256) lin_ctx_mma_kernel(const bf16* __restrict__ qkv, int ld, int D, int H, int W, int nch, int par,
                                                           const float* __restrict__ pmax, float* __restrict__ pctx) {
+    pdl_wait();
     constexpr int TP = 256;                       // positions staged per step
     constexpr int PITCH = HD + 8;                 // bf16 elements per staged row (16-byte aligned, conflict-free ldmatrix rows)
     constexpr int CG = HD / 8;
@@ -1471,6 +1495,7 @@ __global__ void __launch_bounds__(256) lin_ctx_mma_kernel(const bf16* __restrict
 
 template <int HD>
 __global__ void lin_ctx_reduce_kernel(const float* __restrict__ pctx, int nch, float* __restrict__ ctx) {
+    pdl_wait();
     // block = (head, b, quarter of the hd*hd entries); ctx[b][g][c1][c2] = sum_ch pctx / sum_ch S[c1].  The chunk loop is
     // unrolled by 8 with a fixed pairwise order: 8 loads in flight instead of a latency-bound chain, same result every run.
     const size_t bg = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
@@ -1499,6 +1524,7 @@ __global__ void lin_ctx_reduce_kernel(const float* __restrict__ pctx, int nch, f
 template <typename T, int HD>
 __global__ void __launch_bounds__(128) lin_out_kernel(const T* __restrict__ qkv, int ld, int H, int W, int par_q,
                                                       const float* __restrict__ ctx, T* __restrict__ out, int old) {
+    pdl_wait();
     __shared__ float sC[HD][HD];
     const int g = blockIdx.y, b = blockIdx.z;
     const int heads = gridDim.y;
@@ -1555,6 +1581,7 @@ __global__ void __launch_bounds__(128) lin_out_kernel(const T* __restrict__ qkv,
 constexpr int LO_TILES = 8;                      // 16-pixel tiles per warp
 __global__ void __launch_bounds__(128) lin_out_mma32_kernel(const bf16* __restrict__ qkv, int ld, int HW, const float* __restrict__ ctx,
                                                             bf16* __restrict__ out, int old) {
+    pdl_wait();
     __shared__ float sC[32][33];
     __shared__ __align__(16) uint8_t sO[4][16 * 80];
     const int g_head = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
@@ -1632,18 +1659,18 @@ int launch_lin_attn(int bf, const Act& qkv, int D, int heads, int hd, int par_kv
     float* ctx = pctx + (size_t)B * heads * nch * (hd * hd + hd);
 #define LIN_LAUNCH(T, HD)                                                                                          \
     do {                                                                                                           \
-        lin_colmax_kernel<T><<<dim3(nch, (D + 31) / 32, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax); \
+        launch_k(lin_colmax_kernel<T>, dim3(dim3(nch, (D + 31) / 32, B)), dim3(256), 0, s, (const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax); \
         if (sizeof(T) == 2 && (qkv.ld % 8) == 0 && (D % 8) == 0 && (((uintptr_t)qkv.p) % 16) == 0 && !getenv("MLIC_LIN_SIMT"))                  \
-            lin_ctx_mma_kernel<HD><<<dim3(nch, heads, B), 256, 0, s>>>((const bf16*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax, pctx); \
+            launch_k(lin_ctx_mma_kernel<HD>, dim3(dim3(nch, heads, B)), dim3(256), 0, s, (const bf16*)qkv.p, qkv.ld, D, H, W, nch, par_kv, pmax, pctx); \
         else                                                                                                       \
-        lin_ctx_kernel<T, HD><<<dim3(nch, heads, B), 256, 0, s>>>((const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv,   \
+        launch_k(lin_ctx_kernel<T, HD>, dim3(dim3(nch, heads, B)), dim3(256), 0, s, (const T*)qkv.p, qkv.ld, D, H, W, nch, par_kv,   \
                                                                   pmax, pctx);                                     \
-        lin_ctx_reduce_kernel<HD><<<dim3(heads, B, 4), 256, 0, s>>>(pctx, nch, ctx);                                  \
+        launch_k(lin_ctx_reduce_kernel<HD>, dim3(dim3(heads, B, 4)), dim3(256), 0, s, pctx, nch, ctx);                                  \
         if (sizeof(T) == 2 && HD == 32 && par_q == PAR_NONE && (qkv.ld % 8) == 0 && (out.ld % 8) == 0 && (((uintptr_t)qkv.p) % 16) == 0 &&      \
             (((uintptr_t)out.p) % 16) == 0 && !getenv("MLIC_LIN_SIMT"))                                                                      \
-            lin_out_mma32_kernel<<<dim3(cdiv(HW, 4 * 16 * LO_TILES), heads, B), 128, 0, s>>>((const bf16*)qkv.p, qkv.ld, HW, ctx, (bf16*)out.p, out.ld); \
+            launch_k(lin_out_mma32_kernel, dim3(dim3(cdiv(HW, 4 * 16 * LO_TILES), heads, B)), dim3(128), 0, s, (const bf16*)qkv.p, qkv.ld, HW, ctx, (bf16*)out.p, out.ld); \
         else                                                                                                       \
-        lin_out_kernel<T, HD><<<dim3(cdiv(HW, 128), heads, B), 128, 0, s>>>((const T*)qkv.p, qkv.ld, H, W, par_q,  \
+        launch_k(lin_out_kernel<T, HD>, dim3(dim3(cdiv(HW, 128), heads, B)), dim3(128), 0, s, (const T*)qkv.p, qkv.ld, H, W, par_q,  \
                                                                             ctx, (T*)out.p, out.ld);               \
     } while (0)
     if (hd == 32) { if (bf) LIN_LAUNCH(bf16, 32); else LIN_LAUNCH(float, 32); }
@@ -1679,6 +1706,7 @@ __device__ __forceinline__ float vbr_deq(float sq, float rgain, float mu) { retu
 // I: index type -- int when B*H*W*C < 2^31 (the four divisions per element are 64-bit otherwise: a third of the kernel's instructions)
 template <typename T, typename I>
 __global__ void quant_anchor_kernel(QuantArgs a) {
+    pdl_wait();
     const int C = a.C;
     const I total = (I)a.B * a.H * a.W * C;
     for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
@@ -1720,6 +1748,7 @@ __global__ void quant_anchor_kernel(QuantArgs a) {
 // I: index type -- int when B*H*W*C < 2^31 (the four divisions per element are 64-bit otherwise: a third of the kernel's instructions)
 template <typename T, typename I>
 __global__ void quant_nonanchor_kernel(QuantArgs a) {
+    pdl_wait();
     const int C = a.C;
     const I total = (I)a.B * a.H * a.W * C;
     for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
@@ -1772,22 +1801,23 @@ void launch_quant_anchor(int bf, const QuantArgs& a, cudaStream_t s) {
     if (!total) return;
     int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
     const bool small = total + (long long)blocks * 256 < 0x7fffffffLL;
-    if (bf) { if (small) quant_anchor_kernel<bf16, int><<<blocks, 256, 0, s>>>(a); else quant_anchor_kernel<bf16, long long><<<blocks, 256, 0, s>>>(a); }
-    else { if (small) quant_anchor_kernel<float, int><<<blocks, 256, 0, s>>>(a); else quant_anchor_kernel<float, long long><<<blocks, 256, 0, s>>>(a); }
+    if (bf) { if (small) launch_k(quant_anchor_kernel<bf16, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_anchor_kernel<bf16, long long>, dim3(blocks), dim3(256), 0, s, a); }
+    else { if (small) launch_k(quant_anchor_kernel<float, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_anchor_kernel<float, long long>, dim3(blocks), dim3(256), 0, s, a); }
 }
 void launch_quant_nonanchor(int bf, const QuantArgs& a, cudaStream_t s) {
     long long total = (long long)a.B * a.H * a.W * a.C;
     if (!total) return;
     int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
     const bool small = total + (long long)blocks * 256 < 0x7fffffffLL;
-    if (bf) { if (small) quant_nonanchor_kernel<bf16, int><<<blocks, 256, 0, s>>>(a); else quant_nonanchor_kernel<bf16, long long><<<blocks, 256, 0, s>>>(a); }
-    else { if (small) quant_nonanchor_kernel<float, int><<<blocks, 256, 0, s>>>(a); else quant_nonanchor_kernel<float, long long><<<blocks, 256, 0, s>>>(a); }
+    if (bf) { if (small) launch_k(quant_nonanchor_kernel<bf16, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_nonanchor_kernel<bf16, long long>, dim3(blocks), dim3(256), 0, s, a); }
+    else { if (small) launch_k(quant_nonanchor_kernel<float, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_nonanchor_kernel<float, long long>, dim3(blocks), dim3(256), 0, s, a); }
 }
 
 // Stand-alone flat version (any layout, elementwise): the GaussianConditional boundary of the C ABI.
 __global__ void gc_flat_kernel(const float* __restrict__ y, const float* __restrict__ sc, const float* __restrict__ mu,
                                size_t n, float* __restrict__ y_hat, float* __restrict__ lik, int32_t* __restrict__ sym,
                                int32_t* __restrict__ idx, const float* __restrict__ table, int levels) {
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float m = mu[i], s = sc[i];
         float q = rintf(y[i] - m);
@@ -1802,7 +1832,7 @@ void launch_gc_flat(const float* y, const float* sc, const float* mu, size_t n, 
                     int32_t* idx, const float* table, int levels, cudaStream_t s) {
     if (!n) return;
     int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-    gc_flat_kernel<<<blocks, 256, 0, s>>>(y, sc, mu, n, y_hat, lik, sym, idx, table, levels);
+    launch_k(gc_flat_kernel, dim3(blocks), dim3(256), 0, s, y, sc, mu, n, y_hat, lik, sym, idx, table, levels);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1811,6 +1841,7 @@ void launch_gc_flat(const float* y, const float* sc, const float* mu, size_t n, 
 // ------------------------------------------------------------------------------------------
 __global__ void reduce_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int mode,
                                       double* __restrict__ partial) {
+    pdl_wait();
     __shared__ double sh[256];
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1826,6 +1857,7 @@ __global__ void reduce_partial_kernel(const float* __restrict__ a, const float* 
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 __global__ void reduce_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    pdl_wait();
     __shared__ double sh[256];
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
@@ -1841,8 +1873,8 @@ void launch_reduce(const float* a, const float* b, long long n, int mode, double
                    cudaStream_t s) {
     if (n <= 0) return;
     int blocks = (int)std::min<long long>(cdiv(n, 256), RD_BLOCKS);
-    reduce_partial_kernel<<<blocks, 256, 0, s>>>(a, b, n, mode, partial);
-    reduce_final_kernel<<<1, 256, 0, s>>>(partial, blocks, out);
+    launch_k(reduce_partial_kernel, dim3(blocks), dim3(256), 0, s, a, b, n, mode, partial);
+    launch_k(reduce_final_kernel, dim3(1), dim3(256), 0, s, partial, blocks, out);
 }
 
 }  // namespace mlic

@@ -5,6 +5,22 @@
 
 namespace mlic {
 
+// Launch of a CUDA-core kernel with programmatic stream serialization (MLIC_PDL=0: plain launches); the kernel's first statement is
+// pdl_wait() (common.cuh).  ~190 of the 565 launches of an MLICPP_L forward are such kernels (depthwise convs, LayerNorm, the
+// attention kernels, quantisation): without the attribute each of them pays the full launch gap behind a tcgen05 kernel.
+bool pdl_enabled();
+template <typename... KA, typename... A>
+inline cudaError_t launch_k(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A... a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, static_cast<KA>(a)...);
+}
+
 struct ConvGeom {
     int B, H, W, Cin, ld;       // input view
     int Hout, Wout;

@@ -34,6 +34,11 @@ SHAPES = [  # name, B, H, W, Cin, N, ks, shuffle
     ("wide1x1 qkv 288->864 @68x120 b32", 32, 68, 120, 288, 864, 1, False),
     ("wide1x1 pw 320->320 @68x120 b32", 32, 68, 120, 320, 320, 1, False),
     ("wide1x1 ragged 264->200 @37x53 b48", 48, 37, 53, 264, 200, 1, False),
+    ("narrow mlp0 96->128 @68x120 b32", 32, 68, 120, 96, 128, 1, False),
+    ("narrow mlp4 128->64 @68x120 b32", 32, 68, 120, 128, 64, 1, False),
+    ("narrow q 32->32 @68x120 b32", 32, 68, 120, 32, 32, 1, False),
+    ("narrow ep4 256->128 @68x60 b32", 32, 68, 60, 256, 128, 1, False),
+    ("narrow fusion 800->64 @68x60 b32", 32, 68, 60, 800, 64, 1, False),
 ]
 check = "--check" in sys.argv
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
