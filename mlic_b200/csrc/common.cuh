@@ -31,6 +31,8 @@ __device__ __forceinline__ void pdl_wait() {
 __device__ __forceinline__ bool parity_keep(int par, int h, int w) {
     return par == PAR_NONE || (((h + w) & 1) == (par == PAR_ANCHOR ? 1 : 0));
 }
+struct Epi;
+__device__ __forceinline__ int premask_of(const Epi& e, int n);
 
 // What happens to one accumulator row segment on its way to memory.  Order:
 //   v = premask ? (keep ? acc : 0) : acc;  v += bias;  gdn: v = x * (r)sqrt(v);  act;  postmask;  v += res;
@@ -38,6 +40,8 @@ __device__ __forceinline__ bool parity_keep(int par, int h, int w) {
 struct Epi {
     const float* bias;      // [N] in GEMM column order, may be null
     int act, premask, postmask;
+    int pm_w, pm_codes;     // pm_w != 0: the premask of column n is (pm_codes >> 2 (n / pm_w)) & 3 instead of `premask` (one GEMM for the
+                            // q | k | v projections of LinearGlobalIntraContext, whose inputs carry different parity masks); pm_w % 8 == 0
     const void* res; int res_ld;       // residual, addressed like the OUTPUT
     int gdn; const void* gdn_x; int gdn_ld;   // x operand of (I)GDN, addressed like the GEMM-space pixel
     int shuffle;            // 0 | 1: PixelShuffle(2); GEMM column n' = (2r+s)*Cq + c  (weights permuted at pack time)
@@ -47,6 +51,7 @@ struct Epi {
     void* out2; int out2_ld;
     int Hout, Wout, N;      // GEMM-space output grid and column count
 };
+__device__ __forceinline__ int premask_of(const Epi& e, int n) { return e.pm_w ? ((e.pm_codes >> (2 * (n / e.pm_w))) & 3) : e.premask; }
 
 __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU(approximate='none')
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -137,7 +142,7 @@ __device__ __forceinline__ void store4(bf16* p, const float v[4]) {
 template <typename T>
 __device__ __forceinline__ void epi_store4(const Epi& e, int b, int h, int w, int n, float v[4], bool vec) {
     if (n >= e.N) return;
-    const bool keep_pre = parity_keep(e.premask, h, w);
+    const bool keep_pre = parity_keep(premask_of(e, n), h, w);      // (n is a multiple of 4, groups of pm_w % 8 == 0 columns)
     const bool keep_post = parity_keep(e.postmask, h, w);
     int oh = h, ow = w, oc = n, OH = e.Hout, OW = e.Wout;
     bool straddle = false;

@@ -73,6 +73,7 @@ struct EpiOpt {
     int out_f32_ld = 0;
     int nchw = 0;               // out_f32 is a dense NCHW tensor (x_hat)
     int ck = 0;                 // 1 | 2: the GEMM rows are the anchor | non-anchor pixels of `in`, squeezed (TcConv::ck); tcgen05 path only
+    int pm_w = 0, pm_codes = 0; // per-column-group premask (Epi::pm_w)
 };
 
 }  // namespace
@@ -105,6 +106,7 @@ struct mlic_engine {
     int fuse = 1;            // bf16 + tensor cores: depthwise 3x3 and x^2 computed inside the GEMM kernel (A-operand producers)
     int pair = 1;            // fuse: DepthWiseConv / (I)GDN-tail blocks with C = N = 192 | 128 on the two-SM kernel (ds_pair.cu)
     int halo5 = getenv("MLIC_HALO5") ? atoi(getenv("MLIC_HALO5")) : 2;      // 5x5 convs with N <= 128 on the halo-patch kernels (conv_halo.cu): 1 pixels as M, 2 roles swapped (weights as M, 256 pixels as N)
+    int folds = getenv("MLIC_FOLDS") ? atoi(getenv("MLIC_FOLDS")) : 1;      // algebraic folds of the bf16 fast path (pack_folds, pack_fusion_proj)
     int wide_pair = getenv("MLIC_WIDE_PAIR") ? atoi(getenv("MLIC_WIDE_PAIR")) : 1;      // wide 1x1 GEMMs on the two-SM kernel (conv3_pair.cu)
     float z_qstep = 1.0f;    // quantisation step of the hyper prior (EntropyBottleneckVbr, vr_entbttlnck=True); 1: the plain EntropyBottleneck
 
@@ -357,6 +359,59 @@ struct mlic_engine {
         }
         pack_dw_list(p + ".qkv_dw", {p + ".queries.1", p + ".keys.1", p + ".values.1"});
     }
+    // Algebraic folds of the bf16 fast path (the fp32 validation mode keeps the reference's chain of layers, op for op):
+    //  * global_inter_context: skip(att) + mlp.4(h) is ONE GEMM over the channel concatenation [att | h] (context.py:245);
+    //  * global_intra_context: the q / k / v 1x1 convs read adjacent channel ranges of one tensor (previous slice | current slot):
+    //    one GEMM with the block matrix [[Wq 0] [Wk 0] [0 Wv]] and a premask per 32-column group (context.py:172-174).
+    void pack_folds(const std::string& gi, const std::string& ga) {
+        const HostT *ws = get(gi + ".skip.weight"), *bs = get(gi + ".skip.bias"), *w4 = get(gi + ".mlp.4.weight"), *b4 = get(gi + ".mlp.4.bias");
+        if (ws && bs && w4 && b4 && ws->dim(0) == w4->dim(0)) {
+            const int No = (int)ws->dim(0), Ka = (int)ws->dim(1), Kh = (int)w4->dim(1);
+            std::vector<float> w((size_t)No * (Ka + Kh)), b(No);
+            for (int o = 0; o < No; ++o) {
+                for (int c = 0; c < Ka; ++c) w[(size_t)o * (Ka + Kh) + c] = ws->v[(size_t)o * Ka + c];
+                for (int c = 0; c < Kh; ++c) w[(size_t)o * (Ka + Kh) + Ka + c] = w4->v[(size_t)o * Kh + c];
+                b[o] = bs->v[o] + b4->v[o];
+            }
+            pack_conv_raw(gi + ".skip_mlp4", w.data(), b.data(), No, Ka + Kh, 1, 0);
+        }
+        const HostT *wq = get(ga + ".queries.0.weight"), *wk = get(ga + ".keys.0.weight"), *wv = get(ga + ".values.0.weight");
+        const HostT *bq = get(ga + ".queries.0.bias"), *bk = get(ga + ".keys.0.bias"), *bv = get(ga + ".values.0.bias");
+        if (wq && wk && wv && bq && bk && bv) {
+            const int D = (int)wq->dim(0);
+            if ((int)wq->dim(1) == D && (D % 8) == 0) {
+                std::vector<float> w((size_t)3 * D * 2 * D, 0.f), b(3 * D);
+                for (int o = 0; o < D; ++o)
+                    for (int c = 0; c < D; ++c) {
+                        w[(size_t)o * 2 * D + c] = wq->v[(size_t)o * D + c];
+                        w[(size_t)(D + o) * 2 * D + c] = wk->v[(size_t)o * D + c];
+                        w[(size_t)(2 * D + o) * 2 * D + D + c] = wv->v[(size_t)o * D + c];
+                    }
+                for (int o = 0; o < D; ++o) { b[o] = bq->v[o]; b[D + o] = bk->v[o]; b[2 * D + o] = bv->v[o]; }
+                pack_conv_raw(ga + ".qkv_blk", w.data(), b.data(), 3 * D, 2 * D, 1, 0);
+            }
+        }
+    }
+    //  * local_context: proj(fusion(windows)) has no non-linearity in between (context.py:108-109): W' = Wp Wf, b' = Wp bf + bp (in double)
+    void pack_fusion_proj(const std::string& lc) {
+        const HostT *wf = get(lc + ".fusion.weight"), *bf_ = get(lc + ".fusion.bias"), *wp = get(lc + ".proj.weight"), *bp = get(lc + ".proj.bias");
+        if (!wf || !bf_ || !wp || !bp) return;
+        const int No = (int)wf->dim(0), Ci = (int)wf->dim(1), Np = (int)wp->dim(0);
+        if ((int)wp->dim(1) != No || wf->shape.size() != 4 || wf->dim(2) != 5 || wf->dim(3) != 5) return;
+        std::vector<float> wl((size_t)Np * 25 * Ci), bl(Np);
+        for (int o = 0; o < Np; ++o) {
+            double bacc = bp->v[o];
+            for (int m = 0; m < No; ++m) bacc += (double)wp->v[(size_t)o * No + m] * (double)bf_->v[m];
+            bl[o] = (float)bacc;
+            for (int c = 0; c < Ci; ++c)
+                for (int t = 0; t < 25; ++t) {
+                    double acc = 0.0;
+                    for (int m = 0; m < No; ++m) acc += (double)wp->v[(size_t)o * No + m] * (double)wf->v[((size_t)m * Ci + c) * 25 + t];
+                    wl[((size_t)o * 25 + t) * Ci + c] = (float)acc;        // K = tap * C + c, as the `fusion` packing
+                }
+        }
+        pack_conv_raw(lc + ".fusion_proj", wl.data(), bl.data(), Np, 25 * Ci, 1, 0);
+    }
     void pack_dw_mlp(const std::string& p) {
         pack_conv(p + ".0"); pack_dw_list(p + ".2", {p + ".2"}); pack_conv(p + ".4");
     }
@@ -456,7 +511,9 @@ struct mlic_engine {
                 pack_qkv(gi, true); pack_conv(gi + ".reprojection"); pack_dw_mlp(gi + ".mlp"); pack_conv(gi + ".skip");
                 std::string ga = "global_intra_context." + is;
                 pack_qkv(ga, false); pack_conv(ga + ".reprojection"); pack_dw_mlp(ga + ".mlp");
+                pack_folds(gi, ga);
             }
+            pack_fusion_proj(lc);
         }
         // EntropyBottleneck: softplus(matrices), tanh(factors) folded
         {
@@ -565,6 +622,7 @@ struct mlic_engine {
         Epi e;
         memset(&e, 0, sizeof e);
         e.bias = w->bias; e.act = o.act; e.premask = o.premask; e.postmask = o.postmask;
+        if (o.pm_w) { e.pm_w = o.pm_w; e.pm_codes = o.pm_codes; e.premask = PAR_NONANCHOR; }     // (premask != 0 keeps the layer off the kernels without a premask)
         e.N = w->N; e.shuffle = w->shuffle;
         e.Hout = (in.H + 2 * pad - w->ks) / stride + 1;
         e.Wout = (in.W + 2 * pad - w->ks) / stride + 1;
@@ -1040,6 +1098,20 @@ struct mlic_engine {
         Act O = act(X.B, X.H, X.W, D);
         lin_attn(qkv, D, D / 32, 32, PAR_NONE, PAR_NONE, O);
         const ConvW* wr = cw(p + ".reprojection");
+        const ConvW* w0 = cw(p + ".mlp.0");
+        if (bf && use_tc && fuse && folds && wr && w0 && convs.count(p + ".skip_mlp4") && (wr->N % 8) == 0) {
+            // skip(att) + mlp.4(h): one GEMM over [att | h], which the re-projection and the depthwise conv write side by side
+            Act AH = act(X.B, X.H, X.W, wr->N + w0->N);
+            Act A = view(AH, 0, wr->N), h2 = view(AH, wr->N, w0->N);
+            gemm(O, p + ".reprojection", 1, 2, &A, EpiOpt());
+            Act a = act(X.B, X.H, X.W, w0->N);
+            EpiOpt g; g.act = ACT_GELU;
+            gemm(A, p + ".mlp.0", 1, 0, &a, g);
+            dwconv(a, p + ".mlp.2", 1, ACT_GELU, h2);
+            gemm(AH, p + ".skip_mlp4", 1, 0, &out, EpiOpt());
+            ws_off = mark;
+            return;
+        }
         Act A = act(X.B, X.H, X.W, wr ? wr->N : 0);
         gemm(O, p + ".reprojection", 1, 2, &A, EpiOpt());
         gemm(A, p + ".skip", 1, 0, &out, EpiOpt());
@@ -1054,9 +1126,16 @@ struct mlic_engine {
         Act vq = view(pw, 0, D), vk = view(pw, D, D), vv = view(pw, 2 * D, D);
         EpiOpt oq; oq.premask = PAR_NONANCHOR;
         EpiOpt ok; ok.premask = PAR_ANCHOR;
+        if (bf && use_tc && fuse && folds && convs.count(p + ".qkv_blk") && x1.ld == x2.ld && (uint8_t*)x2.p == (uint8_t*)x1.p + (size_t)D * esz()) {
+            // x1 | x2 are adjacent channel ranges: q | k | v in one GEMM (block weights, premask per D-column group)
+            EpiOpt ob; ob.pm_w = D; ob.pm_codes = PAR_NONANCHOR | (PAR_ANCHOR << 2) | (PAR_NONE << 4);
+            Act x12 = x1; x12.C = 2 * D;
+            gemm(x12, p + ".qkv_blk", 1, 0, &pw, ob);
+        } else {
         gemm(x1, p + ".queries.0", 1, 0, &vq, oq);
         gemm(x1, p + ".keys.0", 1, 0, &vk, ok);
         gemm(x2, p + ".values.0", 1, 0, &vv, EpiOpt());
+        }
         dwconv(pw, p + ".qkv_dw", 1, ACT_NONE, qkv);
         Act O = act(x1.B, x1.H, x1.W, D);
         lin_attn(qkv, D, 2, D / 2, PAR_ANCHOR, PAR_NONANCHOR, O);
@@ -1084,8 +1163,11 @@ struct mlic_engine {
                 after_launch("local_attn");
             }
             Act fu = act(1, 1, Mh, 2 * Cc), pr = act(1, 1, Mh, 2 * Cc), n2 = act(1, 1, Mh, 2 * Cc), os = act(1, 1, Mh, 2 * Cc);
+            if (folds && convs.count(p + ".fusion_proj")) gemm(O, p + ".fusion_proj", 1, 0, &pr, EpiOpt());
+            else {
             gemm(O, p + ".fusion", 1, 0, &fu, EpiOpt());
             gemm(fu, p + ".proj", 1, 0, &pr, EpiOpt());
+            }
             layernorm(pr, p + ".norm2", n2);
             Act h = act(1, 1, Mh, 4 * Cc);
             EpiOpt g; g.act = ACT_GELU;

@@ -138,6 +138,7 @@ struct EpiRow {
     const bf16* xp;      // GDN operand row (at column 0) or null
     const bf16* rp;      // residual row (at output channel 0 of this pixel) or null
     bool keep_pre, keep_post;
+    int h, w;            // GEMM-space pixel (column-group premasks: Epi::pm_w)
 };
 // STAGED: the GDN operand / residual chunk of this thread was prefetched into the staging slot (xs / rs, shared memory)
 template <int ACT, int GDN, bool RES, bool STAGED>
@@ -147,7 +148,7 @@ __device__ __forceinline__ void epi_math8(const Epi& e, const float* __restrict_
     float2 v[4];
     {
         const float4 b0 = *reinterpret_cast<const float4*>(sBias + n), b1 = *reinterpret_cast<const float4*>(sBias + n + 4);
-        if (!row.keep_pre) {
+        if (e.pm_w ? !parity_keep(premask_of(e, n), row.h, row.w) : !row.keep_pre) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = 0.0f;
         }
@@ -627,6 +628,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcMaps tm, TcParams p, Epi e, unsign
             const int as = it & 1;
             EpiRow row;
             row.keep_pre = parity_keep(e.premask, h, w);
+            row.h = h; row.w = w;
             row.keep_post = parity_keep(e.postmask, h, w);
             row.xp = (GDN != GDN_NONE && valid) ? reinterpret_cast<const bf16*>(e.gdn_x) + (((size_t)img * e.Hout + h) * e.Wout + w) * e.gdn_ld : nullptr;
             if (p.store_mode != STORE_TMA) {         // (TMA-store mode waits after its operand prefetch)

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) pw_small_cin_kernel(const T* __restrict__
     for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int c = 0; c < 4; ++c) wr[j][c] = (n + j < e.N && c < g.Cin) ? Wt[(size_t)(n + j) * g.Cin + c] : 0.f;
-    const bool simple = vec && n + 8 <= e.N && !e.res && !e.gdn && !e.premask && !e.postmask && !e.shuffle && !e.out2 &&
+    const bool simple = vec && n + 8 <= e.N && !e.res && !e.gdn && !e.premask && !e.pm_w && !e.postmask && !e.shuffle && !e.out2 &&
                         !e.out_f32 && !e.nchw && e.act != ACT_HALF_TANH;
     float br[8];
 #pragma unroll
