@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmlic_b200.so")
-SOURCES = ["kernels.cu", "gemm_tc.cu", "ds_pair.cu", "conv3_pair.cu", "conv_halo.cu", "engine.cu", "rans.cpp"]
+SOURCES = ["kernels.cu", "gemm_tc.cu", "ds_pair.cu", "conv3_pair.cu", "conv_halo.cu", "chain3.cu", "engine.cu", "rans.cpp"]
 HEADERS = ["common.cuh", "kernels.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "mlic_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false"]

@@ -107,6 +107,7 @@ struct mlic_engine {
     int pair = 1;            // fuse: DepthWiseConv / (I)GDN-tail blocks with C = N = 192 | 128 on the two-SM kernel (ds_pair.cu)
     int halo5 = getenv("MLIC_HALO5") ? atoi(getenv("MLIC_HALO5")) : 2;      // 5x5 convs with N <= 128 on the halo-patch kernels (conv_halo.cu): 1 pixels as M, 2 roles swapped (weights as M, 256 pixels as N)
     int folds = getenv("MLIC_FOLDS") ? atoi(getenv("MLIC_FOLDS")) : 1;      // algebraic folds of the bf16 fast path (pack_folds, pack_fusion_proj)
+    int chain = getenv("MLIC_CHAIN") ? atoi(getenv("MLIC_CHAIN")) : 1;      // EntropyParameters / LocalContext tails as one launch (chain3.cu)
     int wide_pair = getenv("MLIC_WIDE_PAIR") ? atoi(getenv("MLIC_WIDE_PAIR")) : 1;      // wide 1x1 GEMMs on the two-SM kernel (conv3_pair.cu)
     float z_qstep = 1.0f;    // quantisation step of the hyper prior (EntropyBottleneckVbr, vr_entbttlnck=True); 1: the plain EntropyBottleneck
 
@@ -1024,11 +1025,65 @@ struct mlic_engine {
     // ck != 0 (bf16 fast path): only the anchor (1) / non-anchor (2) pixels are evaluated -- the stack is per-pixel and its
     // output is multiplied by that mask (mlicpp.py:112-117,148-152); out32 is then squeezed, [B*h*(w/2)][2C].
     bool ep_squeezed(int Hh, int Ww) const { return bf && use_tc && fuse && (Hh % 2) == 0 && (Ww % 2) == 0; }
+    // three chained layers in one launch (chain3.cu); false: not taken, nothing launched
+    bool chain3(int mode, const Act& rows, const std::string& k1, const std::string& k2, const std::string& k3, const LnW* ln, void* out, int out_ld, const char* what) {
+        if (!(bf && use_tc && fuse && chain)) return false;
+        const ConvW *w1 = cw(k1), *w2 = cw(k2), *w3 = cw(k3);
+        if (!w1 || !w2 || !w3 || w1->ks != 1 || w2->ks != 1 || w3->ks != 1) return false;
+        if (w1->Cin != rows.C || w2->Cin != w1->N || w3->Cin != w2->N || w2->Cpad != w1->N || w3->Cpad != w2->N) return false;
+        Chain3Args a;
+        memset(&a, 0, sizeof a);
+        a.mode = mode; a.in = rows.p; a.M = rows.B * rows.H * rows.W; a.K1 = rows.C; a.ld = rows.ld;
+        a.w1 = w1->wbf; a.K1pad = w1->Cpad; a.w2 = w2->wbf; a.w3 = w3->wbf; a.b1 = w1->bias; a.b2 = w2->bias; a.b3 = w3->bias;
+        a.N1 = w1->N; a.N2 = w2->N; a.N3 = w3->N;
+        if (ln) { a.ln_g = ln->g; a.ln_b = ln->b; a.ln_eps = 1e-5f; }
+        a.out = out; a.out_ld = out_ld;
+        if (dry) { a.in = a.out = (void*)16; }                     // (the dry run has no buffers: geometry only)
+        if (!chain3_supported(a)) return false;
+        if (!go()) return true;
+        cudaEvent_t ev1 = nullptr;
+        if (profile) {
+            cudaEventRecord(next_event(), st);
+            ev1 = next_event();
+            ev_flops.push_back(2.0 * (double)a.M * ((double)a.K1 * a.N1 + (double)a.N1 * a.N2 + (double)a.N2 * a.N3));
+        }
+        const int r = launch_chain3(a, st);
+        if (ev1) cudaEventRecord(ev1, st);
+        if (r) { if (!rc) rc = fail("chain '%s': %s", k1.c_str(), chain3_last_error()); return true; }
+        ++launches;
+        if (trace) {
+            char lab[256];
+            snprintf(lab, sizeof lab, "%s [chain3 M=%d K=%d N=%d-%d-%d]", what, a.M, a.K1, a.N1, a.N2, a.N3);
+            tr(lab);
+        }
+        return true;
+    }
     void ep(const Act& in, const std::string& p, float* out32, int ck = 0) {
         size_t mark = ws_off;
         EpiOpt g; g.act = ACT_GELU;
         Act cur = in;
         const int Mh = in.B * in.H * (in.W / 2);
+        if (ck && bf && use_tc && fuse && chain) {
+            // squeezed rows: layer 0 as before (wide GEMM over the 5-D checkerboard gather), layers 1..3 in one launch
+            const ConvW* w0 = cw(p + ".fusion.0");
+            Act h0 = act(1, 1, Mh, w0 ? w0->N : 0);
+            EpiOpt g0 = g; g0.ck = ck;
+            const size_t mark2 = ws_off;
+            (void)mark2;
+            gemm(cur, p + ".fusion.0", 1, 0, &h0, g0);
+            if (chain3(0, h0, p + ".fusion.2", p + ".fusion.4", p + ".fusion.6", nullptr, out32, 2 * C, (p + ".fusion.2-6").c_str())) { ws_off = mark; return; }
+            cur = h0;
+            for (int j : {2, 4}) {
+                const ConvW* w = cw(p + ".fusion." + std::to_string(j));
+                Act nx = act(1, 1, Mh, w ? w->N : 0);
+                gemm(cur, p + ".fusion." + std::to_string(j), 1, 0, &nx, g);
+                cur = nx;
+            }
+            EpiOpt o; o.out_f32 = out32; o.out_f32_ld = 2 * C;
+            gemm(cur, p + ".fusion.6", 1, 0, nullptr, o);
+            ws_off = mark;
+            return;
+        }
         for (int j : {0, 2, 4}) {
             const ConvW* w = cw(p + ".fusion." + std::to_string(j));
             Act nx = ck ? act(1, 1, Mh, w ? w->N : 0) : act(in.B, in.H, in.W, w ? w->N : 0);
@@ -1163,6 +1218,15 @@ struct mlic_engine {
                 after_launch("local_attn");
             }
             Act fu = act(1, 1, Mh, 2 * Cc), pr = act(1, 1, Mh, 2 * Cc), n2 = act(1, 1, Mh, 2 * Cc), os = act(1, 1, Mh, 2 * Cc);
+            {
+                auto itn = lns.find(p + ".norm2");
+                if (folds && convs.count(p + ".fusion_proj") && itn != lns.end() && itn->second.C == 2 * Cc &&
+                    chain3(1, O, p + ".fusion_proj", p + ".mlp.fc1", p + ".mlp.fc2", &itn->second, os.p, os.ld, (p + ".tail").c_str())) {
+                    if (go()) { launch_unsqueeze_nonanchor(os, out, st); after_launch("local_unsqueeze"); }
+                    ws_off = mark;
+                    return;
+                }
+            }
             if (folds && convs.count(p + ".fusion_proj")) gemm(O, p + ".fusion_proj", 1, 0, &pr, EpiOpt());
             else {
             gemm(O, p + ".fusion", 1, 0, &fu, EpiOpt());

@@ -165,4 +165,20 @@ bool conv_halo_supported(const ConvHaloArgs& a);
 int launch_conv_halo(const ConvHaloArgs& a, cudaStream_t s);        // 0 ok
 const char* conv_halo_last_error();
 
+// ---- three chained per-pixel layers in one launch (chain3.cu), bf16: rows [M][K1] -> [M][N3]
+struct Chain3Args {
+    int mode;                               // 0: EntropyParameters tail (GELU, GELU, fp32 out); 1: LocalContext tail (LayerNorm, GELU, + projection, bf16 out)
+    const void* in; int M, K1, ld;          // bf16 rows
+    const void* w1; int K1pad;              // bf16 [N1][K1pad]
+    const void* w2;                         // bf16 [N2][N1]
+    const void* w3;                         // bf16 [N3][N2]
+    const float *b1, *b2, *b3;
+    const float *ln_g, *ln_b; float ln_eps; // mode 1
+    int N1, N2, N3;
+    void* out; int out_ld;                  // mode 0: float [M][out_ld]; mode 1: bf16 [M][out_ld]
+};
+bool chain3_supported(const Chain3Args& a);
+int launch_chain3(const Chain3Args& a, cudaStream_t s);             // 0 ok
+const char* chain3_last_error();
+
 }  // namespace mlic
