@@ -58,9 +58,23 @@ __device__ __forceinline__ uint32_t c3_pack(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// acc columns [c, c + 32) of this thread's row (already in `raw`) -> bias, GELU, bf16 pairs -> 16 columns of the next A operand
+__device__ __forceinline__ void c3_gelu_block(const uint32_t raw[32], const float* __restrict__ sb, uint32_t dst) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 b = *reinterpret_cast<const float2*>(&sb[2 * j]);
+        float2 v = __fadd2_rn(make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1])), b);
+        v = gelu2(v);
+        pk[j] = c3_pack(v.x, v.y);
+    }
+    c3_tmem_st8(dst, pk);
+    c3_tmem_st8(dst + 8, pk + 8);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(C3_THREADS, 1)
-chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
+chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p, unsigned long long* __restrict__ dbg) {
     extern __shared__ uint8_t c3_smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)c3_smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full[C3_MAXSTAGE], empty[C3_MAXSTAGE];
@@ -69,8 +83,14 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
     __shared__ __align__(16) float sB1[256], sB2[128], sB3[64], sG[64], sBt[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long tw[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_start = dbg ? clock64() : 0;
+#define C3_TIMED(acc, stmt) do { if (dbg) { const long long _t = clock64(); stmt; acc += clock64() - _t; } else { stmt; } } while (0)
     const int kch2 = p.N1 >> 6, kch3 = p.N2 >> 6;
     const int w2_chunk = p.N2 * 128, w3_chunk = p.N3 * 128;
+    // GEMM 3 of a tile is issued after the first `split` K chunks of GEMM 1 of the next tile (about the time phase 2 takes), the rest of
+    // that GEMM 1 behind it: the tensor pipe runs in issue order, and GEMM 3 must not wait behind a whole operand-feed-bound GEMM 1
+    const int split = min(p.kch1, MODE == C3_LOCAL ? 3 : 2);
     uint8_t* w2s = base;
     uint8_t* ring = base + (size_t)kch2 * w2_chunk;
 
@@ -110,8 +130,9 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
             for (int k = 0; k < kch2; ++k) tma_load_2d(w2s + (size_t)k * w2_chunk, &tm.w2, &w2_bar, k * 64, 0);
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-                for (int cc = 0; cc < p.kch1; ++cc) {
+            // ring order = the order the MMA thread consumes it: GEMM 1 of the first tile, then per tile GEMM 1 of the NEXT tile and W3 of this one
+            auto load_l1 = [&](int t, int c0, int c1) {
+                for (int cc = c0; cc < c1; ++cc) {
                     mbar_wait<false>(&empty[s], ph ^ 1);
                     uint8_t* st = ring + (size_t)s * p.stage_bytes;
                     mbar_expect_tx(&full[s], (uint32_t)(C3_A_BYTES + p.N1 * 128));
@@ -119,12 +140,18 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
                     tma_load_2d(st + C3_A_BYTES, &tm.w1, &full[s], cc * 64, 0);
                     if (++s == p.nstage) { s = 0; ph ^= 1; }
                 }
+            };
+            if ((int)blockIdx.x < p.ntiles) load_l1((int)blockIdx.x, 0, p.kch1);
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                const int tn = t + (int)gridDim.x;
+                if (tn < p.ntiles) load_l1(tn, 0, split);
                 for (int k = 0; k < kch3; ++k) {
                     mbar_wait<false>(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], (uint32_t)w3_chunk);
                     tma_load_2d(ring + (size_t)s * p.stage_bytes, &tm.w3, &full[s], k * 64, 0);
                     if (++s == p.nstage) { s = 0; ph ^= 1; }
                 }
+                if (tn < p.ntiles) load_l1(tn, split, p.kch1);
             }
         }
     } else if (warp == 1) {
@@ -133,24 +160,29 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
             const uint32_t idesc1 = idesc0 | ((uint32_t)(p.N1 >> 3) << 17), idesc2 = idesc0 | ((uint32_t)(p.N2 >> 3) << 17), idesc3 = idesc0 | ((uint32_t)(p.N3 >> 3) << 17);
             int s = 0, it = 0;
             uint32_t ph = 0;
+            // GEMM 1 of tile it + 1 is issued between GEMM 2 and GEMM 3 of tile it: its accumulator (EP: columns [0, 256), free once phase 1 of
+            // tile it has read them; LOCAL: the other 64-column slot, last read by phase 3 of tile it - 1) fills while the epilogue warps
+            // work on tile it, and the tensor pipe executes the MMAs in issue order
+            auto issue_l1 = [&](int itn, int c0, int c1) {
+                const uint32_t acc1 = tmem_base + C3_ACC1 + (MODE == C3_LOCAL ? (uint32_t)((itn & 1) * 64) : 0u);
+                for (int cc = c0; cc < c1; ++cc) {
+                    const int nk = min(4, (p.K1 - cc * 64 + 15) >> 4);
+                    C3_TIMED(tw[0], mbar_wait<false>(&full[s], ph));
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(ring + (size_t)s * p.stage_bytes);
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + (uint32_t)C3_A_BYTES);
+                    for (int kk = 0; kk < nk; ++kk) umma_bf16(acc1, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc1, (cc | kk) ? 1u : 0u);
+                    tcgen05_commit(&empty[s]);
+                    if (++s == p.nstage) { s = 0; ph ^= 1; }
+                }
+                if (c1 == p.kch1) tcgen05_commit(&acc1_full);
+            };
+            if ((int)blockIdx.x < p.ntiles) issue_l1(0, 0, p.kch1);
             mbar_wait(&w2_bar, 0);
             tcgen05_fence_after();
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
                 const uint32_t tp = (uint32_t)it & 1u;
-                mbar_wait<false>(&tile_done, tp ^ 1u);               // every accumulator of the previous tile has been read
-                tcgen05_fence_after();
-                for (int cc = 0; cc < p.kch1; ++cc) {
-                    const int nk = min(4, (p.K1 - cc * 64 + 15) >> 4);
-                    mbar_wait<false>(&full[s], ph);
-                    tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(ring + (size_t)s * p.stage_bytes);
-                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + (uint32_t)C3_A_BYTES);
-                    for (int kk = 0; kk < nk; ++kk) umma_bf16(tmem_base + C3_ACC1, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc1, (cc | kk) ? 1u : 0u);
-                    tcgen05_commit(&empty[s]);
-                    if (++s == p.nstage) { s = 0; ph ^= 1; }
-                }
-                tcgen05_commit(&acc1_full);
-                mbar_wait<false>(&h1_full, tp);
+                C3_TIMED(tw[1], mbar_wait<false>(&h1_full, tp));
                 tcgen05_fence_after();
                 for (int k = 0; k < kch2; ++k) {
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(w2s + (size_t)k * w2_chunk));
@@ -159,7 +191,9 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
                         umma_ts(tmem_base + C3_ACC2, tmem_base + C3_H1 + (uint32_t)((k * 4 + kk) * 8), bdesc + (uint64_t)(kk * 2), idesc2, (k | kk) ? 1u : 0u);
                 }
                 tcgen05_commit(&acc2_full);
-                mbar_wait<false>(&h2_full, tp);
+                const bool more = t + (int)gridDim.x < p.ntiles;
+                if (more) issue_l1(it + 1, 0, split);
+                C3_TIMED(tw[2], mbar_wait<false>(&h2_full, tp));
                 tcgen05_fence_after();
                 for (int k = 0; k < kch3; ++k) {
                     mbar_wait<false>(&full[s], ph);
@@ -172,7 +206,9 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
                     if (++s == p.nstage) { s = 0; ph ^= 1; }
                 }
                 tcgen05_commit(&acc3_full);
+                if (more) issue_l1(it + 1, split, p.kch1);
             }
+            if (dbg && blockIdx.x == 0) { dbg[0] = (unsigned long long)(clock64() - t_start); dbg[1] = (unsigned long long)tw[0]; dbg[2] = (unsigned long long)tw[1]; dbg[3] = (unsigned long long)tw[2]; }
         }
     } else if (warp >= 4) {
         const int q = warp & 3, sub = (warp - 4) >> 2;
@@ -182,54 +218,63 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
             const uint32_t tp = (uint32_t)it & 1u;
             const long long grow = (long long)t * 128 + row;
-            // ---- phase 1: acc1 -> H1
-            mbar_wait(&acc1_full, tp);
+            // ---- phase 1: acc1 -> H1.  H1 overlays H2 / acc3 of the previous tile: no warp may store before every warp has finished
+            // its phase 3 (tile_done doubles as the barrier among the epilogue warps)
+            const uint32_t acc1c = C3_ACC1 + (MODE == C3_LOCAL ? (uint32_t)((it & 1) * 64) : 0u);
+            if (it > 0) C3_TIMED(tw[3], mbar_wait(&tile_done, tp ^ 1u));
+            C3_TIMED(tw[0], mbar_wait(&acc1_full, tp));
             tcgen05_fence_after();
             if constexpr (MODE == C3_EP) {
-                const int w1c = p.N1 >> 2;                          // columns of this warp: [sub * w1c, + w1c), a multiple of 16
+                // columns of this warp: [sub * N1 / 4, + N1 / 4) in blocks of 32; the loads of block i + 1 are in flight while block i is computed
+                const int w1c = p.N1 >> 2;
+                uint32_t raw[2][32];
+                int c = sub * w1c;
+                const int cend = c + w1c;
+                tmem_ld16(lane_base + acc1c + (uint32_t)c, raw[0]);
+                tmem_ld16(lane_base + acc1c + (uint32_t)(c + 16), raw[0] + 16);
+                tmem_ld_wait();
 #pragma unroll 1
-                for (int c = sub * w1c; c < (sub + 1) * w1c; c += 16) {
-                    uint32_t raw[16], pk[8];
-                    tmem_ld16(lane_base + C3_ACC1 + (uint32_t)c, raw);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float2 b = *reinterpret_cast<const float2*>(&sB1[c + 2 * j]);
-                        float2 v = __fadd2_rn(make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1])), b);
-                        v = gelu2(v);
-                        pk[j] = c3_pack(v.x, v.y);
+                for (; c < cend; c += 64) {
+                    const bool more = c + 32 < cend;
+                    if (more) {
+                        tmem_ld16(lane_base + acc1c + (uint32_t)(c + 32), raw[1]);
+                        tmem_ld16(lane_base + acc1c + (uint32_t)(c + 48), raw[1] + 16);
                     }
-                    c3_tmem_st8(lane_base + C3_H1 + (uint32_t)(c >> 1), pk);
+                    c3_gelu_block(raw[0], sB1 + c, lane_base + C3_H1 + (uint32_t)(c >> 1));
+                    if (more) {
+                        tmem_ld_wait();
+                        if (c + 64 < cend) {
+                            tmem_ld16(lane_base + acc1c + (uint32_t)(c + 64), raw[0]);
+                            tmem_ld16(lane_base + acc1c + (uint32_t)(c + 80), raw[0] + 16);
+                        }
+                        c3_gelu_block(raw[1], sB1 + c + 32, lane_base + C3_H1 + (uint32_t)((c + 32) >> 1));
+                        if (c + 64 < cend) tmem_ld_wait();
+                    }
                 }
             } else {
-                // LayerNorm over the N1 = 64 columns of the row: every warp of the quarter computes the row statistics (two passes over the
-                // accumulator, which stays in TMEM), then normalises its own 16 columns
-                float mean = 0.f, var = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < 64; c += 16) {
-                    uint32_t raw[16];
-                    tmem_ld16(lane_base + C3_ACC1 + (uint32_t)c, raw);
-                    tmem_ld_wait();
+                // LayerNorm over the N1 = 64 columns of the row: every warp of the quarter reads the whole row once (64 registers), computes
+                // its statistics in two passes over the registers, then normalises its own 16 columns (re-read: `sub` is not a constant)
+                uint32_t raw[64];
+                tmem_ld16(lane_base + acc1c, raw);
+                tmem_ld16(lane_base + acc1c + 16u, raw + 16);
+                tmem_ld16(lane_base + acc1c + 32u, raw + 32);
+                tmem_ld16(lane_base + acc1c + 48u, raw + 48);
+                tmem_ld_wait();
+                float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) mean += __uint_as_float(raw[j]) + sB1[c + j];
-                }
-                mean *= (1.f / 64.f);
-#pragma unroll 1
-                for (int c = 0; c < 64; c += 16) {
-                    uint32_t raw[16];
-                    tmem_ld16(lane_base + C3_ACC1 + (uint32_t)c, raw);
-                    tmem_ld_wait();
+                for (int j = 0; j < 64; ++j) { const float x = __uint_as_float(raw[j]) + sB1[j]; raw[j] = __float_as_uint(x); m4[j & 3] += x; }
+                const float mean = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (1.f / 64.f);
+                float v4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { const float d = (__uint_as_float(raw[j]) + sB1[c + j]) - mean; var = fmaf(d, d, var); }
-                }
-                const float rstd = rsqrtf(var * (1.f / 64.f) + p.ln_eps);
+                for (int j = 0; j < 64; ++j) { const float d = __uint_as_float(raw[j]) - mean; v4[j & 3] = fmaf(d, d, v4[j & 3]); }
+                const float rstd = rsqrtf(((v4[0] + v4[1]) + (v4[2] + v4[3])) * (1.f / 64.f) + p.ln_eps);
                 const int c = sub * 16;
-                uint32_t raw[16], pk[8];
-                tmem_ld16(lane_base + C3_ACC1 + (uint32_t)c, raw);
+                uint32_t own[16], pk[8];
+                tmem_ld16(lane_base + acc1c + (uint32_t)c, own);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float x0 = (__uint_as_float(raw[2 * j]) + sB1[c + 2 * j]) - mean, x1 = (__uint_as_float(raw[2 * j + 1]) + sB1[c + 2 * j + 1]) - mean;
+                    const float x0 = (__uint_as_float(own[2 * j]) + sB1[c + 2 * j]) - mean, x1 = (__uint_as_float(own[2 * j + 1]) + sB1[c + 2 * j + 1]) - mean;
                     pk[j] = c3_pack(fmaf(x0 * rstd, sG[c + 2 * j], sBt[c + 2 * j]), fmaf(x1 * rstd, sG[c + 2 * j + 1], sBt[c + 2 * j + 1]));
                 }
                 c3_tmem_st8(lane_base + C3_H1 + (uint32_t)(c >> 1), pk);
@@ -239,31 +284,22 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&h1_full);
             // ---- phase 2: acc2 -> H2 (bias, GELU)
-            mbar_wait(&acc2_full, tp);
+            C3_TIMED(tw[1], mbar_wait(&acc2_full, tp));
             tcgen05_fence_after();
             {
-                const int w2c = p.N2 >> 2;
-#pragma unroll 1
-                for (int c = sub * w2c; c < (sub + 1) * w2c; c += 16) {
-                    uint32_t raw[16], pk[8];
-                    tmem_ld16(lane_base + C3_ACC2 + (uint32_t)c, raw);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float2 b = *reinterpret_cast<const float2*>(&sB2[c + 2 * j]);
-                        float2 v = __fadd2_rn(make_float2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1])), b);
-                        v = gelu2(v);
-                        pk[j] = c3_pack(v.x, v.y);
-                    }
-                    c3_tmem_st8(lane_base + C3_H2 + (uint32_t)(c >> 1), pk);
-                }
+                const int c = sub * 32;                             // N2 = 128: one block of 32 columns per warp
+                uint32_t raw[32];
+                tmem_ld16(lane_base + C3_ACC2 + (uint32_t)c, raw);
+                tmem_ld16(lane_base + C3_ACC2 + (uint32_t)(c + 16), raw + 16);
+                tmem_ld_wait();
+                c3_gelu_block(raw, sB2 + c, lane_base + C3_H2 + (uint32_t)(c >> 1));
             }
             c3_tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h2_full);
             // ---- phase 3: acc3 (+ the folded projection, LOCAL) -> memory; N3 = 64: 16 columns per warp
-            mbar_wait(&acc3_full, tp);
+            C3_TIMED(tw[2], mbar_wait(&acc3_full, tp));
             tcgen05_fence_after();
             {
                 const int c = sub * 16;
@@ -274,7 +310,7 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) + sB3[c + j];
                 if constexpr (MODE == C3_LOCAL) {
-                    tmem_ld16(lane_base + C3_ACC1 + (uint32_t)c, raw);
+                    tmem_ld16(lane_base + acc1c + (uint32_t)c, raw);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(raw[j]) + sB1[c + j];
@@ -295,6 +331,7 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&tile_done);
         }
+        if (dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { dbg[4] = (unsigned long long)(clock64() - t_start); dbg[5] = (unsigned long long)tw[0]; dbg[6] = (unsigned long long)tw[1]; dbg[7] = (unsigned long long)tw[2]; dbg[8] = (unsigned long long)tw[3]; }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -316,7 +353,7 @@ bool chain3_supported(const Chain3Args& a) {
     if (!a.in || !a.w1 || !a.w2 || !a.w3 || !a.b1 || !a.b2 || !a.b3 || !a.out) return false;
     if (a.M <= 0 || a.K1 < 16 || (a.K1 % 8) != 0 || a.K1pad % 64 != 0 || a.K1pad < a.K1 || (a.ld % 8) != 0) return false;
     if (a.N2 != 128 || a.N3 != 64) return false;
-    if (a.mode == 0) { if (a.N1 % 64 != 0 || a.N1 < 64 || a.N1 > 256 || (a.out_ld % 4) != 0 || ((uintptr_t)a.out % 16) != 0) return false; }
+    if (a.mode == 0) { if (a.N1 % 128 != 0 || a.N1 < 128 || a.N1 > 256 || (a.out_ld % 4) != 0 || ((uintptr_t)a.out % 16) != 0) return false; }
     else if (a.mode == 1) { if (a.N1 != 64 || !a.ln_g || !a.ln_b || (a.out_ld % 8) != 0 || ((uintptr_t)a.out % 16) != 0) return false; }
     else return false;
     if (((uintptr_t)a.in % 16) != 0 || ((uintptr_t)a.w1 % 16) != 0 || ((uintptr_t)a.w2 % 16) != 0 || ((uintptr_t)a.w3 % 16) != 0) return false;
@@ -377,7 +414,26 @@ int launch_chain3(const Chain3Args& a, cudaStream_t s) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    cudaError_t er = cudaLaunchKernelEx(&cfg, fn, tm, p);
+    static const int dbgmode = getenv("MLIC_TC_DEBUG") ? atoi(getenv("MLIC_TC_DEBUG")) : 0;
+    unsigned long long* dbg = nullptr;
+    if (dbgmode & 32) {
+        static unsigned long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc((void**)&dbuf, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(dbuf, 0, 16 * sizeof(unsigned long long), s);
+        dbg = dbuf;
+    }
+    cudaError_t er = cudaLaunchKernelEx(&cfg, fn, tm, p, dbg);
+    if (dbg && er == cudaSuccess) {
+        static int printed[2] = {0, 0};
+        unsigned long long h[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
+        if (printed[a.mode]++ < 3) {
+            const double tiles = (double)((p.ntiles + cfg.gridDim.x - 1) / cfg.gridDim.x);
+            fprintf(stderr, "[chain3 dbg mode %d] tiles/cta %.0f stages %d | per tile: mma total %.0f wait-ring %.0f wait-h1 %.0f wait-h2 %.0f | epilogue w4 total %.0f wait-acc1 %.0f wait-acc2 %.0f wait-acc3 %.0f wait-tile-done %.0f\n",
+                    a.mode, tiles, p.nstage, h[0] / tiles, h[1] / tiles, h[2] / tiles, h[3] / tiles, h[4] / tiles, h[5] / tiles, h[6] / tiles, h[7] / tiles, h[8] / tiles);
+        }
+    }
     if (er != cudaSuccess) { snprintf(g_c3_err, sizeof g_c3_err, "chain3 launch: %s (smem %d)", cudaGetErrorString(er), smem); return 5; }
     return 0;
 }
