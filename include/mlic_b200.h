@@ -175,6 +175,17 @@ int mlic_local_attn(int impl, const void* F, int B, int H, int W, const float* r
 int mlic_lin_attn(int precision, const void* qkv, int B, int H, int W, int D, int heads, int par_kv, int par_q, void* out, int iters,
                   float* avg_ms, void* cuda_stream);
 
+/* Stand-alone three-layer per-pixel chain of the bf16 fast mode in ONE launch (chain3.cu), replacing per row of `in`
+ *   mode 0: EntropyParameters layers 1..3 (modules/transform/entropy.py:13-17): out = W3 GELU(W2 GELU(W1 in + b1) + b2) + b3, fp32
+ *   mode 1: the LocalContext tail (modules/transform/context.py:108-110 with proj folded into fusion): p = W1 in + b1,
+ *           out = p + W3 GELU(W2 LayerNorm(p) + b2) + b3, bf16
+ * in DEVICE bf16 [M][K1]; w1 [N1][K1], w2 [N2][N1], w3 [N3][N2], biases, ln_gamma / ln_beta [N1] HOST fp32;
+ * N2 = 128, N3 = 64, N1 = 128 | 256 (mode 0) or 64 (mode 1); out DEVICE fp32 (mode 0) / bf16 (mode 1) [M][N3].
+ * Timing as mlic_conv2d_nhwc.  Kernel-level test / micro-benchmark hook. */
+int mlic_chain3(int mode, const void* in, int M, int K1, const float* w1, const float* b1, int N1, const float* w2, const float* b2, int N2,
+                const float* w3, const float* b3, int N3, const float* ln_gamma, const float* ln_beta, void* out, int iters, float* avg_ms,
+                void* cuda_stream);
+
 /* Stand-alone g_a stage-0 head of the bf16 path (ResidualBlockWithStride(3 -> N, stride 2), modules/layers/res_blk.py:82-93
  * with DepthWiseConv, conv.py:46-63): x DEVICE fp32 NCHW [B,3,H,W] ->
  *   t_out    = GELU(point_conv(depth_conv_s2(x)))   DEVICE bf16 NHWC [B,H/2,W/2,N]

@@ -14,7 +14,7 @@ MODE_FORWARD, MODE_COMPRESS, MODE_DECODER, MODE_DECOMPRESS = 0, 1, 2, 3
 EXPORTS = (
     "mlic_engine_create", "mlic_engine_destroy", "mlic_engine_set_param", "mlic_engine_finalize",
     "mlic_engine_set_option", "mlic_engine_set_option_f", "mlic_workspace_bytes", "mlic_run", "mlic_run_host", "mlic_last_launch_count",
-    "mlic_profile_read", "mlic_profile_read_top", "mlic_trace_dump", "mlic_conv2d_nhwc", "mlic_dwconv3x3_nhwc", "mlic_dsconv_nhwc", "mlic_ds_gdn_nhwc", "mlic_final_subpel", "mlic_local_attn", "mlic_lin_attn", "mlic_ga_head", "mlic_gaussian_conditional", "mlic_last_error", "mlic_version",
+    "mlic_profile_read", "mlic_profile_read_top", "mlic_trace_dump", "mlic_conv2d_nhwc", "mlic_dwconv3x3_nhwc", "mlic_dsconv_nhwc", "mlic_ds_gdn_nhwc", "mlic_final_subpel", "mlic_local_attn", "mlic_lin_attn", "mlic_chain3", "mlic_ga_head", "mlic_gaussian_conditional", "mlic_last_error", "mlic_version",
     "mlic_engine_set_cdf", "mlic_decompress", "mlic_pmf_to_quantized_cdf", "mlic_rans_encode_bound", "mlic_rans_encode",
     "mlic_rans_decoder_create", "mlic_rans_decoder_destroy", "mlic_rans_decode_stream",
 )
@@ -68,6 +68,7 @@ def lib():
     L.mlic_final_subpel.argtypes = [i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, C.POINTER(f32), vp]
     L.mlic_local_attn.argtypes = [i32, vp, i32, i32, i32, vp, vp, i32, C.POINTER(f32), vp]
     L.mlic_lin_attn.argtypes = [i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, C.POINTER(f32), vp]
+    L.mlic_chain3.argtypes = [i32, vp, i32, i32, vp, vp, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, C.POINTER(f32), vp]
     L.mlic_ga_head.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, C.POINTER(f32), vp]
     L.mlic_gaussian_conditional.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
     L.mlic_engine_set_cdf.argtypes = [vp, vp, i32, vp, vp, i32]

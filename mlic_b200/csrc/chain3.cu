@@ -36,6 +36,7 @@ struct C3Params {
     const float *b1, *b2, *b3, *ln_g, *ln_b;
     void* out; int out_ld;
     float ln_eps;
+    int unsq_H, unsq_W;             // LOCAL: != 0: row r is the r-th NON-ANCHOR pixel of a [.., H, W] grid (utils/ckbd.py squeeze order); `out` is that grid
 };
 struct C3Maps { CUtensorMap a, w1, w2, w3; };
 
@@ -321,7 +322,14 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p, unsigned long
 #pragma unroll
                         for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     } else {
-                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.out_ld + c);
+                        long long orow = grow;
+                        if (p.unsq_W) {                             // squeezed row -> its pixel: w = 2 j + (h & 1)
+                            const int W2 = p.unsq_W >> 1;
+                            const long long bh = grow / W2;
+                            const int j = (int)(grow - bh * W2), h = (int)(bh % p.unsq_H);
+                            orow = bh * p.unsq_W + 2 * j + (h & 1);
+                        }
+                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)orow * p.out_ld + c);
                         o[0] = make_uint4(c3_pack(v[0], v[1]), c3_pack(v[2], v[3]), c3_pack(v[4], v[5]), c3_pack(v[6], v[7]));
                         o[1] = make_uint4(c3_pack(v[8], v[9]), c3_pack(v[10], v[11]), c3_pack(v[12], v[13]), c3_pack(v[14], v[15]));
                     }
@@ -371,7 +379,7 @@ int launch_chain3(const Chain3Args& a, cudaStream_t s) {
     p.M = a.M; p.ntiles = (a.M + 127) / 128;
     p.K1 = a.K1; p.kch1 = a.K1pad / 64; p.N1 = a.N1; p.N2 = a.N2; p.N3 = a.N3;
     p.b1 = a.b1; p.b2 = a.b2; p.b3 = a.b3; p.ln_g = a.ln_g; p.ln_b = a.ln_b; p.ln_eps = a.ln_eps;
-    p.out = a.out; p.out_ld = a.out_ld;
+    p.out = a.out; p.out_ld = a.out_ld; p.unsq_H = a.unsq_H; p.unsq_W = a.unsq_W;
     p.stage_bytes = C3_A_BYTES + a.N1 * 128;
     const int resident = (a.N1 / 64) * a.N2 * 128;
     const int budget = 232448 - 4096 - 1024;            // (static shared memory: barriers + biases, ~2.5 KB)

@@ -1026,7 +1026,7 @@ struct mlic_engine {
     // output is multiplied by that mask (mlicpp.py:112-117,148-152); out32 is then squeezed, [B*h*(w/2)][2C].
     bool ep_squeezed(int Hh, int Ww) const { return bf && use_tc && fuse && (Hh % 2) == 0 && (Ww % 2) == 0; }
     // three chained layers in one launch (chain3.cu); false: not taken, nothing launched
-    bool chain3(int mode, const Act& rows, const std::string& k1, const std::string& k2, const std::string& k3, const LnW* ln, void* out, int out_ld, const char* what) {
+    bool chain3(int mode, const Act& rows, const std::string& k1, const std::string& k2, const std::string& k3, const LnW* ln, void* out, int out_ld, const char* what, int unsq_H = 0, int unsq_W = 0) {
         if (!(bf && use_tc && fuse && chain)) return false;
         const ConvW *w1 = cw(k1), *w2 = cw(k2), *w3 = cw(k3);
         if (!w1 || !w2 || !w3 || w1->ks != 1 || w2->ks != 1 || w3->ks != 1) return false;
@@ -1037,7 +1037,7 @@ struct mlic_engine {
         a.w1 = w1->wbf; a.K1pad = w1->Cpad; a.w2 = w2->wbf; a.w3 = w3->wbf; a.b1 = w1->bias; a.b2 = w2->bias; a.b3 = w3->bias;
         a.N1 = w1->N; a.N2 = w2->N; a.N3 = w3->N;
         if (ln) { a.ln_g = ln->g; a.ln_b = ln->b; a.ln_eps = 1e-5f; }
-        a.out = out; a.out_ld = out_ld;
+        a.out = out; a.out_ld = out_ld; a.unsq_H = unsq_H; a.unsq_W = unsq_W;
         if (dry) { a.in = a.out = (void*)16; }                     // (the dry run has no buffers: geometry only)
         if (!chain3_supported(a)) return false;
         if (!go()) return true;
@@ -1220,11 +1220,15 @@ struct mlic_engine {
             Act fu = act(1, 1, Mh, 2 * Cc), pr = act(1, 1, Mh, 2 * Cc), n2 = act(1, 1, Mh, 2 * Cc), os = act(1, 1, Mh, 2 * Cc);
             {
                 auto itn = lns.find(p + ".norm2");
-                if (folds && convs.count(p + ".fusion_proj") && itn != lns.end() && itn->second.C == 2 * Cc &&
-                    chain3(1, O, p + ".fusion_proj", p + ".mlp.fc1", p + ".mlp.fc2", &itn->second, os.p, os.ld, (p + ".tail").c_str())) {
-                    if (go()) { launch_unsqueeze_nonanchor(os, out, st); after_launch("local_unsqueeze"); }
-                    ws_off = mark;
-                    return;
+                if (folds && convs.count(p + ".fusion_proj") && itn != lns.end() && itn->second.C == 2 * Cc) {
+                    // with squeezed EntropyParameters rows only the non-anchor pixels of `out` are ever read: the chain stores each row at its pixel
+                    const bool direct = ep_squeezed(x.H, x.W) && (out.ld % 8) == 0 && ((uintptr_t)out.p % 16) == 0;
+                    if (direct ? chain3(1, O, p + ".fusion_proj", p + ".mlp.fc1", p + ".mlp.fc2", &itn->second, out.p, out.ld, (p + ".tail").c_str(), x.H, x.W)
+                               : chain3(1, O, p + ".fusion_proj", p + ".mlp.fc1", p + ".mlp.fc2", &itn->second, os.p, os.ld, (p + ".tail").c_str())) {
+                        if (!direct && go()) { launch_unsqueeze_nonanchor(os, out, st); after_launch("local_unsqueeze"); }
+                        ws_off = mark;
+                        return;
+                    }
                 }
             }
             if (folds && convs.count(p + ".fusion_proj")) gemm(O, p + ".fusion_proj", 1, 0, &pr, EpiOpt());
@@ -1936,6 +1940,49 @@ int mlic_lin_attn(int precision, const void* qkv, int B, int H, int W, int D, in
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(scratch);
     if (r) return fail("linear attention: unsupported head dim %d", hd);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mlic_chain3(int mode, const void* in, int M, int K1, const float* w1, const float* b1, int N1, const float* w2, const float* b2, int N2,
+                const float* w3, const float* b3, int N3, const float* ln_gamma, const float* ln_beta, void* out, int iters, float* avg_ms,
+                void* cuda_stream) {
+    if (!in || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !out || iters < 1 || M < 1 || (mode == 1 && (!ln_gamma || !ln_beta))) return fail("bad arguments");
+    mlic_engine e;
+    e.N = e.M = e.S = e.C = 0; e.kind = 0; e.sd = e.vbr = false; e.Me = 0; e.rc = 0;
+    e.pack_conv_raw("l1", w1, b1, N1, K1, 1, 0);
+    e.pack_conv_raw("l2", w2, b2, N2, N1, 1, 0);
+    e.pack_conv_raw("l3", w3, b3, N3, N2, 1, 0);
+    if (e.rc) return e.rc;
+    const ConvW &c1 = e.convs["l1"], &c2 = e.convs["l2"], &c3 = e.convs["l3"];
+    Chain3Args a;
+    memset(&a, 0, sizeof a);
+    a.mode = mode; a.in = in; a.M = M; a.K1 = K1; a.ld = K1;
+    a.w1 = c1.wbf; a.K1pad = c1.Cpad; a.w2 = c2.wbf; a.w3 = c3.wbf; a.b1 = c1.bias; a.b2 = c2.bias; a.b3 = c3.bias;
+    a.N1 = N1; a.N2 = N2; a.N3 = N3; a.out = out; a.out_ld = N3; a.ln_eps = 1e-5f;
+    if (mode == 1) {
+        a.ln_g = e.upload(std::vector<float>(ln_gamma, ln_gamma + N1));
+        a.ln_b = e.upload(std::vector<float>(ln_beta, ln_beta + N1));
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int r = 0;
+    if (c2.Cpad != N1 || c3.Cpad != N2 || !chain3_supported(a)) r = 1;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    for (int i = 0; i < iters && !r; ++i) {
+        if (i == 1) CUDA_OK(cudaEventRecord(e0, st));
+        r = launch_chain3(a, st);
+    }
+    if (iters == 1) CUDA_OK(cudaEventRecord(e0, st));
+    CUDA_OK(cudaEventRecord(e1, st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    if (avg_ms) *avg_ms = iters > 1 ? ms / (iters - 1) : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (void* q : e.dev_allocs) cudaFree(q);
+    e.dev_allocs.clear();
+    if (r) return fail("chain3: %s", r == 1 && !chain3_last_error()[0] ? "unsupported layer chain" : chain3_last_error());
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -176,6 +176,7 @@ struct Chain3Args {
     const float *ln_g, *ln_b; float ln_eps; // mode 1
     int N1, N2, N3;
     void* out; int out_ld;                  // mode 0: float [M][out_ld]; mode 1: bf16 [M][out_ld]
+    int unsq_H, unsq_W;                     // mode 1, != 0: rows are the non-anchor pixels of a [.., H, W] grid in squeeze order and `out` is that grid (NHWC, out_ld per pixel): each row is stored at its pixel
 };
 bool chain3_supported(const Chain3Args& a);
 int launch_chain3(const Chain3Args& a, cudaStream_t s);             // 0 ok

@@ -183,3 +183,27 @@ def final_subpel(x, weight, bias, impl=1, iters=1):
                                                 C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), iters, C.byref(ms),
                                                 C.c_void_p(st)))
     return out, float(ms.value)
+
+
+def chain3(x, w1, b1, w2, b2, w3, b3, ln=None, iters=1):
+    """Three chained per-row layers in one launch (chain3.cu).  x: CUDA bf16 [M, K1]; w*: [N, K] fp32 (any device).
+    ln = None: EntropyParameters tail, out fp32 [M, N3] = W3 GELU(W2 GELU(W1 x + b1) + b2) + b3;
+    ln = (gamma, beta): LocalContext tail, p = W1 x + b1, out bf16 = p + W3 GELU(W2 LayerNorm(p) + b2) + b3.  -> (out, avg ms)"""
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.bfloat16 and x.dim() == 2
+    M, K1 = x.shape
+    hs = [t.detach().to("cpu", torch.float32).contiguous() for t in (w1, b1, w2, b2, w3, b3)]
+    N1, N2, N3 = hs[0].shape[0], hs[2].shape[0], hs[4].shape[0]
+    mode = 0 if ln is None else 1
+    g = bt = None
+    if ln is not None:
+        g, bt = (t.detach().to("cpu", torch.float32).contiguous() for t in ln)
+    out = torch.empty((M, N3), dtype=torch.float32 if mode == 0 else torch.bfloat16, device=x.device)
+    ms = C.c_float(0)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mlic_chain3(mode, C.c_void_p(x.data_ptr()), M, K1, C.c_void_p(hs[0].data_ptr()), C.c_void_p(hs[1].data_ptr()), N1,
+                                          C.c_void_p(hs[2].data_ptr()), C.c_void_p(hs[3].data_ptr()), N2, C.c_void_p(hs[4].data_ptr()),
+                                          C.c_void_p(hs[5].data_ptr()), N3, C.c_void_p(g.data_ptr()) if g is not None else None,
+                                          C.c_void_p(bt.data_ptr()) if bt is not None else None, C.c_void_p(out.data_ptr()), iters, C.byref(ms),
+                                          C.c_void_p(st)))
+    return out, float(ms.value)

@@ -278,3 +278,34 @@ def test_final_subpel_conv(impl, B, H, W, C):
     out, _ = ops.final_subpel(x, w, b, impl=impl)
     ref = F.pixel_shuffle(F.conv2d(x.float().permute(0, 3, 1, 2), w.cuda(), b.cuda(), padding=1), 2)
     np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,K1,N1,ln", [(1000, 320, 256, False), (128 * 149 + 37, 320, 256, False), (777, 128, 128, False), (1000, 800, 64, True), (128 * 150 + 5, 800, 64, True)])
+def test_chained_three_layer_kernel(M, K1, N1, ln):
+    """chain3.cu (EntropyParameters layers 1..3, entropy.py:13-17; the LocalContext tail, context.py:108-110): the intermediates are
+    bf16 A operands in tensor memory, so the statement it is compared with rounds them to bf16 at the same places (operands bf16,
+    accumulation fp32, exact erf GELU: the kernel's tanh-form GELU is within 3e-4); ragged last tile and more tiles than SMs included."""
+    torch.manual_seed(8)
+    x = torch.randn(M, K1, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn(N1, K1) / K1 ** 0.5).to(torch.bfloat16).float()
+    w2 = (torch.randn(128, N1) / N1 ** 0.5).to(torch.bfloat16).float()
+    w3 = (torch.randn(64, 128) / 128 ** 0.5).to(torch.bfloat16).float()
+    b1, b2, b3 = torch.randn(N1) * 0.2, torch.randn(128) * 0.2, torch.randn(64) * 0.2
+    bfr = lambda t: t.to(torch.bfloat16).float()
+    xf = x.float().cpu()
+    if not ln:
+        out, _ = ops.chain3(x, w1, b1, w2, b2, w3, b3)
+        h1 = bfr(torch.nn.functional.gelu(xf @ w1.T + b1))
+        h2 = bfr(torch.nn.functional.gelu(h1 @ w2.T + b2))
+        ref = h2 @ w3.T + b3
+        assert out.dtype == torch.float32
+        torch.testing.assert_close(out.cpu(), ref, atol=2e-2, rtol=1e-2)
+    else:
+        g, bt = 1.0 + 0.1 * torch.randn(N1), 0.1 * torch.randn(N1)
+        out, _ = ops.chain3(x, w1, b1, w2, b2, w3, b3, ln=(g, bt))
+        p = xf @ w1.T + b1
+        h1 = bfr(torch.nn.functional.layer_norm(p, (N1,), g, bt, 1e-5))
+        h2 = bfr(torch.nn.functional.gelu(h1 @ w2.T + b2))
+        ref = p + h2 @ w3.T + b3
+        assert out.dtype == torch.bfloat16
+        torch.testing.assert_close(out.float().cpu(), ref, atol=4e-2, rtol=2e-2)
