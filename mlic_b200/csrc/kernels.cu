@@ -1740,15 +1740,15 @@ __device__ __forceinline__ float vbr_deq(float sq, float rgain, float mu) { retu
 template <typename T, typename I>
 __global__ void quant_anchor_kernel(QuantArgs a) {
     pdl_wait();
+    // grid = (chunks of a row's W * C elements, H, B): one division (a shift for C = 32) per element instead of four
     const int C = a.C;
-    const I total = (I)a.B * a.H * a.W * C;
-    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
-        I p = i / C;
-        int c = (int)(i - p * C);
-        int w = (int)(p % a.W);
-        I q = p / a.W;
-        int h = (int)(q % a.H);
-        int b = (int)(q / a.H);
+    const int ir = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int once = (ir < a.W * C) ? 0 : 1; once < 1; ++once) {
+        const int h = blockIdx.y, b = blockIdx.z;
+        const int w = (C & (C - 1)) ? ir / C : ir >> (31 - __clz(C));
+        const int c = ir - w * C;
+        const I q = (I)b * a.H + h;
+        const I p = q * a.W + w;
         T* slot = reinterpret_cast<T*>(a.slot.p) + (long long)p * a.slot.ld + c;
         if (((h + w) & 1) == 0) { if (a.mode != 3) *slot = from_f<T>(0.f); continue; }
         const long long pe = a.sq ? ((long long)q * (a.W >> 1) + (w >> 1)) : (long long)p;       // row of this pixel in the entropy-parameter buffer
@@ -1782,15 +1782,15 @@ __global__ void quant_anchor_kernel(QuantArgs a) {
 template <typename T, typename I>
 __global__ void quant_nonanchor_kernel(QuantArgs a) {
     pdl_wait();
+    // grid = (chunks of a row's W * C elements, H, B): one division (a shift for C = 32) per element instead of four
     const int C = a.C;
-    const I total = (I)a.B * a.H * a.W * C;
-    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
-        I p = i / C;
-        int c = (int)(i - p * C);
-        int w = (int)(p % a.W);
-        I q = p / a.W;
-        int h = (int)(q % a.H);
-        int b = (int)(q / a.H);
+    const int ir = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int once = (ir < a.W * C) ? 0 : 1; once < 1; ++once) {
+        const int h = blockIdx.y, b = blockIdx.z;
+        const int w = (C & (C - 1)) ? ir / C : ir >> (31 - __clz(C));
+        const int c = ir - w * C;
+        const I q = (I)b * a.H + h;
+        const I p = q * a.W + w;
         const bool anchor = ((h + w) & 1) == 1;
         T* slot = reinterpret_cast<T*>(a.slot.p) + (long long)p * a.slot.ld + c;
         const float* pp = anchor ? a.pa : a.pn;
@@ -1829,21 +1829,24 @@ __global__ void quant_nonanchor_kernel(QuantArgs a) {
     }
 }
 
+static bool quant_grid(const QuantArgs& a, dim3& grid, bool& small) {
+    const long long total = (long long)a.B * a.H * a.W * a.C;
+    if (!total) return false;
+    grid = dim3((unsigned)cdiv((long long)a.W * a.C, 256), (unsigned)a.H, (unsigned)a.B);
+    small = total < 0x7fffffffLL;
+    return true;
+}
 void launch_quant_anchor(int bf, const QuantArgs& a, cudaStream_t s) {
-    long long total = (long long)a.B * a.H * a.W * a.C;
-    if (!total) return;
-    int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
-    const bool small = total + (long long)blocks * 256 < 0x7fffffffLL;
-    if (bf) { if (small) launch_k(quant_anchor_kernel<bf16, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_anchor_kernel<bf16, long long>, dim3(blocks), dim3(256), 0, s, a); }
-    else { if (small) launch_k(quant_anchor_kernel<float, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_anchor_kernel<float, long long>, dim3(blocks), dim3(256), 0, s, a); }
+    dim3 grid; bool small;
+    if (!quant_grid(a, grid, small)) return;
+    if (bf) { if (small) launch_k(quant_anchor_kernel<bf16, int>, grid, dim3(256), 0, s, a); else launch_k(quant_anchor_kernel<bf16, long long>, grid, dim3(256), 0, s, a); }
+    else { if (small) launch_k(quant_anchor_kernel<float, int>, grid, dim3(256), 0, s, a); else launch_k(quant_anchor_kernel<float, long long>, grid, dim3(256), 0, s, a); }
 }
 void launch_quant_nonanchor(int bf, const QuantArgs& a, cudaStream_t s) {
-    long long total = (long long)a.B * a.H * a.W * a.C;
-    if (!total) return;
-    int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
-    const bool small = total + (long long)blocks * 256 < 0x7fffffffLL;
-    if (bf) { if (small) launch_k(quant_nonanchor_kernel<bf16, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_nonanchor_kernel<bf16, long long>, dim3(blocks), dim3(256), 0, s, a); }
-    else { if (small) launch_k(quant_nonanchor_kernel<float, int>, dim3(blocks), dim3(256), 0, s, a); else launch_k(quant_nonanchor_kernel<float, long long>, dim3(blocks), dim3(256), 0, s, a); }
+    dim3 grid; bool small;
+    if (!quant_grid(a, grid, small)) return;
+    if (bf) { if (small) launch_k(quant_nonanchor_kernel<bf16, int>, grid, dim3(256), 0, s, a); else launch_k(quant_nonanchor_kernel<bf16, long long>, grid, dim3(256), 0, s, a); }
+    else { if (small) launch_k(quant_nonanchor_kernel<float, int>, grid, dim3(256), 0, s, a); else launch_k(quant_nonanchor_kernel<float, long long>, grid, dim3(256), 0, s, a); }
 }
 
 // Stand-alone flat version (any layout, elementwise): the GaussianConditional boundary of the C ABI.
