@@ -7,7 +7,9 @@ from mlic_b200 import ops
 SHAPES = [("ds192 @544x960 b4", 4, 544, 960, 192, 192, True, "gelu"), ("ds192 @544x960 b4 nores", 4, 544, 960, 192, 192, False, "gelu"),
           ("ds192 @544x960 b4 nores noact", 4, 544, 960, 192, 192, False, None), ("ds192 @544x960 b4 res noact", 4, 544, 960, 192, 192, True, None),
           ("ds192 @272x480 b4", 4, 272, 480, 192, 192, True, "gelu"), ("ds192 @136x240 b4", 4, 136, 240, 192, 192, True, "gelu"),
-          ("ds 128->128 @68x120 b4", 4, 68, 120, 128, 128, False, None)]
+          ("ds 128->128 @68x120 b4", 4, 68, 120, 128, 128, False, None),
+          ("lrp2 224->128 @68x120 b32", 32, 68, 120, 224, 128, False, "gelu"), ("lrp4 128->32 @68x120 b32", 32, 68, 120, 128, 32, False, None),
+          ("cc2 192->128 @68x120 b32", 32, 68, 120, 192, 128, False, "gelu")]
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
 torch.manual_seed(0)
 for name, B, H, W, Cin, N, res, act in SHAPES:
