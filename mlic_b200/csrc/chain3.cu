@@ -134,7 +134,7 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p, unsigned long
             // ring order = the order the MMA thread consumes it: GEMM 1 of the first tile, then per tile GEMM 1 of the NEXT tile and W3 of this one
             auto load_l1 = [&](int t, int c0, int c1) {
                 for (int cc = c0; cc < c1; ++cc) {
-                    mbar_wait<false>(&empty[s], ph ^ 1);
+                    mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = ring + (size_t)s * p.stage_bytes;
                     mbar_expect_tx(&full[s], (uint32_t)(C3_A_BYTES + p.N1 * 128));
                     tma_load_2d(st, &tm.a, &full[s], cc * 64, t * 128);
@@ -147,7 +147,7 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p, unsigned long
                 const int tn = t + (int)gridDim.x;
                 if (tn < p.ntiles) load_l1(tn, 0, split);
                 for (int k = 0; k < kch3; ++k) {
-                    mbar_wait<false>(&empty[s], ph ^ 1);
+                    mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], (uint32_t)w3_chunk);
                     tma_load_2d(ring + (size_t)s * p.stage_bytes, &tm.w3, &full[s], k * 64, 0);
                     if (++s == p.nstage) { s = 0; ph ^= 1; }
@@ -168,7 +168,7 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p, unsigned long
                 const uint32_t acc1 = tmem_base + C3_ACC1 + (MODE == C3_LOCAL ? (uint32_t)((itn & 1) * 64) : 0u);
                 for (int cc = c0; cc < c1; ++cc) {
                     const int nk = min(4, (p.K1 - cc * 64 + 15) >> 4);
-                    C3_TIMED(tw[0], mbar_wait<false>(&full[s], ph));
+                    C3_TIMED(tw[0], mbar_wait(&full[s], ph));
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(ring + (size_t)s * p.stage_bytes);
                     const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + (uint32_t)C3_A_BYTES);
@@ -183,7 +183,7 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p, unsigned long
             tcgen05_fence_after();
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
                 const uint32_t tp = (uint32_t)it & 1u;
-                C3_TIMED(tw[1], mbar_wait<false>(&h1_full, tp));
+                C3_TIMED(tw[1], mbar_wait(&h1_full, tp));
                 tcgen05_fence_after();
                 for (int k = 0; k < kch2; ++k) {
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(w2s + (size_t)k * w2_chunk));
@@ -194,10 +194,10 @@ chain3_kernel(const __grid_constant__ C3Maps tm, const C3Params p, unsigned long
                 tcgen05_commit(&acc2_full);
                 const bool more = t + (int)gridDim.x < p.ntiles;
                 if (more) issue_l1(it + 1, 0, split);
-                C3_TIMED(tw[2], mbar_wait<false>(&h2_full, tp));
+                C3_TIMED(tw[2], mbar_wait(&h2_full, tp));
                 tcgen05_fence_after();
                 for (int k = 0; k < kch3; ++k) {
-                    mbar_wait<false>(&full[s], ph);
+                    mbar_wait(&full[s], ph);
                     tcgen05_fence_after();
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + (size_t)s * p.stage_bytes));
 #pragma unroll
