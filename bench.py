@@ -402,8 +402,10 @@ def main():
                 "whole_step": ({"achieved": whole, "unit": "TFLOP/s (algorithmic FLOP of SURVEY.md 8d / step time, per GPU)",
                                 "frac_of_sustained": whole / pk["tf_sust"], "frac_of_burst": whole / pk["tf_burst"]} if whole else None),
                 # the contract's single-kernel line: the heaviest launch shape of the step
-                "kernel": "heaviest tcgen05 launch shape of the step (MLICPP_L forward: conv3_pair_kernel, the two-SM 3x3 192->768 sub-pixel conv "
-                          "of g_s stage 5, 2 launches per step)",
+                "kernel": ("heaviest tcgen05 launch shape of the step (MLICPP_L forward: conv3_pair_kernel, the two-SM 3x3 192->768 sub-pixel conv "
+                           "of g_s stage 5, 2 launches per step)" if cfg_name != "sd_decode" else
+                           "heaviest tcgen05 launch shape of the step (MLICPP_M_SMALL_DEC decoder walk: an HBM-bound depthwise-separable block of g_s at full "
+                           "resolution, quoted here against the tensor peak like the other configs; see DESIGN.md 4.2)"),
                 # against the BURST cuBLAS figure: inside the step this kernel runs above the sustained one (1361 TFLOP/s), so the stricter
                 # denominator is the honest one
                 "achieved": top_tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": top_tflops / pk["tf_burst"],
